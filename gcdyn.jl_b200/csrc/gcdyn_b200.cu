@@ -1,0 +1,787 @@
+// libgcdyn_b200 — host side of the C ABI declared in include/gcdyn_b200.h.
+// Handles, validation, packing, workspace management and kernel launches.  No C++ exception
+// leaves this file: every extern "C" entry point catches and converts to a GCDYN_E* code.
+#include "../../include/gcdyn_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace gcdyn;
+
+namespace {
+
+thread_local std::string g_tls_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct gcdyn_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // workspace (grow-only)
+    DevBuf params_blob, pack, table, out_tree, out_pset, status, probe;
+    PinBuf pin_in, pin_out;
+    // diagnostics of the last evaluation
+    int last_steps = 0, last_order = 0, last_launches = 0, last_P = 0;
+    PsetPack last_pack{};
+};
+
+struct gcdyn_forest {
+    int device = 0;
+    ForestView v{};
+    std::vector<void*> allocs;
+    int64_t n_chunks = 0;
+    int64_t* d_chunk_off = nullptr;
+    int64_t max_tree_items = 0;
+};
+
+struct gcdyn_dparams {
+    int device = 0;
+    void* blob = nullptr;
+    ParamsView v{};
+    double rate_max = 0.0;   // max over psets and types of λ_i + μ + γ_i, from the host copy
+};
+
+namespace {
+
+int fail(gcdyn_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    g_tls_error = msg;
+    return code;
+}
+
+#define CU_TRY(ctx, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? GCDYN_ENOMEM : GCDYN_ECUDA,       \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// parameter packing
+// ---------------------------------------------------------------------------------------------
+struct ParamLayout {
+    size_t n_doubles = 0;
+    size_t o_lambda = 0, o_xs = 0, o_xsh = 0, o_ys = 0, o_ysh = 0, o_ts = 0, o_mu = 0, o_delta = 0, o_rho = 0,
+           o_sigma = 0, o_gamma = 0;
+    size_t n_lambda = 0, n_gamma = 0;
+};
+
+int check_params(gcdyn_ctx* ctx, const gcdyn_params* pr) {
+    if (!pr) return fail(ctx, GCDYN_EINVAL, "params is NULL");
+    if (pr->n_psets <= 0) return fail(ctx, GCDYN_EINVAL, "n_psets must be positive");
+    if (pr->n_types <= 0) return fail(ctx, GCDYN_EINVAL, "n_types must be positive");
+    if (pr->n_types > GCDYN_MAX_TYPES) return fail(ctx, GCDYN_EUNSUPPORTED, "n_types exceeds GCDYN_MAX_TYPES");
+    if (pr->response < 0 || pr->response > 2) return fail(ctx, GCDYN_EINVAL, "unknown response kind");
+    if (pr->gamma_pset_stride != 0 && pr->gamma_pset_stride != pr->n_types * pr->n_types)
+        return fail(ctx, GCDYN_EINVAL, "gamma_pset_stride must be 0 or n_types*n_types");
+    if (!pr->mu || !pr->delta || !pr->rho || !pr->sigma || !pr->Gamma)
+        return fail(ctx, GCDYN_EINVAL, "mu, delta, rho, sigma and Gamma are required");
+    if (pr->response == GCDYN_LAMBDA_SIGMOID) {
+        if (!pr->xscale || !pr->xshift || !pr->yscale || !pr->yshift || !pr->type_space)
+            return fail(ctx, GCDYN_EINVAL, "sigmoid response needs xscale, xshift, yscale, yshift and type_space");
+    } else if (!pr->lambda) {
+        return fail(ctx, GCDYN_EINVAL, "lambda is required for table/constant response");
+    }
+    for (int p = 0; p < pr->n_psets; ++p) {   // types.jl:78-81
+        if (!(pr->rho[p] >= 0.0 && pr->rho[p] <= 1.0)) return fail(ctx, GCDYN_EINVAL, "rho must be between 0 and 1");
+        if (!(pr->sigma[p] >= 0.0 && pr->sigma[p] <= 1.0)) return fail(ctx, GCDYN_EINVAL, "sigma must be between 0 and 1");
+    }
+    return GCDYN_OK;
+}
+
+ParamLayout layout_of(const gcdyn_params* pr) {
+    ParamLayout L;
+    const size_t P = pr->n_psets, K = pr->n_types;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += n; return r; };
+    L.n_lambda = pr->response == 0 ? P * K : (pr->response == 1 ? P : 0);
+    L.o_lambda = take(L.n_lambda);
+    if (pr->response == 2) { L.o_xs = take(P); L.o_xsh = take(P); L.o_ys = take(P); L.o_ysh = take(P); L.o_ts = take(K); }
+    L.o_mu = take(P); L.o_delta = take(P); L.o_rho = take(P); L.o_sigma = take(P);
+    L.n_gamma = pr->gamma_pset_stride ? P * K * K : K * K;
+    L.o_gamma = take(L.n_gamma);
+    L.n_doubles = o;
+    return L;
+}
+
+void pack_host(const gcdyn_params* pr, const ParamLayout& L, double* dst) {
+    const size_t P = pr->n_psets, K = pr->n_types;
+    if (L.n_lambda) std::memcpy(dst + L.o_lambda, pr->lambda, L.n_lambda * 8);
+    if (pr->response == 2) {
+        std::memcpy(dst + L.o_xs, pr->xscale, P * 8);
+        std::memcpy(dst + L.o_xsh, pr->xshift, P * 8);
+        std::memcpy(dst + L.o_ys, pr->yscale, P * 8);
+        std::memcpy(dst + L.o_ysh, pr->yshift, P * 8);
+        std::memcpy(dst + L.o_ts, pr->type_space, K * 8);
+    }
+    std::memcpy(dst + L.o_mu, pr->mu, P * 8);
+    std::memcpy(dst + L.o_delta, pr->delta, P * 8);
+    std::memcpy(dst + L.o_rho, pr->rho, P * 8);
+    std::memcpy(dst + L.o_sigma, pr->sigma, P * 8);
+    std::memcpy(dst + L.o_gamma, pr->Gamma, L.n_gamma * 8);
+}
+
+ParamsView view_of(const gcdyn_params* pr, const ParamLayout& L, const double* d) {
+    ParamsView v{};
+    v.P = pr->n_psets; v.K = pr->n_types; v.response = pr->response; v.gamma_stride = pr->gamma_pset_stride;
+    v.lambda = L.n_lambda ? d + L.o_lambda : nullptr;
+    if (pr->response == 2) {
+        v.xscale = d + L.o_xs; v.xshift = d + L.o_xsh; v.yscale = d + L.o_ys; v.yshift = d + L.o_ysh;
+        v.type_space = d + L.o_ts;
+    }
+    v.mu = d + L.o_mu; v.delta = d + L.o_delta; v.rho = d + L.o_rho; v.sigma = d + L.o_sigma;
+    v.Gamma = d + L.o_gamma;
+    return v;
+}
+
+// max over psets and types of Λ_i = λ_i + μ + γ_i (host copy; picks the Taylor step count)
+double rate_max_of(const gcdyn_params* pr) {
+    const int P = pr->n_psets, K = pr->n_types;
+    double best = 0.0;
+    for (int p = 0; p < P; ++p) {
+        const double* G = pr->Gamma + (size_t)p * pr->gamma_pset_stride;
+        for (int i = 0; i < K; ++i) {
+            double lam;
+            if (pr->response == 0) lam = pr->lambda[(size_t)p * K + i];
+            else if (pr->response == 1) lam = pr->lambda[p];
+            else lam = pr->yscale[p] * (1.0 / (1.0 + std::exp(-(pr->xscale[p] * (pr->type_space[i] - pr->xshift[p]))))) + pr->yshift[p];
+            // off-diagonal mass also bounds the spectrum of δΓ; use |λ| + |μ| + 2|γ_i|
+            const double g = std::fabs(pr->delta[p] * G[i + (size_t)i * K]);
+            const double r = std::fabs(lam) + std::fabs(pr->mu[p]) + 2.0 * g;
+            if (r > best || r != r) best = r;
+        }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// step-count rule: h·rate_max ≤ target(M), from the numerical study in tests/algo_model.py
+// ---------------------------------------------------------------------------------------------
+constexpr int S_CAP = 8192;
+
+int normalise_order(int order) {
+    if (order == 0) return 16;
+    const int allowed[] = {8, 12, 16, 20, 24};
+    for (int a : allowed) if (order == a) return a;
+    return -1;
+}
+
+int auto_steps(double present_time, double rate_max, int M) {
+    double target;
+    switch (M) {
+        case 8: target = 0.055; break;
+        case 12: target = 0.20; break;
+        case 16: target = 0.36; break;
+        case 20: target = 0.50; break;
+        default: target = 0.62; break;
+    }
+    if (!(rate_max == rate_max) || !(present_time > 0.0)) return 4;
+    double s = std::ceil(present_time * rate_max / target);
+    if (s < 4.0) s = 4.0;
+    if (s > (double)S_CAP) s = (double)S_CAP;
+    return (int)s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace carving for PsetPack
+// ---------------------------------------------------------------------------------------------
+int carve_pack(gcdyn_ctx* ctx, int P, int K, PsetPack* pk) {
+    const size_t ntw = (size_t)K + (size_t)K * K + 2;
+    const size_t PK = (size_t)P * K;
+    const size_t n_doubles = PK * 6 + (size_t)P * ntw + (size_t)P;
+    const size_t bytes = n_doubles * 8 + (size_t)P * 4 + 64;
+    CU_TRY(ctx, ctx->pack.ensure(bytes));
+    double* d = ctx->pack.as<double>();
+    pk->ntw = (int)ntw;
+    pk->lam = d; d += PK;
+    pk->Lam = d; d += PK;
+    pk->logcond = d; d += PK;
+    pk->st_c = d; d += PK;
+    pk->st_A = d; d += PK;
+    pk->st_B = d; d += PK;
+    pk->nt = d; d += (size_t)P * ntw;
+    pk->perr = d; d += P;
+    pk->pstatus = reinterpret_cast<int*>(d);
+    return GCDYN_OK;
+}
+
+template <int M, int KPL>
+int launch_traj_inst(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, double T, int S, double* tab,
+                     cudaStream_t st) {
+    const size_t smem = ((size_t)pv.K * pv.K + 2 * (size_t)pv.K) * sizeof(double);
+    if (smem > 48 * 1024)
+        CU_TRY(ctx, cudaFuncSetAttribute(traj_kernel<M, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    traj_kernel<M, KPL><<<pv.P, 32, smem, st>>>(pv, pk, T, S, tab);
+    CU_TRY(ctx, cudaGetLastError());
+    return GCDYN_OK;
+}
+
+template <int M>
+int launch_traj_m(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, double T, int S, double* tab,
+                  cudaStream_t st) {
+    if (pv.K <= 32) return launch_traj_inst<M, 1>(ctx, pv, pk, T, S, tab, st);
+    if (pv.K <= 64) return launch_traj_inst<M, 2>(ctx, pv, pk, T, S, tab, st);
+    return launch_traj_inst<M, 4>(ctx, pv, pk, T, S, tab, st);
+}
+
+int launch_traj(gcdyn_ctx* ctx, int M, const ParamsView& pv, const PsetPack& pk, double T, int S, double* tab,
+                cudaStream_t st) {
+    switch (M) {
+        case 8: return launch_traj_m<8>(ctx, pv, pk, T, S, tab, st);
+        case 12: return launch_traj_m<12>(ctx, pv, pk, T, S, tab, st);
+        case 16: return launch_traj_m<16>(ctx, pv, pk, T, S, tab, st);
+        case 20: return launch_traj_m<20>(ctx, pv, pk, T, S, tab, st);
+        case 24: return launch_traj_m<24>(ctx, pv, pk, T, S, tab, st);
+    }
+    return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
+}
+
+int launch_sweep(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& pk, const double* tab, double T,
+                 int S, int P, double* out_tree, int32_t* status, cudaStream_t st) {
+    dim3 grid((unsigned)f->n_chunks, (unsigned)P);
+    switch (M) {
+        case 8: sweep_kernel<8><<<grid, 256, 0, st>>>(f->v, pk, tab, f->d_chunk_off, T, S, out_tree, status); break;
+        case 12: sweep_kernel<12><<<grid, 256, 0, st>>>(f->v, pk, tab, f->d_chunk_off, T, S, out_tree, status); break;
+        case 16: sweep_kernel<16><<<grid, 256, 0, st>>>(f->v, pk, tab, f->d_chunk_off, T, S, out_tree, status); break;
+        case 20: sweep_kernel<20><<<grid, 256, 0, st>>>(f->v, pk, tab, f->d_chunk_off, T, S, out_tree, status); break;
+        case 24: sweep_kernel<24><<<grid, 256, 0, st>>>(f->v, pk, tab, f->d_chunk_off, T, S, out_tree, status); break;
+        default: return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
+    }
+    CU_TRY(ctx, cudaGetLastError());
+    return GCDYN_OK;
+}
+
+// Enqueue one evaluation on `st`.  All pointers are device pointers; d_out_tree/d_status may be null.
+int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, double T, int method, int M, int S,
+                 bool run_prep, double* d_out_pset, double* d_out_tree, int32_t* d_status, cudaStream_t st,
+                 PsetPack* pk_out) {
+    const int P = pv.P, K = pv.K;
+    if (P > 65535) return fail(ctx, GCDYN_EUNSUPPORTED, "more than 65535 parameter sets per call");
+    PsetPack pk{};
+    int rc = carve_pack(ctx, P, K, &pk);
+    if (rc) return rc;
+    const int64_t Tn = f->v.n_trees;
+    if (!d_out_tree) {
+        CU_TRY(ctx, ctx->out_tree.ensure((size_t)P * Tn * 8));
+        d_out_tree = ctx->out_tree.as<double>();
+    }
+    int launches = 0;
+    if (run_prep) {
+        prep_kernel<<<P, 128, 0, st>>>(pv, pk, method);
+        CU_TRY(ctx, cudaGetLastError());
+        ++launches;
+    }
+    if (method == GCDYN_METHOD_ODE) {
+        const size_t tab_bytes = (size_t)P * S * (M + 2) * K * 8;
+        CU_TRY(ctx, ctx->table.ensure(tab_bytes));
+        rc = launch_traj(ctx, M, pv, pk, T, S, ctx->table.as<double>(), st);
+        if (rc) return rc;
+        ++launches;
+        rc = launch_sweep(ctx, M, f, pk, ctx->table.as<double>(), T, S, P, d_out_tree, d_status, st);
+        if (rc) return rc;
+        ++launches;
+    } else {
+        if (method == GCDYN_METHOD_STADLER) {
+            stadler_cond_kernel<<<P, 128, 0, st>>>(pv, pk, T);
+            CU_TRY(ctx, cudaGetLastError());
+            ++launches;
+        }
+        dim3 grid((unsigned)f->n_chunks, (unsigned)P);
+        alt_kernel<<<grid, 256, 0, st>>>(f->v, pv, pk, f->d_chunk_off, T, method, d_out_tree, d_status);
+        CU_TRY(ctx, cudaGetLastError());
+        ++launches;
+    }
+    reduce_kernel<<<P, 256, 0, st>>>(d_out_tree, Tn, d_out_pset);
+    CU_TRY(ctx, cudaGetLastError());
+    ++launches;
+    ctx->last_steps = method == GCDYN_METHOD_ODE ? S : 0;
+    ctx->last_order = method == GCDYN_METHOD_ODE ? M : 0;
+    ctx->last_launches = launches;
+    ctx->last_P = P;
+    ctx->last_pack = pk;
+    if (pk_out) *pk_out = pk;
+    return GCDYN_OK;
+}
+
+template <class T>
+int upload(gcdyn_ctx* ctx, gcdyn_forest* f, const T* src, size_t n, const T** dst) {
+    void* d = nullptr;
+    CU_TRY(ctx, cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    f->allocs.push_back(d);
+    if (n) CU_TRY(ctx, cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = reinterpret_cast<const T*>(d);
+    return GCDYN_OK;
+}
+
+void free_forest(gcdyn_forest* f) {
+    if (!f) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(f->device);
+    for (void* p : f->allocs) cudaFree(p);
+    cudaSetDevice(prev);
+    delete f;
+}
+
+int forest_create_impl(gcdyn_ctx* ctx, const gcdyn_forest_desc* d, gcdyn_forest** out) {
+    if (!ctx || !d || !out) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    *out = nullptr;
+    const int64_t T = d->n_trees, N = d->n_nodes;
+    const int K = d->n_types;
+    if (T < 0 || N < 0) return fail(ctx, GCDYN_EINVAL, "negative sizes");
+    if (K <= 0) return fail(ctx, GCDYN_EINVAL, "n_types must be positive");
+    if (K > GCDYN_MAX_TYPES) return fail(ctx, GCDYN_EUNSUPPORTED, "n_types exceeds GCDYN_MAX_TYPES");
+    if (!d->tree_off || !d->root_type_idx || !d->root_time) return fail(ctx, GCDYN_EINVAL, "tree_off/root arrays are required");
+    if (N > 0 && (!d->event || !d->type_idx || !d->btype_idx || !d->t_start || !d->t_end))
+        return fail(ctx, GCDYN_EINVAL, "per-node arrays are required");
+    if (d->tree_off[0] != 0 || d->tree_off[T] != N) return fail(ctx, GCDYN_EINVAL, "tree_off must start at 0 and end at n_nodes");
+    for (int64_t t = 0; t < T; ++t)
+        if (d->tree_off[t + 1] < d->tree_off[t]) return fail(ctx, GCDYN_EINVAL, "tree_off must be non-decreasing");
+    for (int64_t i = 0; i < N; ++i) {
+        if (d->event[i] > 6) return fail(ctx, GCDYN_EINVAL, "event code out of range");
+        if (d->btype_idx[i] < 0 || d->btype_idx[i] >= K) return fail(ctx, GCDYN_EINVAL, "btype_idx out of range");
+        if (d->type_idx[i] < -1 || d->type_idx[i] >= K) return fail(ctx, GCDYN_EINVAL, "type_idx out of range");
+        if (d->event[i] == EV_TC && d->type_idx[i] < 0) return fail(ctx, GCDYN_EINVAL, "type_change to a type outside the type space");
+        if (!(d->t_start[i] == d->t_start[i]) || !(d->t_end[i] == d->t_end[i])) return fail(ctx, GCDYN_EINVAL, "NaN node time");
+    }
+    for (int64_t t = 0; t < T; ++t)
+        if (d->root_type_idx[t] < -1 || d->root_type_idx[t] >= K) return fail(ctx, GCDYN_EINVAL, "root_type_idx out of range");
+    if (d->parent && d->child_off && d->child_idx) {   // structural cross-check of the CSR the flattener built
+        for (int64_t t = 0; t < T; ++t) {
+            const int64_t lo = d->tree_off[t], n = d->tree_off[t + 1] - lo;
+            for (int64_t i = 0; i < n; ++i) {
+                const int32_t par = d->parent[lo + i];
+                if (par < -1 || par >= n || (par >= 0 && par <= i)) return fail(ctx, GCDYN_EINVAL, "parent is not a later post-order position");
+                for (int64_t c = d->child_off[lo + i]; c < d->child_off[lo + i + 1]; ++c) {
+                    const int32_t ch = d->child_idx[c];
+                    if (ch < 0 || ch >= i || d->parent[lo + ch] != (int32_t)i) return fail(ctx, GCDYN_EINVAL, "child_idx inconsistent with parent");
+                }
+            }
+        }
+    }
+
+    // ---- lookup items of the regrouped ODE sum
+    std::vector<int64_t> item_off(T + 1, 0);
+    std::vector<double> it_time;
+    std::vector<int32_t> it_tw, it_aux, n_death(T, 0), n_surv(T, 0);
+    std::vector<uint8_t> live_all, loop_all;
+    it_time.reserve(N + T); it_tw.reserve(N + T); it_aux.reserve(N + T);
+    auto push = [&](double tm, int type, int w, int aux) {
+        it_time.push_back(tm);
+        it_tw.push_back((int32_t)((uint32_t)type | ((uint32_t)(uint8_t)(int8_t)w << 24)));
+        it_aux.push_back(aux);
+    };
+    int64_t max_items = 0;
+    for (int64_t t = 0; t < T; ++t) {
+        for (int64_t i = d->tree_off[t]; i < d->tree_off[t + 1]; ++i) {
+            if (d->live && !d->live[i]) continue;
+            const int ev = d->event[i], x = d->btype_idx[i], y = d->type_idx[i];
+            const double te = d->t_end[i];
+            if (ev == EV_BIRTH) {
+                if (y == x || y < 0) push(te, x, +1, x);
+                else { push(te, x, -1, x); push(te, y, +2, -1); }
+            } else if (ev == EV_TC) {
+                push(te, x, -1, K + x * K + y);
+                push(te, y, +1, -1);
+            } else if (ev == EV_SDEATH) {
+                push(te, x, -1, -1);
+                ++n_death[t];
+            } else if (ev == EV_SSURV) {
+                ++n_surv[t];
+            }
+        }
+        const int rt = d->root_type_idx[t] < 0 ? 0 : d->root_type_idx[t];
+        push(d->root_time[t], rt, +1, -1);
+        item_off[t + 1] = (int64_t)it_time.size();
+        max_items = std::max(max_items, item_off[t + 1] - item_off[t]);
+    }
+    // ---- chunks of trees with roughly equal work
+    const int64_t n_items = (int64_t)it_time.size();
+    const int64_t target = 4096;
+    std::vector<int64_t> chunk_off{0};
+    int64_t acc = 0;
+    for (int64_t t = 0; t < T; ++t) {
+        const int64_t wgt = std::max<int64_t>(item_off[t + 1] - item_off[t], d->tree_off[t + 1] - d->tree_off[t]);
+        acc += wgt;
+        if (acc >= target) { chunk_off.push_back(t + 1); acc = 0; }
+    }
+    if (chunk_off.back() != T) chunk_off.push_back(T);
+    if (chunk_off.size() == 1) chunk_off.push_back(0);   // empty forest: one empty chunk
+    if ((int64_t)chunk_off.size() - 1 > 2147483647LL) return fail(ctx, GCDYN_EUNSUPPORTED, "too many chunks");
+
+    gcdyn_forest* f = new (std::nothrow) gcdyn_forest();
+    if (!f) return fail(ctx, GCDYN_ENOMEM, "host allocation failed");
+    f->device = ctx->device;
+    f->max_tree_items = max_items;
+    ForestView& v = f->v;
+    v.n_trees = T; v.n_nodes = N; v.n_items = n_items; v.K = K;
+    if (!d->live) live_all.assign((size_t)std::max<int64_t>(N, 1), 1);
+    if (!d->self_loop) loop_all.assign((size_t)std::max<int64_t>(T, 1), 0);
+    int rc = GCDYN_OK;
+#define UP(field, src, n) if (!rc) rc = upload(ctx, f, src, (size_t)(n), &v.field)
+    UP(tree_off, d->tree_off, T + 1);
+    UP(event, d->event, N);
+    UP(type_idx, d->type_idx, N);
+    UP(btype_idx, d->btype_idx, N);
+    UP(t_start, d->t_start, N);
+    UP(t_end, d->t_end, N);
+    UP(live, d->live ? d->live : live_all.data(), N);
+    UP(root_type, d->root_type_idx, T);
+    UP(root_time, d->root_time, T);
+    UP(self_loop, d->self_loop ? d->self_loop : loop_all.data(), T);
+    UP(item_off, item_off.data(), T + 1);
+    UP(it_time, it_time.data(), n_items);
+    UP(it_tw, it_tw.data(), n_items);
+    UP(it_aux, it_aux.data(), n_items);
+    UP(n_death, n_death.data(), T);
+    UP(n_surv, n_surv.data(), T);
+#undef UP
+    const int64_t* dco = nullptr;
+    if (!rc) rc = upload(ctx, f, chunk_off.data(), chunk_off.size(), &dco);
+    if (rc) { free_forest(f); return rc; }
+    f->d_chunk_off = const_cast<int64_t*>(dco);
+    f->n_chunks = (int64_t)chunk_off.size() - 1;
+    *out = f;
+    return GCDYN_OK;
+}
+
+int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, double T, int method,
+               const gcdyn_opts* opts, double* out_pset, double* out_tree_pset, int32_t* status) {
+    if (!ctx || !f || !out_pset) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    int rc = check_params(ctx, pr);
+    if (rc) return rc;
+    if (method < 0 || method > 3) return fail(ctx, GCDYN_EINVAL, "unknown method");
+    if (pr->n_types != f->v.K) return fail(ctx, GCDYN_EINVAL, "params and forest disagree on n_types");
+    if (f->device != ctx->device) return fail(ctx, GCDYN_EINVAL, "forest lives on another device");
+    if (method != GCDYN_METHOD_NAIVE && !(T > 0.0) ) return fail(ctx, GCDYN_EINVAL, "present_time must be positive");
+    gcdyn_opts o{};
+    if (opts) o = *opts;
+    const int M = normalise_order(o.order);
+    if (M < 0) return fail(ctx, GCDYN_EINVAL, "order must be 0, 8, 12, 16, 20 or 24");
+    if (o.steps < 0 || o.steps > S_CAP) return fail(ctx, GCDYN_EINVAL, "steps out of range");
+    const double tol = o.tol > 0.0 ? o.tol : 1e-11;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int P = pr->n_psets;
+    const int64_t Tn = f->v.n_trees;
+
+    // parameters: pack into pinned staging, one H2D copy
+    const ParamLayout L = layout_of(pr);
+    CU_TRY(ctx, ctx->pin_in.ensure(L.n_doubles * 8));
+    pack_host(pr, L, reinterpret_cast<double*>(ctx->pin_in.p));
+    CU_TRY(ctx, ctx->params_blob.ensure(L.n_doubles * 8));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->params_blob.p, ctx->pin_in.p, L.n_doubles * 8, cudaMemcpyHostToDevice, st));
+    const ParamsView pv = view_of(pr, L, ctx->params_blob.as<double>());
+
+    int S = o.steps > 0 ? o.steps : auto_steps(T, rate_max_of(pr), M);
+    const bool want_rows = out_tree_pset || status;
+    CU_TRY(ctx, ctx->out_pset.ensure((size_t)P * 8));
+    if (status) CU_TRY(ctx, ctx->status.ensure((size_t)P * Tn * 4));
+    // pinned result staging: out_pset[P] | perr[P] | pstatus[P]
+    CU_TRY(ctx, ctx->pin_out.ensure((size_t)P * (8 + 8 + 4) + 64));
+    double* h_out = reinterpret_cast<double*>(ctx->pin_out.p);
+    double* h_err = h_out + P;
+    int* h_pst = reinterpret_cast<int*>(h_err + P);
+
+    int total_launches = 0;
+    bool first = true;
+    std::vector<char> unconverged(P, 0);
+    for (int attempt = 0;; ++attempt) {
+        PsetPack pk{};
+        rc = enqueue_eval(ctx, f, pv, T, method, M, S, first, ctx->out_pset.as<double>(), nullptr,
+                          status ? ctx->status.as<int32_t>() : nullptr, st, &pk);
+        if (rc) return rc;
+        total_launches += ctx->last_launches;
+        first = false;
+        CU_TRY(ctx, cudaMemcpyAsync(h_out, ctx->out_pset.p, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaMemcpyAsync(h_err, pk.perr, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaMemcpyAsync(h_pst, pk.pstatus, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+        if (method != GCDYN_METHOD_ODE) break;
+        bool need = false;
+        for (int p = 0; p < P; ++p) {
+            unconverged[p] = !(h_err[p] <= tol);
+            // a pset whose p left [0,1] may simply be under-resolved: refine it too
+            if (unconverged[p] || (h_pst[p] & ST_SOLVER)) need = true;
+        }
+        if (!need || (o.flags & GCDYN_FLAG_NO_REFINE) || o.steps > 0 || S >= S_CAP || attempt >= 6) break;
+        S = std::min<int>(S_CAP, S + S / 2 + 1);
+        // pstatus is sticky across attempts: clear it before re-running the trajectory
+        CU_TRY(ctx, cudaMemsetAsync(pk.pstatus, 0, (size_t)P * 4, st));
+    }
+    ctx->last_launches = total_launches;
+    std::memcpy(out_pset, h_out, (size_t)P * 8);
+    if (want_rows) {
+        if (out_tree_pset)
+            CU_TRY(ctx, cudaMemcpyAsync(out_tree_pset, ctx->out_tree.p, (size_t)P * Tn * 8, cudaMemcpyDeviceToHost, st));
+        if (status)
+            CU_TRY(ctx, cudaMemcpyAsync(status, ctx->status.p, (size_t)P * Tn * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+    }
+    if (method == GCDYN_METHOD_ODE) {
+        // psets still above tolerance at the cap count as a solver failure: density evaluates to zero
+        for (int p = 0; p < P; ++p) {
+            if (!unconverged[p] || (h_pst[p] & ST_SOLVER)) continue;
+            out_pset[p] = -INFINITY;
+            for (int64_t t = 0; t < Tn; ++t) {
+                if (out_tree_pset) out_tree_pset[(size_t)p * Tn + t] = -INFINITY;
+                if (status) status[(size_t)p * Tn + t] |= ST_SOLVER;
+            }
+        }
+    }
+    return GCDYN_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// extern "C" entry points
+// =================================================================================================
+#define GUARD_BEGIN try {
+#define GUARD_END(ctx)                                                                        \
+    } catch (const std::bad_alloc&) { return fail(ctx, GCDYN_ENOMEM, "host allocation failed"); } \
+    catch (const std::exception& e) { return fail(ctx, GCDYN_EINVAL, e.what()); }             \
+    catch (...) { return fail(ctx, GCDYN_EINVAL, "unknown C++ exception"); }
+
+extern "C" {
+
+int gcdyn_version(void) { return GCDYN_B200_VERSION; }
+
+int gcdyn_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* gcdyn_last_error(const gcdyn_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    return g_tls_error.c_str();
+}
+
+int gcdyn_ctx_create(int device, gcdyn_ctx** out) {
+    gcdyn_ctx* none = nullptr;
+    GUARD_BEGIN
+    if (!out) return fail(none, GCDYN_EINVAL, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(none, GCDYN_ENODEVICE, "no CUDA device available (libgcdyn_b200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(none, GCDYN_EINVAL, "device index out of range");
+    CU_TRY(none, cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    CU_TRY(none, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(none, GCDYN_ENODEVICE, std::string("device is ") + prop.name + " (sm_" + std::to_string(prop.major) +
+                                               std::to_string(prop.minor) + "); this library is built for sm_100a only");
+    gcdyn_ctx* ctx = new gcdyn_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return fail(none, GCDYN_ECUDA, cudaGetErrorString(e)); }
+    *out = ctx;
+    return GCDYN_OK;
+    GUARD_END(none)
+}
+
+void gcdyn_ctx_destroy(gcdyn_ctx* ctx) {
+    if (!ctx) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    ctx->params_blob.release(); ctx->pack.release(); ctx->table.release(); ctx->out_tree.release();
+    ctx->out_pset.release(); ctx->status.release(); ctx->probe.release();
+    ctx->pin_in.release(); ctx->pin_out.release();
+    cudaSetDevice(prev);
+    delete ctx;
+}
+
+int gcdyn_forest_create(gcdyn_ctx* ctx, const gcdyn_forest_desc* desc, gcdyn_forest** out) {
+    GUARD_BEGIN
+    if (!ctx) return fail(ctx, GCDYN_EINVAL, "ctx is NULL");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    return forest_create_impl(ctx, desc, out);
+    GUARD_END(ctx)
+}
+
+void gcdyn_forest_destroy(gcdyn_forest* forest) { free_forest(forest); }
+
+int gcdyn_forest_info(const gcdyn_forest* f, int64_t* n_trees, int64_t* n_nodes, int64_t* n_items, int32_t* n_types) {
+    if (!f) return fail(nullptr, GCDYN_EINVAL, "forest is NULL");
+    if (n_trees) *n_trees = f->v.n_trees;
+    if (n_nodes) *n_nodes = f->v.n_nodes;
+    if (n_items) *n_items = f->v.n_items;
+    if (n_types) *n_types = f->v.K;
+    return GCDYN_OK;
+}
+
+int gcdyn_forest_event_counts(gcdyn_ctx* ctx, const gcdyn_forest* f, int64_t* out) {
+    GUARD_BEGIN
+    if (!ctx || !f || !out) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t T = f->v.n_trees;
+    if (T == 0) return GCDYN_OK;
+    CU_TRY(ctx, ctx->status.ensure((size_t)T * 7 * 8));
+    int64_t* d = ctx->status.as<int64_t>();
+    const int wpb = 8;
+    event_count_kernel<<<(unsigned)((T + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(f->v, d);
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaMemcpyAsync(out, d, (size_t)T * 7 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+int gcdyn_loglik_batch(gcdyn_ctx* ctx, const gcdyn_forest* forest, const gcdyn_params* params, double present_time,
+                       int method, const gcdyn_opts* opts, double* out_pset, double* out_tree_pset, int32_t* status) {
+    GUARD_BEGIN
+    return batch_impl(ctx, forest, params, present_time, method, opts, out_pset, out_tree_pset, status);
+    GUARD_END(ctx)
+}
+
+int gcdyn_params_upload(gcdyn_ctx* ctx, const gcdyn_params* pr, gcdyn_dparams** out) {
+    GUARD_BEGIN
+    if (!ctx || !out) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    *out = nullptr;
+    int rc = check_params(ctx, pr);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const ParamLayout L = layout_of(pr);
+    std::vector<double> host(L.n_doubles);
+    pack_host(pr, L, host.data());
+    gcdyn_dparams* dp = new gcdyn_dparams();
+    dp->device = ctx->device;
+    cudaError_t e = cudaMalloc(&dp->blob, L.n_doubles * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(dp->blob, host.data(), L.n_doubles * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (dp->blob) cudaFree(dp->blob);
+        delete dp;
+        return fail(ctx, GCDYN_ECUDA, cudaGetErrorString(e));
+    }
+    dp->v = view_of(pr, L, reinterpret_cast<const double*>(dp->blob));
+    dp->rate_max = rate_max_of(pr);
+    *out = dp;
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+void gcdyn_dparams_destroy(gcdyn_dparams* dp) {
+    if (!dp) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(dp->device);
+    if (dp->blob) cudaFree(dp->blob);
+    cudaSetDevice(prev);
+    delete dp;
+}
+
+int gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_dparams* dp, double present_time,
+                                int method, const gcdyn_opts* opts, double* d_out_pset, double* d_out_tree_pset,
+                                int32_t* d_status, void* stream) {
+    GUARD_BEGIN
+    if (!ctx || !f || !dp || !d_out_pset) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    if (method < 0 || method > 3) return fail(ctx, GCDYN_EINVAL, "unknown method");
+    if (dp->v.K != f->v.K) return fail(ctx, GCDYN_EINVAL, "params and forest disagree on n_types");
+    if (f->device != ctx->device || dp->device != ctx->device) return fail(ctx, GCDYN_EINVAL, "handles live on another device");
+    if (method != GCDYN_METHOD_NAIVE && !(present_time > 0.0)) return fail(ctx, GCDYN_EINVAL, "present_time must be positive");
+    gcdyn_opts o{};
+    if (opts) o = *opts;
+    const int M = normalise_order(o.order);
+    if (M < 0) return fail(ctx, GCDYN_EINVAL, "order must be 0, 8, 12, 16, 20 or 24");
+    if (o.steps < 0 || o.steps > S_CAP) return fail(ctx, GCDYN_EINVAL, "steps out of range");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const int S = o.steps > 0 ? o.steps : auto_steps(present_time, dp->rate_max, M);
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
+    return enqueue_eval(ctx, f, dp->v, present_time, method, M, S, true, d_out_pset, d_out_tree_pset, d_status, st, nullptr);
+    GUARD_END(ctx)
+}
+
+int gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_launches, double* err_indicator,
+                    int32_t n_psets) {
+    GUARD_BEGIN
+    if (!ctx) return fail(ctx, GCDYN_EINVAL, "ctx is NULL");
+    if (steps) *steps = ctx->last_steps;
+    if (order) *order = ctx->last_order;
+    if (n_launches) *n_launches = ctx->last_launches;
+    if (err_indicator && n_psets > 0) {
+        if (n_psets > ctx->last_P || !ctx->last_pack.perr) return fail(ctx, GCDYN_EINVAL, "no evaluation with that many psets to report on");
+        CU_TRY(ctx, cudaSetDevice(ctx->device));
+        CU_TRY(ctx, cudaDeviceSynchronize());
+        CU_TRY(ctx, cudaMemcpy(err_indicator, ctx->last_pack.perr, (size_t)n_psets * 8, cudaMemcpyDeviceToHost));
+    }
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+int gcdyn_probe_fp64_peak(gcdyn_ctx* ctx, double* tflops) {
+    GUARD_BEGIN
+    if (!ctx || !tflops) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, ctx->probe.ensure(64));
+    const int iters = 1 << 15;
+    const int blocks = ctx->sm_count * 8;
+    cudaEvent_t a, b;
+    CU_TRY(ctx, cudaEventCreate(&a));
+    CU_TRY(ctx, cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a, ctx->stream);
+        dfma_probe_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->probe.as<double>(), iters, 1.0 + rep);
+        cudaEventRecord(b, ctx->stream);
+        cudaError_t e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) { cudaEventDestroy(a); cudaEventDestroy(b); return fail(ctx, GCDYN_ECUDA, cudaGetErrorString(e)); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        const double flops = 2.0 * 8.0 * (double)iters * 256.0 * (double)blocks;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+}  // extern "C"

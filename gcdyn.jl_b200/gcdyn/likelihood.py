@@ -1,0 +1,384 @@
+"""Likelihood entry points: flatten on the host, evaluate on the B200 through the C ABI.
+
+Replaces `StatsAPI.loglikelihood(model, tree(s), present_time; …)` (mbp.jl:110-259) and the
+alternates of extra_likelihoods.jl:10-151.  This module is the Python stand-in for the Julia
+`ccall` wrapper: it only packs arrays and calls `libgcdyn_b200.so`
+(`include/gcdyn_b200.h`).  There is NO CPU fallback — if the library or a CUDA device is
+missing every call raises `GcdynError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import warnings
+
+import numpy as np
+
+from .types import (AbstractBranchingProcess, ArgumentError, ConstantBranchingProcess,
+                    DiscreteBranchingProcess, DomainError, SigmoidalBranchingProcess, TreeNode)
+from .flatten import FlatForest, flatten
+
+__all__ = ["loglikelihood", "naive_loglikelihood", "stadler_appx_loglikelihood",
+           "stadler_appx_unconditioned_loglikelihood", "Forest", "Context", "pack_params",
+           "GcdynError", "library_path"]
+
+METHOD_CODE = {"ode": 0, "naive": 1, "stadler": 2, "stadler_unconditioned": 3}
+STATUS_SELF_LOOP, STATUS_SOLVER, STATUS_DOMAIN = 1, 2, 4
+FLAG_NO_REFINE, FLAG_TOTALS_VIA_MOMENTS = 1, 2
+
+_ERRNAMES = {-1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "EUNSUPPORTED", -5: "ENODEVICE",
+             -6: "ENOTCONVERGED"}
+
+
+class GcdynError(RuntimeError):
+    """The native library reported an error (or could not be loaded)."""
+
+    def __init__(self, msg, code=None):
+        super().__init__(msg)
+        self.code = code
+
+
+# ----------------------------------------------------------------------------- ctypes mirror of the header
+
+_p_f64 = C.POINTER(C.c_double)
+_p_i32 = C.POINTER(C.c_int32)
+_p_i64 = C.POINTER(C.c_int64)
+_p_u8 = C.POINTER(C.c_uint8)
+
+
+class ForestDesc(C.Structure):
+    _fields_ = [("n_trees", C.c_int64), ("n_nodes", C.c_int64), ("n_types", C.c_int32), ("reserved", C.c_int32),
+                ("tree_off", _p_i64), ("event", _p_u8), ("type_idx", _p_i32), ("btype_idx", _p_i32),
+                ("t_start", _p_f64), ("t_end", _p_f64), ("parent", _p_i32), ("child_off", _p_i64),
+                ("child_idx", _p_i32), ("live", _p_u8), ("root_type_idx", _p_i32), ("root_time", _p_f64),
+                ("self_loop", _p_u8)]
+
+
+class Params(C.Structure):
+    _fields_ = [("n_psets", C.c_int32), ("n_types", C.c_int32), ("response", C.c_int32),
+                ("gamma_pset_stride", C.c_int32),
+                ("lambda_", _p_f64), ("xscale", _p_f64), ("xshift", _p_f64), ("yscale", _p_f64), ("yshift", _p_f64),
+                ("type_space", _p_f64), ("mu", _p_f64), ("delta", _p_f64), ("rho", _p_f64), ("sigma", _p_f64),
+                ("Gamma", _p_f64)]
+
+
+class Opts(C.Structure):
+    _fields_ = [("steps", C.c_int32), ("order", C.c_int32), ("tol", C.c_double), ("flags", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+_LIB = None
+
+
+def library_path():
+    """Where the in-tree build puts the shared library (override: $GCDYN_B200_LIB)."""
+    env = os.environ.get("GCDYN_B200_LIB")
+    if env:
+        return env
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libgcdyn_b200.so")
+
+
+def _lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise GcdynError(f"{path} not found: build it with `python __graft_entry__.py build` "
+                         "(there is no CPU fallback for the likelihood path)")
+    try:
+        lib = C.CDLL(path)
+    except OSError as e:
+        raise GcdynError(f"cannot load {path}: {e} (there is no CPU fallback)") from e
+    vp = C.c_void_p
+    sig = {
+        "gcdyn_version": (C.c_int, []),
+        "gcdyn_device_count": (C.c_int, []),
+        "gcdyn_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "gcdyn_ctx_destroy": (None, [vp]),
+        "gcdyn_last_error": (C.c_char_p, [vp]),
+        "gcdyn_forest_create": (C.c_int, [vp, C.POINTER(ForestDesc), C.POINTER(vp)]),
+        "gcdyn_forest_destroy": (None, [vp]),
+        "gcdyn_forest_info": (C.c_int, [vp, _p_i64, _p_i64, _p_i64, _p_i32]),
+        "gcdyn_forest_event_counts": (C.c_int, [vp, vp, _p_i64]),
+        "gcdyn_loglik_batch": (C.c_int, [vp, vp, C.POINTER(Params), C.c_double, C.c_int, C.POINTER(Opts),
+                                         _p_f64, _p_f64, _p_i32]),
+        "gcdyn_params_upload": (C.c_int, [vp, C.POINTER(Params), C.POINTER(vp)]),
+        "gcdyn_dparams_destroy": (None, [vp]),
+        "gcdyn_loglik_batch_resident": (C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.POINTER(Opts),
+                                                  vp, vp, vp, vp]),
+        "gcdyn_last_diag": (C.c_int, [vp, _p_i32, _p_i32, _p_i32, _p_f64, C.c_int32]),
+        "gcdyn_probe_fp64_peak": (C.c_int, [vp, _p_f64]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)       # AttributeError here = header and library out of sync
+        fn.restype, fn.argtypes = res, args
+    _LIB = lib
+    return lib
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ) if a is not None else typ()
+
+
+def _check(code, ctx_handle=None):
+    if code == 0:
+        return
+    msg = _lib().gcdyn_last_error(ctx_handle)
+    msg = msg.decode("utf-8", "replace") if msg else ""
+    raise GcdynError(f"libgcdyn_b200: {_ERRNAMES.get(code, code)}: {msg}", code)
+
+
+# ----------------------------------------------------------------------------- handles
+
+class Context:
+    """`gcdyn_ctx`: one CUDA device, its stream and workspace."""
+
+    _default = {}
+
+    def __init__(self, device=0):
+        lib = _lib()
+        h = C.c_void_p()
+        _check(lib.gcdyn_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    @classmethod
+    def default(cls, device=None):
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("GCDYN_B200_USE_LOCAL_RANK") else 0
+        if device not in cls._default:
+            cls._default[device] = cls(device)
+        return cls._default[device]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().gcdyn_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_diag(self, n_psets=0):
+        s, o, nl = C.c_int32(), C.c_int32(), C.c_int32()
+        err = np.zeros(max(n_psets, 1))
+        _check(_lib().gcdyn_last_diag(self._h, C.byref(s), C.byref(o), C.byref(nl),
+                                      _ptr(err, _p_f64) if n_psets else _p_f64(), int(n_psets)), self._h)
+        return dict(steps=s.value, order=o.value, n_launches=nl.value, err_indicator=err[:n_psets])
+
+    def probe_fp64_peak(self):
+        v = C.c_double()
+        _check(_lib().gcdyn_probe_fp64_peak(self._h, C.byref(v)), self._h)
+        return v.value
+
+
+class Forest:
+    """A flattened forest resident in HBM (`gcdyn_forest`).  Flatten + upload once per dataset,
+    then evaluate many parameter sets against it."""
+
+    def __init__(self, trees, type_space, present_time=None, method="ode", ctx=None, *,
+                 discrete_lambda=False):
+        self.ctx = ctx or Context.default()
+        self.method = method
+        self.present_time = present_time
+        self.flat = trees if isinstance(trees, FlatForest) else flatten(
+            trees, type_space, present_time, method, discrete_lambda=discrete_lambda)
+        f = self.flat
+        d = ForestDesc(
+            n_trees=f.n_trees, n_nodes=f.n_nodes, n_types=f.n_types, reserved=0,
+            tree_off=_ptr(f.tree_off, _p_i64), event=_ptr(f.event, _p_u8), type_idx=_ptr(f.type_idx, _p_i32),
+            btype_idx=_ptr(f.btype_idx, _p_i32), t_start=_ptr(f.t_start, _p_f64), t_end=_ptr(f.t_end, _p_f64),
+            parent=_ptr(f.parent, _p_i32), child_off=_ptr(f.child_off, _p_i64), child_idx=_ptr(f.child_idx, _p_i32),
+            live=_ptr(f.live, _p_u8), root_type_idx=_ptr(f.root_type_idx, _p_i32),
+            root_time=_ptr(f.root_time, _p_f64), self_loop=_ptr(f.self_loop, _p_u8))
+        h = C.c_void_p()
+        _check(_lib().gcdyn_forest_create(self.ctx._h, C.byref(d), C.byref(h)), self.ctx._h)
+        self._h = h
+
+    @property
+    def n_trees(self):
+        return self.flat.n_trees
+
+    def info(self):
+        a, b, c, k = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        _check(_lib().gcdyn_forest_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(k)))
+        return dict(n_trees=a.value, n_nodes=b.value, n_items=c.value, n_types=k.value)
+
+    def event_counts(self):
+        """Per-tree event histogram [T,7], computed by a device kernel."""
+        out = np.zeros((self.flat.n_trees, 7), dtype=np.int64)
+        _check(_lib().gcdyn_forest_event_counts(self.ctx._h, self._h, _ptr(out, _p_i64)), self.ctx._h)
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().gcdyn_forest_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PackedParams:
+    """Host arrays of a parameter batch + the ctypes struct pointing at them."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def struct(self):
+        return Params(
+            n_psets=self.n_psets, n_types=self.n_types, response=self.response,
+            gamma_pset_stride=self.gamma_pset_stride,
+            lambda_=_ptr(self.lam, _p_f64), xscale=_ptr(self.xscale, _p_f64), xshift=_ptr(self.xshift, _p_f64),
+            yscale=_ptr(self.yscale, _p_f64), yshift=_ptr(self.yshift, _p_f64),
+            type_space=_ptr(self.type_space, _p_f64), mu=_ptr(self.mu, _p_f64), delta=_ptr(self.delta, _p_f64),
+            rho=_ptr(self.rho, _p_f64), sigma=_ptr(self.sigma, _p_f64), Gamma=_ptr(self.Gamma, _p_f64))
+
+
+def pack_params(models, response="table"):
+    """Canonical arrays for a batch of models: λ per type, μ, δ, ρ, σ per pset,
+    Γ column-major (shared when every model holds the same matrix).
+
+    response = "table" evaluates λ on the host exactly as the reference does (mbp.jl:27-43);
+    "sigmoid" ships the four response parameters and lets the device evaluate them
+    (all models must then be `SigmoidalBranchingProcess`)."""
+    if isinstance(models, AbstractBranchingProcess):
+        models = [models]
+    models = list(models)
+    if not models:
+        raise ArgumentError("need at least one model")
+    ts = models[0].type_space
+    K = len(ts)
+    for m in models[1:]:
+        if len(m.type_space) != K or not np.array_equal(m.type_space, ts):
+            raise ArgumentError("all models of a batch must share one type_space")
+    P = len(models)
+    f = lambda name: np.ascontiguousarray([getattr(m, name) for m in models], dtype=np.float64)
+    mu, delta, rho, sigma = f("μ"), f("δ"), f("ρ"), f("σ")
+    G0 = models[0].Γ
+    shared = all(m.Γ is G0 or np.array_equal(m.Γ, G0) for m in models[1:])
+    if shared:
+        Gamma = np.ascontiguousarray(G0.ravel(order="F"))
+        stride = 0
+    else:
+        Gamma = np.ascontiguousarray(np.concatenate([m.Γ.ravel(order="F") for m in models]))
+        stride = K * K
+    lam = xs = xsh = ys = ysh = None
+    if response == "sigmoid":
+        if not all(isinstance(m, SigmoidalBranchingProcess) for m in models):
+            raise ArgumentError("response='sigmoid' needs SigmoidalBranchingProcess models")
+        xs, xsh, ys, ysh = f("λ_xscale"), f("λ_xshift"), f("λ_yscale"), f("λ_yshift")
+        code = 2
+    elif all(isinstance(m, ConstantBranchingProcess) for m in models):
+        lam = f("λ")
+        code = 1
+    else:
+        lam = np.ascontiguousarray(np.stack([m.birth_rates() for m in models]), dtype=np.float64)
+        code = 0
+    return PackedParams(n_psets=P, n_types=K, response=code, gamma_pset_stride=stride, lam=lam,
+                        xscale=xs, xshift=xsh, yscale=ys, yshift=ysh,
+                        type_space=np.ascontiguousarray(ts, dtype=np.float64),
+                        mu=mu, delta=delta, rho=rho, sigma=sigma, Gamma=Gamma)
+
+
+# ----------------------------------------------------------------------------- evaluation
+
+def _opts(reltol=None, abstol=None, steps=0, order=0, flags=0):
+    tol = 0.0
+    for t in (reltol, abstol):
+        if t is not None and 0 < t < 1e-11:   # we are always at least as tight as requested
+            tol = t if tol == 0.0 else min(tol, t)
+    return Opts(steps=int(steps), order=int(order), tol=float(tol), flags=int(flags), reserved=0)
+
+
+def evaluate(forest: Forest, params: PackedParams, present_time, method="ode", *, per_tree=False,
+             want_status=True, reltol=None, abstol=None, steps=0, order=0, flags=0):
+    """One `gcdyn_loglik_batch` call.  Returns (out_pset[P], out_tree_pset[P,T] | None, status[P,T] | None)."""
+    lib = _lib()
+    P, T = params.n_psets, forest.flat.n_trees
+    if params.n_types != forest.flat.n_types:
+        raise ArgumentError("model type_space and forest disagree on the number of types")
+    out = np.empty(P, dtype=np.float64)
+    tp = np.empty((P, T), dtype=np.float64) if per_tree else None
+    st = np.zeros((P, T), dtype=np.int32) if (want_status or per_tree) else None
+    ps = params.struct()
+    op = _opts(reltol, abstol, steps, order, flags)
+    _check(lib.gcdyn_loglik_batch(forest.ctx._h, forest._h, C.byref(ps),
+                                  float(present_time if present_time is not None else 0.0),
+                                  METHOD_CODE[method], C.byref(op),
+                                  _ptr(out, _p_f64), _ptr(tp, _p_f64), _ptr(st, _p_i32)), forest.ctx._h)
+    return out, tp, st
+
+
+def _report(status, method):
+    """Re-issue the reference's `@warn`s / exceptions from the status words."""
+    if status is None:
+        return
+    bits = int(np.bitwise_or.reduce(status, axis=None)) if status.size else 0
+    if bits & STATUS_DOMAIN:
+        raise DomainError("log or sqrt of a negative number while evaluating the likelihood "
+                          "(Julia raises DomainError here)")
+    if bits & STATUS_SELF_LOOP:
+        warnings.warn("Self-loop encountered at a type change event in the tree. Density will evaluate to zero.")
+    if bits & STATUS_SOLVER:
+        warnings.warn("Extinction probabilities left [0, 1] or became non-finite while integrating. "
+                      "Density will evaluate to zero.")
+
+
+def _run(method, model, trees, present_time, **kw):
+    single = isinstance(model, AbstractBranchingProcess)
+    models = [model] if single else list(model)
+    params = pack_params(models)
+    if isinstance(trees, Forest):
+        forest, own = trees, False
+    else:
+        forest = Forest(trees, models[0].type_space, present_time, method,
+                        discrete_lambda=isinstance(models[0], DiscreteBranchingProcess))
+        own = True
+    try:
+        out, _, st = evaluate(forest, params, present_time, method, **kw)
+    finally:
+        if own:
+            forest.close()
+    _report(st, method)
+    return float(out[0]) if single else out
+
+
+def loglikelihood(model, trees, present_time, *, reltol=1e-3, abstol=1e-3, maxiters=1e5, steps=0, order=0):
+    """`loglikelihood(model, tree, present_time; reltol, abstol, maxiters)` and the
+    `trees::Vector{TreeNode}` method (mbp.jl:110-117, 250-259).
+
+    `model` may also be a list of models — the batched entry — returning one value per model.
+    `trees` may be a `TreeNode`, a list of them, or a `Forest` already resident on the GPU.
+    The result is the CONVERGED solution (error indicator ≤ 1e-13), which is at least as accurate
+    as any `reltol`/`abstol` the reference accepts; `maxiters` is accepted and ignored."""
+    return _run("ode", model, trees, present_time, reltol=reltol, abstol=abstol, steps=steps, order=order)
+
+
+def _alt(method, model, tree, present_time):
+    if isinstance(tree, (list, tuple)):
+        raise TypeError(f"{method}: the reference has no method for a vector of trees; sum over trees "
+                        "or pass a Forest")
+    return _run(method, model, tree, present_time)
+
+
+def naive_loglikelihood(model, tree):
+    """`gcdyn.naive_loglikelihood(model, tree)` (extra_likelihoods.jl:10-34)."""
+    return _alt("naive", model, tree, None)
+
+
+def stadler_appx_loglikelihood(model, tree, present_time):
+    """`gcdyn.stadler_appx_loglikelihood(model, tree, present_time)` (extra_likelihoods.jl:45-102)."""
+    return _alt("stadler", model, tree, present_time)
+
+
+def stadler_appx_unconditioned_loglikelihood(model, tree, present_time):
+    """`gcdyn.stadler_appx_unconditioned_loglikelihood(model, tree, present_time)` (extra_likelihoods.jl:115-151)."""
+    return _alt("stadler_unconditioned", model, tree, present_time)

@@ -1,0 +1,79 @@
+"""Tree sharding for multi-GPU evaluation.
+
+Trees are independent (`loglikelihood(model, trees, T)` is a plain sum, mbp.jl:258), so a forest is
+split by trees across ranks — balanced by node count, because tree sizes are heavy-tailed — the small
+parameter block is replicated, every rank produces its partial `[P]` sums, and ONE all-reduce of `[P]`
+doubles combines them.  No other data-path collective exists.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .flatten import FlatForest
+
+__all__ = ["partition_trees", "subset_flat", "shard_flat", "allreduce_sum"]
+
+
+def partition_trees(sizes, n_shards):
+    """Longest-processing-time assignment of trees to shards; returns a list of sorted index arrays.
+    Deterministic: ties broken by tree index, so every rank computes the same partition."""
+    sizes = np.asarray(sizes, dtype=np.int64)
+    order = np.lexsort((np.arange(len(sizes)), -sizes))
+    load = np.zeros(n_shards, dtype=np.int64)
+    bins = [[] for _ in range(n_shards)]
+    for t in order:
+        r = int(np.argmin(load))          # first minimum
+        bins[r].append(int(t))
+        load[r] += sizes[t] + 1           # +1: the per-tree root item
+    return [np.array(sorted(b), dtype=np.int64) for b in bins]
+
+
+def subset_flat(flat: FlatForest, tree_ids) -> FlatForest:
+    """The sub-forest made of `tree_ids` (in the given order); positions inside trees are unchanged."""
+    tree_ids = np.asarray(tree_ids, dtype=np.int64)
+    lo, hi = flat.tree_off[tree_ids], flat.tree_off[tree_ids + 1]
+    n = hi - lo
+    tree_off = np.zeros(len(tree_ids) + 1, dtype=np.int64)
+    np.cumsum(n, out=tree_off[1:])
+    if len(tree_ids):
+        node_sel = np.concatenate([np.arange(a, b) for a, b in zip(lo, hi)]) if n.sum() else np.zeros(0, dtype=np.int64)
+    else:
+        node_sel = np.zeros(0, dtype=np.int64)
+    c_lo, c_hi = flat.child_off[node_sel], flat.child_off[node_sel + 1]
+    cn = c_hi - c_lo
+    child_off = np.zeros(len(node_sel) + 1, dtype=np.int64)
+    np.cumsum(cn, out=child_off[1:])
+    child_sel = (np.concatenate([np.arange(a, b) for a, b in zip(c_lo, c_hi)])
+                 if cn.sum() else np.zeros(0, dtype=np.int64))
+    take = lambda a: np.ascontiguousarray(a[node_sel])
+    return FlatForest(
+        n_types=flat.n_types, tree_off=tree_off, event=take(flat.event), type_idx=take(flat.type_idx),
+        btype_idx=take(flat.btype_idx), t_start=take(flat.t_start), t_end=take(flat.t_end),
+        parent=take(flat.parent), child_off=child_off, child_idx=np.ascontiguousarray(flat.child_idx[child_sel]),
+        live=take(flat.live), root_type_idx=np.ascontiguousarray(flat.root_type_idx[tree_ids]),
+        root_time=np.ascontiguousarray(flat.root_time[tree_ids]),
+        self_loop=np.ascontiguousarray(flat.self_loop[tree_ids]),
+        event_counts=None if flat.event_counts is None else np.ascontiguousarray(flat.event_counts[tree_ids]))
+
+
+def shard_flat(flat: FlatForest, n_shards):
+    """Split a flattened forest into `n_shards` balanced sub-forests."""
+    sizes = np.diff(flat.tree_off)
+    return [subset_flat(flat, ids) for ids in partition_trees(sizes, n_shards)]
+
+
+def allreduce_sum(tensor_or_array, group=None):
+    """Sum partial per-pset log-likelihoods across ranks with one all-reduce (NCCL on GPUs, gloo on
+    CPU).  Accepts a torch tensor (reduced in place, returned) or a numpy array (returned as numpy)."""
+    import torch
+    import torch.distributed as dist
+    if isinstance(tensor_or_array, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(tensor_or_array, dtype=np.float64).copy())
+        if dist.is_initialized() and dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.cpu().numpy()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tensor_or_array, op=dist.ReduceOp.SUM, group=group)
+    return tensor_or_array

@@ -1,0 +1,178 @@
+/* gcdyn_b200.h — C ABI of libgcdyn_b200.so, the B200 (sm_100a) implementation of
+ * gcdyn.jl's multitype branching-process tree log-likelihood.
+ *
+ * The reference (thanasibakis/gcdyn.jl) has no FFI boundary: the path is ordinary Julia
+ * multiple dispatch.  These entry points are what a Julia `ccall` binding for that path
+ * needs; each one names the reference interface it replaces (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the Julia-side stubs.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns GCDYN_OK (0) or a negative
+ *     GCDYN_E* code and never throws, exits or longjmps across the boundary;
+ *   - caller owns every input/output buffer; inputs are copied before the call returns
+ *     and never retained; opaque handles own device memory;
+ *   - the library calls cudaSetDevice itself, installs no signal handlers, and a
+ *     gcdyn_ctx may be used from any host thread (one call at a time per ctx);
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     GCDYN_ENODEVICE.
+ *   - "density evaluates to zero" cases of the reference (`@warn` + `return -Inf`,
+ *     src/multitype_branching_process.jl:154-158,181-185,211-214,238-241) come back as
+ *     -Inf values with a non-zero status word, not as error codes.
+ */
+#ifndef GCDYN_B200_H
+#define GCDYN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCDYN_B200_VERSION 100  /* major*100 + minor */
+
+/* return codes */
+#define GCDYN_OK            0
+#define GCDYN_EINVAL       (-1)  /* bad argument / malformed forest or parameters          */
+#define GCDYN_ECUDA        (-2)  /* a CUDA runtime call failed (see gcdyn_last_error)       */
+#define GCDYN_ENOMEM       (-3)  /* host or device allocation failed                        */
+#define GCDYN_EUNSUPPORTED (-4)  /* e.g. n_types above GCDYN_MAX_TYPES                      */
+#define GCDYN_ENODEVICE    (-5)  /* no usable CUDA device                                   */
+#define GCDYN_ENOTCONVERGED (-6) /* Taylor error indicator above tolerance at the step cap  */
+
+#define GCDYN_MAX_TYPES 128
+
+/* which likelihood: replaces the four reference entry points
+ *   ODE            StatsAPI.loglikelihood(model, tree(s), present_time; reltol, abstol, maxiters)
+ *                  src/multitype_branching_process.jl:110-117,250-257
+ *   NAIVE          gcdyn.naive_loglikelihood(model, tree)                         src/extra_likelihoods.jl:10
+ *   STADLER        gcdyn.stadler_appx_loglikelihood(model, tree, present_time)    src/extra_likelihoods.jl:45
+ *   STADLER_UNCOND gcdyn.stadler_appx_unconditioned_loglikelihood(...)            src/extra_likelihoods.jl:115 */
+#define GCDYN_METHOD_ODE            0
+#define GCDYN_METHOD_NAIVE          1
+#define GCDYN_METHOD_STADLER        2
+#define GCDYN_METHOD_STADLER_UNCOND 3
+
+/* how birth rates are given: replaces λ(model, type), src/multitype_branching_process.jl:27-43 */
+#define GCDYN_LAMBDA_TABLE    0  /* lambda[P*K], pset-major (DiscreteBranchingProcess, or pre-evaluated) */
+#define GCDYN_LAMBDA_CONSTANT 1  /* lambda[P]                (ConstantBranchingProcess)                   */
+#define GCDYN_LAMBDA_SIGMOID  2  /* xscale,xshift,yscale,yshift[P] + type_space[K], evaluated on device
+                                    (SigmoidalBranchingProcess; sigmoid() at :4-7)                          */
+
+/* per-(tree,pset) status words */
+#define GCDYN_STATUS_OK         0
+#define GCDYN_STATUS_SELF_LOOP  1  /* type_change with type == up.type        -> -Inf (mbp.jl:181-185)      */
+#define GCDYN_STATUS_SOLVER     2  /* p left [0,1] or went non-finite          -> -Inf (mbp.jl:154,211,238)  */
+#define GCDYN_STATUS_DOMAIN     4  /* log/sqrt of a negative number: Julia would throw DomainError; value NaN */
+
+typedef struct gcdyn_ctx gcdyn_ctx;          /* one CUDA device + stream + workspace            */
+typedef struct gcdyn_forest gcdyn_forest;    /* a flattened forest resident in HBM              */
+typedef struct gcdyn_dparams gcdyn_dparams;  /* a batch of parameter sets resident in HBM       */
+
+/* Flattened forest = what the host-side flattener produces from `TreeNode` trees
+ * (src/types.jl:23-37): per tree the nodes of PostOrderTraversal(tree.children[1])
+ * (src/treenode.jl:159-175, mbp.jl:166); the root is per-tree metadata.  Event codes are
+ * 0-based positions in EVENTS (src/types.jl:6).  Type indices are 0-based positions in
+ * model.type_space (type_space_index, mbp.jl:16-18). */
+typedef struct {
+    int64_t n_trees;
+    int64_t n_nodes;
+    int32_t n_types;
+    int32_t reserved;
+    const int64_t* tree_off;       /* [n_trees+1] CSR over nodes                                          */
+    const uint8_t* event;          /* [n_nodes]                                                            */
+    const int32_t* type_idx;       /* [n_nodes] node's own type (new type of a type_change); may be -1     */
+    const int32_t* btype_idx;      /* [n_nodes] type of the branch above the node = idx(up.type)           */
+    const double*  t_start;        /* [n_nodes] up.time                                                    */
+    const double*  t_end;          /* [n_nodes] time                                                       */
+    const int32_t* parent;         /* [n_nodes] position of `up` inside the tree, -1 if `up` is the root   */
+    const int64_t* child_off;      /* [n_nodes+1] CSR over children                                        */
+    const int32_t* child_idx;      /* [child_off[n_nodes]] positions inside the tree, `children` order     */
+    const uint8_t* live;           /* [n_nodes] or NULL (= all 1): 0 marks subtrees the ODE likelihood
+                                      computes but never uses (3rd+ child of a birth, mbp.jl:173-179)      */
+    const int32_t* root_type_idx;  /* [n_trees] idx(tree.type)                                             */
+    const double*  root_time;      /* [n_trees] tree.time                                                  */
+    const uint8_t* self_loop;      /* [n_trees] or NULL: 1 = the reference returns -Inf for this tree      */
+} gcdyn_forest_desc;
+
+/* A batch of P parameter sets = P model objects (src/types.jl:65-207) in canonical form. */
+typedef struct {
+    int32_t n_psets;
+    int32_t n_types;
+    int32_t response;              /* GCDYN_LAMBDA_*                                                       */
+    int32_t gamma_pset_stride;     /* 0: one Γ shared by all psets; n_types*n_types: one Γ per pset        */
+    const double* lambda;          /* TABLE: [P*K]; CONSTANT: [P]; SIGMOID: NULL                           */
+    const double* xscale;          /* SIGMOID: [P] each, else NULL                                         */
+    const double* xshift;
+    const double* yscale;
+    const double* yshift;
+    const double* type_space;      /* [K] (SIGMOID only, else may be NULL)                                 */
+    const double* mu;              /* [P]                                                                  */
+    const double* delta;           /* [P]                                                                  */
+    const double* rho;             /* [P]                                                                  */
+    const double* sigma;           /* [P]                                                                  */
+    const double* Gamma;           /* K×K COLUMN-major (Julia Matrix{Float64}), 1 or P matrices            */
+} gcdyn_params;
+
+/* Replaces the solver keywords reltol/abstol/maxiters (mbp.jl:114-116).  The kernels use a
+ * fixed-order Taylor-series integrator on a uniform grid; all zero = defaults. */
+typedef struct {
+    int32_t steps;   /* S, Taylor steps on [0, present_time]; 0 = choose from the fastest rate         */
+    int32_t order;   /* M, Taylor order (8, 12, 16, 20 or 24); 0 = 16                                  */
+    double  tol;     /* accepted size of the last Taylor terms (error indicator); 0 = 1e-11, which
+                        keeps the relative error of a log-likelihood below ~1e-12        */
+    int32_t flags;   /* GCDYN_FLAG_*                                                                    */
+    int32_t reserved;
+} gcdyn_opts;
+
+#define GCDYN_FLAG_NO_REFINE 1  /* do not re-run with more steps when the indicator exceeds tol */
+#define GCDYN_FLAG_TOTALS_VIA_MOMENTS 2  /* out_pset from forest moments (no per-tree pass)      */
+
+int  gcdyn_version(void);
+int  gcdyn_device_count(void);
+
+int  gcdyn_ctx_create(int device, gcdyn_ctx** out);
+void gcdyn_ctx_destroy(gcdyn_ctx* ctx);
+/* Last error message of this ctx (or of the calling thread when ctx == NULL). Never NULL. */
+const char* gcdyn_last_error(const gcdyn_ctx* ctx);
+
+/* Validate, copy to the device and index a flattened forest.  Upload once per dataset and
+ * reuse across many likelihood evaluations. */
+int  gcdyn_forest_create(gcdyn_ctx* ctx, const gcdyn_forest_desc* desc, gcdyn_forest** out);
+void gcdyn_forest_destroy(gcdyn_forest* forest);
+int  gcdyn_forest_info(const gcdyn_forest* forest, int64_t* n_trees, int64_t* n_nodes,
+                       int64_t* n_items, int32_t* n_types);
+/* Per-tree histogram of event codes, computed on the device: out[n_trees*7], tree-major. */
+int  gcdyn_forest_event_counts(gcdyn_ctx* ctx, const gcdyn_forest* forest, int64_t* out);
+
+/* Batched likelihood, HOST buffers (the call a Julia `ccall` makes).
+ *   out_pset      [P]        Σ over trees, per parameter set  (= loglikelihood(model, trees, T), mbp.jl:250-259)
+ *   out_tree_pset [P*T] or NULL   per tree, pset-major: out_tree_pset[p*T + t]  (a Julia T×P Matrix)
+ *   status        [P*T] or NULL   GCDYN_STATUS_* bits, same layout
+ * present_time is ignored by GCDYN_METHOD_NAIVE. */
+int  gcdyn_loglik_batch(gcdyn_ctx* ctx, const gcdyn_forest* forest, const gcdyn_params* params,
+                        double present_time, int method, const gcdyn_opts* opts,
+                        double* out_pset, double* out_tree_pset, int32_t* status);
+
+/* Device-resident variant: parameters uploaded once, outputs are DEVICE pointers, work is
+ * enqueued on `stream` (a cudaStream_t passed as void*; NULL = the ctx's own stream) and the
+ * call returns without synchronising.  opts->steps == 0 uses the step count derived from the
+ * rates at upload time; no refinement is attempted. */
+int  gcdyn_params_upload(gcdyn_ctx* ctx, const gcdyn_params* params, gcdyn_dparams** out);
+void gcdyn_dparams_destroy(gcdyn_dparams* dparams);
+int  gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* forest, const gcdyn_dparams* dparams,
+                                 double present_time, int method, const gcdyn_opts* opts,
+                                 double* d_out_pset, double* d_out_tree_pset, int32_t* d_status,
+                                 void* stream);
+/* Diagnostics of the last ODE evaluation on this ctx (host copies; synchronises the stream):
+ * steps and order used, number of kernels launched, and per-pset error indicators [P] (may be NULL). */
+int  gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_launches,
+                     double* err_indicator, int32_t n_psets);
+
+/* FP64 FMA peak probe (roofline denominator; not part of the likelihood path): runs a
+ * register-resident DFMA loop on every SM and returns achieved TFLOP/s. */
+int  gcdyn_probe_fp64_peak(gcdyn_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCDYN_B200_H */

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "gcdyn.jl_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build the native pieces in-tree if they are missing or stale (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as ge
+    ge.build_cuda()
+    ge.build_oracle()
+    yield
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    import gcdyn
+    return gcdyn.Context.default()

@@ -1,0 +1,59 @@
+"""The C-ABI library loads, exports every symbol include/gcdyn_b200.h declares, and fails loudly
+(no CPU fallback) when there is no CUDA device.  No compute happens here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import gcdyn
+from gcdyn import likelihood
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "gcdyn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gcdyn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared()
+    assert len(names) >= 15
+    lib = ctypes.CDLL(likelihood.library_path())
+    for n in names:
+        assert hasattr(lib, n), n
+    assert likelihood._lib().gcdyn_version() == 100
+    assert likelihood._lib().gcdyn_last_error(None) is not None
+
+
+def test_ctypes_structs_match_header_layout():
+    # field order/size of the structs the Python binding mirrors (a Julia `struct` would mirror the same)
+    assert ctypes.sizeof(likelihood.ForestDesc) == 8 + 8 + 4 + 4 + 13 * 8
+    assert ctypes.sizeof(likelihood.Params) == 4 * 4 + 11 * 8
+    assert ctypes.sizeof(likelihood.Opts) == 4 + 4 + 8 + 4 + 4
+
+
+def test_no_cpu_fallback_without_a_device():
+    lib = likelihood._lib()
+    if lib.gcdyn_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(gcdyn.GcdynError) as e:
+        gcdyn.Context(0)
+    assert e.value.code == -5 and "no CPU fallback" in str(e.value)
+    model = gcdyn.ConstantBranchingProcess(1.8, 1.0, 1.0, 1, 0, [1, 2])
+    r = gcdyn.TreeNode("root", 0, 1)
+    gcdyn.attach(r, gcdyn.TreeNode("sampled_survival", 2.0, 1))
+    with pytest.raises(gcdyn.GcdynError):
+        gcdyn.loglikelihood(model, r, 2.0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gcdyn.jl_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                text = open(os.path.join(d, f), encoding="utf-8").read()
+                assert not re.search(r"(import|from)\s+(oracle|refcpu|algo_model)\b", text), f
+                assert "librefcpu" not in text, f

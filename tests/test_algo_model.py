@@ -1,0 +1,53 @@
+"""CPU check of the numerical DESIGN of the GPU path: tests/algo_model.py restates the kernels' algorithm
+(Taylor-series trajectory → per-cell polynomials of F → lookup items → per-tree sums, and the moment
+contraction) in numpy and is compared with the oracle.  This validates the order/step rule without a GPU;
+the CUDA kernels themselves are compared with the oracle in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import algo_model as am
+import gcdyn
+from helpers import load_golden, rel
+
+
+@pytest.mark.parametrize("name,key", [("g1_config1", "ode_closed"), ("g2_config2", "ode_branch"),
+                                      ("g5_batched_discrete", "ode_shared"), ("g4_no_extinction", "stadler")])
+def test_taylor_lookup_model_matches_oracle(name, key):
+    flat, params, T, exp, par = load_golden(name)
+    items = am.build_items(flat, T)
+    want = exp[key]
+    for p in range(want.shape[0]):
+        S = am.auto_steps(T, par["lam"][p], par["mu"][p], par["delta"][p], par["Gamma"][p], 16)
+        out, err = am.loglik_per_tree(flat, items, par["lam"][p], par["mu"][p], par["delta"][p], par["Gamma"][p],
+                                      par["rho"][p], par["sigma"][p], T, S=S, M=16)
+        assert err <= 1e-11          # the library's default acceptance threshold for the indicator
+        assert rel(out, want[p]) <= 1e-10
+
+
+def test_moment_contraction_equals_item_sweep():
+    flat, params, T, exp, par = load_golden("g2_config2")
+    items = am.build_items(flat, T)
+    S, M, K = 24, 16, flat.n_types
+    Mom = am.moments(items, T, S, M, K)
+    Fc, pT, err, bad = am.taylor_table(par["lam"][0], par["mu"][0], par["delta"][0], par["Gamma"][0],
+                                       par["rho"][0], par["sigma"][0], T, S, M)
+    per_tree, _ = am.loglik_per_tree(flat, items, par["lam"][0], par["mu"][0], par["delta"][0], par["Gamma"][0],
+                                     par["rho"][0], par["sigma"][0], T, S, M)
+    with np.errstate(divide="ignore"):
+        loglam = np.log(par["lam"][0])
+        logG = np.log(par["delta"][0] * par["Gamma"][0]).reshape(-1)
+    node_terms = (am._xlogy_count(items["nb"].sum(0), loglam).sum() + am._xlogy_count(items["ntc"].sum(0), logG).sum()
+                  + items["nd"].sum() * (np.log(par["mu"][0]) + np.log(par["sigma"][0]))
+                  + items["ns"].sum() * np.log(par["rho"][0]))
+    total = (Fc * Mom).sum() + node_terms - np.log1p(-pT)[flat.root_type_idx].sum()
+    assert abs(total - per_tree.sum()) <= 1e-12 * abs(total)
+    assert abs(total - exp["ode_branch"].sum()) <= 1e-10 * abs(total)
+
+
+def test_item_count_is_below_node_count():
+    """Regrouping by node time needs no lookup for survivors: items ≈ births + deaths + 2·type changes + 1."""
+    flat, _, T, exp, _ = load_golden("g2_config2")
+    items = am.build_items(flat, T)
+    c = exp["event_counts"].sum(axis=0)
+    assert len(items["time"]) == c[1] + c[2] + 2 * c[4] + flat.n_trees
+    assert len(items["time"]) < flat.n_nodes

@@ -1,0 +1,212 @@
+"""GPU parity tests (run on the B200 with `-m gpu`): the CUDA path, called through the C ABI, against
+the committed golden fixtures and against the oracle on seeded inputs.
+
+Tolerances: the north star asks for ≤ 1e-8 relative on the summed log-likelihood; we hold the sum to
+1e-10 and every single tree to 1e-9 relative (the golden values themselves carry ≈1e-13 from the
+oracle's DOP853 tolerance).  Integer outputs (event counts, statuses) are compared exactly.
+"""
+import math
+import warnings
+
+import numpy as np
+import pytest
+
+import gcdyn
+from gcdyn.likelihood import evaluate, pack_params
+from helpers import load_golden, rel
+
+pytestmark = pytest.mark.gpu
+
+SUM_RTOL = 1e-10
+TREE_RTOL = 1e-9
+
+
+def _check(forest, params, T, method, want, **kw):
+    out, tp, st = evaluate(forest, params, T, method, per_tree=True, **kw)
+    want = np.asarray(want)
+    P = want.shape[0]
+    assert rel(tp[:P], want) <= TREE_RTOL, (method, rel(tp[:P], want))
+    assert rel(out[:P], want.sum(axis=1)) <= SUM_RTOL
+    # out_pset must be the sum of the rows it was reduced from
+    assert rel(out, tp.sum(axis=1)) <= 1e-13
+    assert not st.any()
+    return out, tp
+
+
+@pytest.mark.parametrize("name,keys", [
+    ("g1_config1", ("ode_branch", "ode_shared", "ode_closed")),
+    ("g2_config2", ("ode_branch", "ode_shared")),
+    ("g3_fully_observed", ("ode_branch", "naive")),       # runtests.jl:27 tightened: ρ=σ=1 ⇒ ode == naive
+    ("g4_no_extinction", ("ode_branch", "ode_closed", "stadler")),   # runtests.jl:37 tightened: γ=0 ⇒ ode == stadler
+    ("g5_batched_discrete", ("ode_branch", "ode_shared")),
+])
+def test_ode_against_golden(ctx, name, keys):
+    flat, params, T, exp, _ = load_golden(name)
+    forest = gcdyn.Forest(flat, None, T, ctx=ctx)
+    for k in keys:
+        _check(forest, params, T, "ode", exp[k])
+
+
+@pytest.mark.parametrize("name", ["g1_config1", "g2_config2", "g3_fully_observed", "g4_no_extinction",
+                                  "g5_batched_discrete"])
+def test_alternates_against_golden(ctx, name):
+    flat, params, T, exp, _ = load_golden(name)
+    forest = gcdyn.Forest(flat, None, T, ctx=ctx)
+    for method, key in (("naive", "naive"), ("stadler", "stadler"), ("stadler_unconditioned", "stadler_uncond")):
+        if key in exp:
+            _check(forest, params, T, method, exp[key])
+
+
+def test_event_counts_bit_exact(ctx):
+    for name in ("g1_config1", "g2_config2", "g5_batched_discrete"):
+        flat, params, T, exp, _ = load_golden(name)
+        forest = gcdyn.Forest(flat, None, T, ctx=ctx)
+        assert np.array_equal(forest.event_counts(), exp["event_counts"])
+        info = forest.info()
+        assert info["n_nodes"] == flat.n_nodes and info["n_trees"] == flat.n_trees
+
+
+@pytest.mark.parametrize("order", [8, 12, 16, 20, 24])
+def test_every_taylor_order_converges(ctx, order):
+    flat, params, T, exp, _ = load_golden("g2_config2")
+    forest = gcdyn.Forest(flat, None, T, ctx=ctx)
+    _check(forest, params, T, "ode", exp["ode_branch"], order=order)
+    d = ctx.last_diag(params.n_psets)
+    assert d["order"] == order and d["steps"] >= 4 and np.all(d["err_indicator"] <= 1e-11)
+
+
+def test_steps_refinement_and_explicit_steps(ctx):
+    flat, params, T, exp, _ = load_golden("g2_config2")
+    forest = gcdyn.Forest(flat, None, T, ctx=ctx)
+    # far too few steps, no refinement allowed: the pset is reported as a solver failure (-Inf), not a wrong number
+    out, tp, st = evaluate(forest, params, T, "ode", per_tree=True, steps=2, order=8)
+    assert np.all(np.isneginf(out)) and np.all(st & 2)
+    # explicit, sufficient steps reproduce the converged value
+    _check(forest, params, T, "ode", exp["ode_branch"], steps=64, order=16)
+
+
+def test_public_api_matches_oracle_on_simulated_trees(ctx):
+    """The reference-style call `loglikelihood(model, trees, present_time)` on freshly simulated trees."""
+    import oracle
+    rng = np.random.default_rng(11)
+    ts = np.linspace(-1.5, 1.5, 6)
+    model = gcdyn.SigmoidalBranchingProcess(1.2, 0.1, 2.2, 0.4, 0.9, 0.8, 0.7, 0.25, ts)
+    trees = gcdyn.rand_tree(model, 3.0, ts[2], 15, rng=rng)
+    want = oracle.loglikelihood_shared(model, trees, 3.0)
+    got = gcdyn.loglikelihood(model, trees, 3.0)
+    assert abs(got - want) <= SUM_RTOL * abs(want)
+    # single tree method, and reltol/abstol/maxiters keywords are accepted
+    one = gcdyn.loglikelihood(model, trees[0], 3.0, reltol=1e-6, abstol=1e-6, maxiters=1e4)
+    assert abs(one - oracle.loglikelihood_shared(model, trees[0], 3.0)) <= TREE_RTOL * abs(one)
+    # batched entry: a list of models gives one value per model
+    models = [model, gcdyn.SigmoidalBranchingProcess(1.0, 0.0, 2.0, 0.5, 1.0, 1.0, 0.7, 0.25, ts)]
+    got2 = gcdyn.loglikelihood(models, trees, 3.0)
+    want2 = [oracle.loglikelihood_shared(m, trees, 3.0) for m in models]
+    assert rel(got2, want2) <= SUM_RTOL
+    # alternates through the public API
+    t0 = trees[0]
+    assert abs(gcdyn.naive_loglikelihood(model, t0) - oracle.naive_loglikelihood(model, t0)) <= 1e-10 * abs(oracle.naive_loglikelihood(model, t0))
+    assert abs(gcdyn.stadler_appx_loglikelihood(model, t0, 3.0) - oracle.stadler_appx_loglikelihood(model, t0, 3.0)) <= 1e-10 * abs(oracle.stadler_appx_loglikelihood(model, t0, 3.0))
+    assert abs(gcdyn.stadler_appx_unconditioned_loglikelihood(model, t0, 3.0) - oracle.stadler_appx_unconditioned_loglikelihood(model, t0, 3.0)) <= 1e-10 * abs(oracle.stadler_appx_unconditioned_loglikelihood(model, t0, 3.0))
+
+
+def test_sigmoid_evaluated_on_device(ctx):
+    import oracle
+    rng = np.random.default_rng(12)
+    ts = np.linspace(-2, 2, 10)
+    models = [gcdyn.SigmoidalBranchingProcess(1.5 * a, 0.1 * b, 2.5, 0.5, 1.0, 1.0, 0.5, 0.1, ts)
+              for a, b in ((1.0, 0.0), (0.8, 1.0), (1.3, -1.0))]
+    trees = gcdyn.rand_tree(models[0], 3.0, ts[4], 8, rng=rng)
+    forest = gcdyn.Forest(trees, ts, 3.0, ctx=ctx)
+    out_t, _, _ = evaluate(forest, pack_params(models), 3.0)
+    out_s, _, _ = evaluate(forest, pack_params(models, response="sigmoid"), 3.0)
+    assert rel(out_s, out_t) <= 1e-13
+    want = [oracle.loglikelihood_shared(m, trees, 3.0) for m in models]
+    assert rel(out_s, want) <= SUM_RTOL
+
+
+def test_edge_cases(ctx):
+    import oracle
+    N = gcdyn.TreeNode
+    ts = [1.0, 2.0]
+    T = 2.0
+    model = gcdyn.ConstantBranchingProcess(1.5, 0.7, 0.9, 0.8, 0.4, ts)
+
+    def tiny():   # root -> survivor: the smallest legal tree (one node record)
+        r = N("root", 0, 1.0)
+        gcdyn.attach(r, N("sampled_survival", T, 1.0))
+        return r
+
+    def small():  # root -> type_change(1→2) -> birth -> (death, survivor)
+        r = N("root", 0, 1.0)
+        tc = N("type_change", 0.5, 2.0); gcdyn.attach(r, tc)
+        b = N("birth", 1.1, 2.0); gcdyn.attach(tc, b)
+        gcdyn.attach(b, N("sampled_death", 1.6, 2.0))
+        gcdyn.attach(b, N("sampled_survival", T, 2.0))
+        return r
+    for tr in (tiny(), small()):
+        got = gcdyn.loglikelihood(model, tr, T)
+        want = oracle.loglikelihood(model, tr, T)
+        assert abs(got - want) <= 1e-11 * max(1.0, abs(want))
+    # ragged forest: tiny trees mixed with a large one
+    rng = np.random.default_rng(13)
+    big = gcdyn.rand_tree(model, T, 1.0, rng=rng, min_leaves=20)
+    forest_trees = [tiny(), big, small(), tiny()]
+    assert abs(gcdyn.loglikelihood(model, forest_trees, T) - oracle.loglikelihood_shared(model, forest_trees, T)) <= 1e-10 * 50
+    # self loop: `@warn` + -Inf (mbp.jl:181-185)
+    loop = small()
+    loop.children[0].type = 1.0
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert gcdyn.loglikelihood(model, loop, T) == -math.inf
+        assert any("Self-loop" in str(x.message) for x in w)
+    assert oracle.loglikelihood(model, loop, T) == -math.inf
+    # σ = 0 with a sampled death in the tree: log 0 = -Inf flows through silently (mbp.jl:171)
+    m0 = gcdyn.ConstantBranchingProcess(1.5, 0.7, 0.9, 0.8, 0.0, ts)
+    assert gcdyn.loglikelihood(m0, small(), T) == -math.inf
+    assert oracle.loglikelihood(m0, small(), T) == -math.inf
+    # ... but not when no sampled death occurs (0 · log 0 must not poison the sum)
+    assert math.isfinite(gcdyn.loglikelihood(m0, tiny(), T))
+    # ρ = 0 with a sampled survivor
+    mr = gcdyn.ConstantBranchingProcess(1.5, 0.7, 0.9, 0.0, 0.4, ts)
+    assert gcdyn.loglikelihood(mr, tiny(), T) == -math.inf
+    # negative birth rate on a birth branch: Julia's log throws DomainError
+    mneg = gcdyn.DiscreteBranchingProcess([1.0, -0.5], 0.7, 0.9, 0.8, 0.4, ts)
+    with pytest.raises(gcdyn.DomainError):
+        gcdyn.loglikelihood(mneg, small(), T)
+    # empty forest: the sum over no trees is 0
+    forest = gcdyn.Forest([], ts, T, ctx=ctx)
+    out, _, _ = evaluate(forest, pack_params(model), T)
+    assert out[0] == 0.0
+
+
+def test_many_types_uses_multi_type_lanes(ctx):
+    """K = 40 (> 32): two types per lane in the trajectory kernel."""
+    import oracle
+    rng = np.random.default_rng(14)
+    K = 40
+    ts = np.linspace(-2, 2, K)
+    model = gcdyn.SigmoidalBranchingProcess(1.5, 0.0, 2.5, 0.5, 1.0, 1.0, 0.5, 0.1, ts)
+    trees = gcdyn.rand_tree(model, 3.0, ts[K // 2], 6, rng=rng)
+    got = gcdyn.loglikelihood(model, trees, 3.0)
+    want = oracle.loglikelihood_shared(model, trees, 3.0)
+    assert abs(got - want) <= SUM_RTOL * abs(want)
+    K = 70
+    ts = np.linspace(-2, 2, K)
+    model = gcdyn.SigmoidalBranchingProcess(1.5, 0.0, 2.5, 0.5, 1.0, 1.0, 0.5, 0.1, ts)
+    trees = gcdyn.rand_tree(model, 2.5, ts[K // 2], 4, rng=rng)
+    got = gcdyn.loglikelihood(model, trees, 2.5)
+    want = oracle.loglikelihood_shared(model, trees, 2.5)
+    assert abs(got - want) <= SUM_RTOL * abs(want)
+
+
+def test_shards_sum_to_the_whole(ctx):
+    """Multi-GPU emulation: R tree-shards evaluated separately sum to the unsharded result."""
+    flat, params, T, exp, _ = load_golden("g2_config2")
+    whole = gcdyn.Forest(flat, None, T, ctx=ctx)
+    out_w, tp_w, _ = evaluate(whole, params, T, per_tree=True)
+    from gcdyn.sharding import shard_flat
+    for R in (2, 3):
+        parts = [gcdyn.Forest(s, None, T, ctx=ctx) for s in shard_flat(flat, R)]
+        total = sum(evaluate(p, params, T)[0] for p in parts)
+        assert rel(total, out_w) <= 1e-13
