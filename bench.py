@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched multitype branching-process tree log-likelihood.
+
+    python bench.py --gpus N --steps K --warmup W            # this build, one rank per GPU (torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the reference algorithm on host cores
+
+Workload at every N: BASELINE.json config 3 — 1000 trees per GPU × 256 parameter sets, K = 20 types
+(weak scaling: trees are sharded, the [P] partial sums are combined by ONE all-reduce).  A step is one
+batched evaluation of all P parameter sets against the rank's trees, producing the per-(tree,pset)
+matrix and the [P] sums.  `value` = (tree, pset) evaluations per second over the whole job, with the
+forest and the parameters resident in HBM; `e2e` is the same through the host-buffer C-ABI call
+(`gcdyn_loglik_batch`: parameters copied H2D from pinned staging, results D2H) every step.
+
+The real Julia reference cannot run here (no Julia in the image); the CPU arm times `oracle/refcpu.c`,
+a C restatement of the reference algorithm as written (one adaptive RK5(4) solve per node, reference
+default tolerances), OpenMP over (tree, pset) pairs on all host cores.  It prints one JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "gcdyn.jl_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOAD = "C3"
+METRIC = "tree_loglik_evals_per_sec"
+UNIT = "(tree,pset) evals/s"
+
+
+def config_dict(name, trees_per_gpu, psets, n_gpus, extra=None):
+    import workloads
+    c = workloads.CONFIGS[name]
+    d = {"workload": f"BASELINE config 3: {trees_per_gpu} trees/GPU x {psets} parameter sets, K={c['K']} "
+                     f"sigmoid birth response, rho=0.5, sigma=0.1, present_time={c['T']}, simulator seed {c['seed']}",
+         "trees_per_gpu": trees_per_gpu, "trees_total": trees_per_gpu * n_gpus, "psets": psets, "K": c["K"],
+         "present_time": c["T"], "parallelism": f"trees sharded over {n_gpus} GPU(s), one all-reduce of [P] doubles"
+         if n_gpus > 1 else "single GPU",
+         "l2": "L2 flushed (256 MiB write) before every timed step; inputs (forest+table < 126 MB) would otherwise stay in L2"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ------------------------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+
+def cpu_reference_rate(flat, par, T, n_trees, n_psets, nthreads=0):
+    """Time oracle/refcpu.c (reference algorithm as written, reltol = abstol = 1e-3 like the reference's
+    defaults) on the first `n_trees` trees × first `n_psets` parameter sets.  Returns (pairs/s, seconds)."""
+    import refcpu
+    from gcdyn.sharding import subset_flat
+    sub = subset_flat(flat, np.arange(n_trees))
+    sp = {k: (v[:n_psets] if k != "Gamma" else v[:n_psets]) for k, v in par.items()}
+    t0 = time.perf_counter()
+    refcpu.loglik(sub, sp, T, rtol=1e-3, atol=1e-3, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return n_trees * n_psets / dt, dt
+
+
+def cpu_baseline(flat, par, T, budget_s=12.0):
+    import refcpu
+    cores = refcpu.max_threads()
+    n_trees = min(flat.n_trees, 64)
+    n_psets = min(par["lam"].shape[0], 4)
+    rate, dt = cpu_reference_rate(flat, par, T, n_trees, n_psets)
+    # grow the sample towards the budget (bounded by the full workload)
+    P, Tn = par["lam"].shape[0], flat.n_trees
+    while dt < budget_s / 3 and (n_trees < Tn or n_psets < P):
+        grow = min(8.0, max(2.0, 0.6 * budget_s / max(dt, 1e-3)))
+        if n_trees < Tn:
+            n_trees = int(min(Tn, n_trees * grow))
+        else:
+            n_psets = int(min(P, max(n_psets + 1, n_psets * grow)))
+        rate, dt = cpu_reference_rate(flat, par, T, n_trees, n_psets)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n_trees} trees x first {n_psets} parameter sets of the same workload, "
+                      f"{dt:.1f} s, oracle/refcpu.c (C restatement of mbp.jl:110-259 as written: one adaptive "
+                      f"RK5(4) solve per node, reltol=abstol=1e-3), OpenMP over (tree,pset) pairs; "
+                      f"the real Julia reference cannot run in this image"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import workloads
+    c = workloads.CONFIGS[WORKLOAD]
+    flat = workloads.flat_forest(WORKLOAD, 0, args.trees)
+    par = workloads.par_dict(workloads.jittered_models(WORKLOAD, args.psets))
+    import refcpu
+    cores = refcpu.max_threads()
+    # bounded sample per step: sized from a probe so that (warmup + steps) stay within a few minutes
+    n_trees, n_psets = min(flat.n_trees, 64), min(args.psets, 4)
+    rate, dt = cpu_reference_rate(flat, par, c["T"], n_trees, n_psets)
+    target = 6.0
+    if dt < target / 2:
+        n_trees = int(min(flat.n_trees, max(n_trees, n_trees * target / max(dt, 1e-3))))
+        if n_trees == flat.n_trees:
+            n_psets = int(min(args.psets, max(n_psets, rate * target / n_trees)))
+    for _ in range(args.warmup):
+        cpu_reference_rate(flat, par, c["T"], min(n_trees, 32), 1)
+    times = []
+    for _ in range(args.steps):
+        _, dt = cpu_reference_rate(flat, par, c["T"], n_trees, n_psets)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = n_trees * n_psets / (ms * 1e-3)
+    sample = (f"each step = first {n_trees} trees x first {n_psets} parameter sets of the workload "
+              f"(bounded sample), oracle/refcpu.c at reltol=abstol=1e-3, {cores} OpenMP threads")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(WORKLOAD, args.trees, args.psets, args.gpus,
+                                  {"note": "CPU arm: C restatement of the reference algorithm (Julia unavailable in this image)"}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import gcdyn
+    import workloads
+    from gcdyn.likelihood import DeviceParams, evaluate, evaluate_resident, pack_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    c = workloads.CONFIGS[WORKLOAD]
+    T, K, P, Tn = c["T"], c["K"], args.psets, args.trees
+
+    # ---- inputs: this rank's shard of the forest, the replicated parameter batch
+    flat = workloads.flat_forest(WORKLOAD, rank * Tn, Tn)
+    models = workloads.jittered_models(WORKLOAD, P)
+    params = pack_params(models)
+    ctx = gcdyn.Context(local)
+    forest = gcdyn.Forest(flat, None, T, ctx=ctx)
+    dpar = DeviceParams(params, ctx)
+    info = forest.info()
+    out = torch.zeros(P, dtype=torch.float64, device="cuda")
+    out_tree = torch.zeros(P * Tn, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    # a non-default stream: its handle is what the library launches on, so these CUDA events bracket the kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+
+    def step_resident():
+        evaluate_resident(forest, dpar, T, out.data_ptr(), out_tree.data_ptr(), 0, stream.cuda_stream,
+                          steps=args.taylor_steps, order=args.order)
+        if world > 1:
+            dist.all_reduce(out)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step_resident()
+    barrier()
+    diag = ctx.last_diag(P)
+    launches_per_step = diag["n_launches"]
+
+    # ---- timed region: K steps, each bracketed by CUDA events on the launching stream, L2 flushed between
+    sampler = ClockSampler(local) if rank == 0 else None
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record(stream)
+        step_resident()
+        ends[i].record(stream)
+    barrier()
+    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    # keep the GPU busy a little longer so the clock sampler sees load even for very short runs
+    t_end = time.perf_counter() + 1.0
+    while time.perf_counter() < t_end:
+        step_resident()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    tm = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tm.item()) / args.steps
+    value = world * Tn * P / (ms_per_step * 1e-3)
+    result = out.cpu().numpy().copy()
+
+    # ---- e2e: the host-buffer C-ABI call (parameters H2D, results D2H inside the timed region)
+    for _ in range(3):
+        evaluate(forest, params, T, steps=args.taylor_steps, order=args.order, want_status=False)
+    barrier()
+    e2e_s = 0.0
+    for i in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        o, _, _ = evaluate(forest, params, T, steps=args.taylor_steps, order=args.order, want_status=False)
+        if world > 1:
+            t = torch.from_numpy(o).cuda()
+            dist.all_reduce(t)
+            o = t.cpu().numpy()
+        e2e_s += time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * Tn * P / (float(te.item()) / args.steps)
+    n_par_doubles = sum(int(np.size(a)) for a in (params.lam, params.mu, params.delta, params.rho, params.sigma, params.Gamma)
+                        if a is not None)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_par_doubles,
+           "d2h_bytes_per_step": P * (8 + 8 + 4), "ms_per_step": 1e3 * float(te.item()) / args.steps,
+           "api": "gcdyn_loglik_batch (host buffers; forest handle created once per dataset, as a sampler would)"}
+    if world > 1:
+        assert np.allclose(o, result, rtol=1e-12, atol=0)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel durations (CUDA events inside the library, on the launching stream), roofline
+    ctx.set_profiling(True)
+    acc = {}
+    nprof = 10
+    for _ in range(nprof):
+        flush.zero_()
+        evaluate_resident(forest, dpar, T, out.data_ptr(), out_tree.data_ptr(), 0, stream.cuda_stream,
+                          steps=args.taylor_steps, order=args.order)
+        for k, v in ctx.last_kernel_ms().items():
+            acc[k] = acc.get(k, 0.0) + v / nprof
+    ctx.set_profiling(False)
+    S, M = diag["steps"], diag["order"]
+    n_items = info["n_items"]
+    fp64_peak = ctx.probe_fp64_peak()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    # algorithmic FLOPs: sweep = items·P·(2(M+1) Horner + 8), trajectory = P·S·[M(2K²+5K) + M(M+1)K + 6(M+2)K]
+    flops = {"sweep": n_items * P * (2.0 * (M + 1) + 8.0),
+             "trajectory": P * S * (M * (2.0 * K * K + 5.0 * K) + M * (M + 1.0) * K + 6.0 * (M + 2) * K)}
+    dom = max(("sweep", "trajectory"), key=lambda k: acc.get(k, 0.0))
+    achieved = flops[dom] / (acc[dom] * 1e-3) / 1e12
+    # algorithmic bytes of the sweep: item records once per pset + per-(tree,pset) output
+    sweep_bytes = n_items * 16.0 * P + Tn * P * 8.0
+    roofline = {"kernel": f"{dom}_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                "peak_source": "measured live: register-resident DFMA loop on all SMs (gcdyn_probe_fp64_peak); "
+                               "MEASURED_PEAKS.json has no FP64 figure",
+                "traffic": None, "kernel_ms": acc, "kernel_share": {k: v / sum(acc.values()) for k, v in acc.items()},
+                "algorithmic_flops_per_launch": flops[dom],
+                "hbm": {"achieved_gbs": sweep_bytes / (acc["sweep"] * 1e-3) / 1e9 if acc.get("sweep") else None,
+                        "peak_gbs": peaks.get("hbm_gbs"), "note": "node/item sweep algorithmic bytes; working set is L2-resident"}}
+
+    # ---- parity beside the number: oracle (shared-trajectory form, scipy DOP853 1e-13) on 2 parameter sets
+    import oracle
+    par = workloads.par_dict(models)
+    host_tree = out_tree.cpu().numpy().reshape(P, Tn)
+    rels = []
+    for p in (0, P - 1):
+        want = oracle.loglik_flat_shared(flat, par, p, T)
+        rels.append(abs(host_tree[p].sum() - want.sum()) / abs(want.sum()))
+    parity = {"psets_checked": 2, "max_rel_err_sum": float(max(rels)), "gate": 1e-8}
+
+    cpu = cpu_baseline(flat, par, T) if world == 1 else None
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(WORKLOAD, Tn, P, world, {
+                "nodes_per_gpu": info["n_nodes"], "lookup_items_per_gpu": n_items, "taylor_steps": S,
+                "taylor_order": M, "max_err_indicator": float(np.max(diag["err_indicator"]))}),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "parity": parity}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="gcdyn_b200", choices=["gcdyn_b200", "reference"])
+    ap.add_argument("--trees", type=int, default=1000, help="trees per GPU")
+    ap.add_argument("--psets", type=int, default=256)
+    ap.add_argument("--order", type=int, default=0)
+    ap.add_argument("--taylor-steps", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,6 +62,10 @@ struct gcdyn_ctx {
     // diagnostics of the last evaluation
     int last_steps = 0, last_order = 0, last_launches = 0, last_P = 0;
     PsetPack last_pack{};
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool profile = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
 };
 
 struct gcdyn_forest {
@@ -306,17 +310,22 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         d_out_tree = ctx->out_tree.as<double>();
     }
     int launches = 0;
+    const bool prof = ctx->profile && ctx->ev[0];
+    ctx->ev_valid = false;
+    if (prof) cudaEventRecord(ctx->ev[0], st);
     if (run_prep) {
         prep_kernel<<<P, 128, 0, st>>>(pv, pk, method);
         CU_TRY(ctx, cudaGetLastError());
         ++launches;
     }
+    if (prof) cudaEventRecord(ctx->ev[1], st);
     if (method == GCDYN_METHOD_ODE) {
         const size_t tab_bytes = (size_t)P * S * (M + 2) * K * 8;
         CU_TRY(ctx, ctx->table.ensure(tab_bytes));
         rc = launch_traj(ctx, M, pv, pk, T, S, ctx->table.as<double>(), st);
         if (rc) return rc;
         ++launches;
+        if (prof) cudaEventRecord(ctx->ev[2], st);
         rc = launch_sweep(ctx, M, f, pk, ctx->table.as<double>(), T, S, P, d_out_tree, d_status, st);
         if (rc) return rc;
         ++launches;
@@ -326,14 +335,17 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             CU_TRY(ctx, cudaGetLastError());
             ++launches;
         }
+        if (prof) cudaEventRecord(ctx->ev[2], st);
         dim3 grid((unsigned)f->n_chunks, (unsigned)P);
         alt_kernel<<<grid, 256, 0, st>>>(f->v, pv, pk, f->d_chunk_off, T, method, d_out_tree, d_status);
         CU_TRY(ctx, cudaGetLastError());
         ++launches;
     }
+    if (prof) cudaEventRecord(ctx->ev[3], st);
     reduce_kernel<<<P, 256, 0, st>>>(d_out_tree, Tn, d_out_pset);
     CU_TRY(ctx, cudaGetLastError());
     ++launches;
+    if (prof) { cudaEventRecord(ctx->ev[4], st); ctx->ev_valid = true; }
     ctx->last_steps = method == GCDYN_METHOD_ODE ? S : 0;
     ctx->last_order = method == GCDYN_METHOD_ODE ? M : 0;
     ctx->last_launches = launches;
@@ -631,6 +643,7 @@ void gcdyn_ctx_destroy(gcdyn_ctx* ctx) {
     cudaGetDevice(&prev);
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     ctx->params_blob.release(); ctx->pack.release(); ctx->table.release(); ctx->out_tree.release();
     ctx->out_pset.release(); ctx->status.release(); ctx->probe.release();
     ctx->pin_in.release(); ctx->pin_out.release();
@@ -751,6 +764,29 @@ int gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_l
         CU_TRY(ctx, cudaDeviceSynchronize());
         CU_TRY(ctx, cudaMemcpy(err_indicator, ctx->last_pack.perr, (size_t)n_psets * 8, cudaMemcpyDeviceToHost));
     }
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+int gcdyn_set_profiling(gcdyn_ctx* ctx, int on) {
+    GUARD_BEGIN
+    if (!ctx) return fail(ctx, GCDYN_EINVAL, "ctx is NULL");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (on && !ctx->ev[0])
+        for (auto& e : ctx->ev) CU_TRY(ctx, cudaEventCreate(&e));
+    ctx->profile = on != 0;
+    ctx->ev_valid = false;
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+int gcdyn_last_kernel_ms(gcdyn_ctx* ctx, float* ms) {
+    GUARD_BEGIN
+    if (!ctx || !ms) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    if (!ctx->ev_valid) return fail(ctx, GCDYN_EINVAL, "no profiled evaluation to report on");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaEventSynchronize(ctx->ev[4]));
+    for (int i = 0; i < 4; ++i) CU_TRY(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
     return GCDYN_OK;
     GUARD_END(ctx)
 }

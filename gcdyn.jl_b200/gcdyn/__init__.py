@@ -13,7 +13,8 @@ from .multitype_branching_process import (expit, sigmoid, type_space_index, λ, 
 from .flatten import FlatForest, flatten
 from .likelihood import (loglikelihood, naive_loglikelihood, stadler_appx_loglikelihood,
                          stadler_appx_unconditioned_loglikelihood, Forest, Context,
-                         pack_params, GcdynError, library_path)
+                         pack_params, DeviceParams, evaluate, evaluate_resident,
+                         GcdynError, library_path)
 
 __all__ = [
     # reference exports (gcdyn.jl:15-33)
@@ -25,6 +26,7 @@ __all__ = [
     "naive_loglikelihood", "stadler_appx_loglikelihood", "stadler_appx_unconditioned_loglikelihood",
     "expit", "sigmoid", "type_space_index", "mutate", "sample_child", "EVENTS",
     # additions of this build
-    "Forest", "Context", "FlatForest", "flatten", "pack_params", "lambda_", "mu", "gamma",
+    "Forest", "Context", "FlatForest", "flatten", "pack_params", "DeviceParams", "evaluate",
+    "evaluate_resident", "lambda_", "mu", "gamma",
     "ArgumentError", "DimensionMismatch", "BoundsError", "DomainError", "GcdynError", "library_path",
 ]

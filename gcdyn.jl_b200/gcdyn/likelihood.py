@@ -21,7 +21,7 @@ from .flatten import FlatForest, flatten
 
 __all__ = ["loglikelihood", "naive_loglikelihood", "stadler_appx_loglikelihood",
            "stadler_appx_unconditioned_loglikelihood", "Forest", "Context", "pack_params",
-           "GcdynError", "library_path"]
+           "DeviceParams", "evaluate", "evaluate_resident", "GcdynError", "library_path"]
 
 METHOD_CODE = {"ode": 0, "naive": 1, "stadler": 2, "stadler_unconditioned": 3}
 STATUS_SELF_LOOP, STATUS_SOLVER, STATUS_DOMAIN = 1, 2, 4
@@ -110,6 +110,8 @@ def _lib():
                                                   vp, vp, vp, vp]),
         "gcdyn_last_diag": (C.c_int, [vp, _p_i32, _p_i32, _p_i32, _p_f64, C.c_int32]),
         "gcdyn_probe_fp64_peak": (C.c_int, [vp, _p_f64]),
+        "gcdyn_set_profiling": (C.c_int, [vp, C.c_int]),
+        "gcdyn_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)       # AttributeError here = header and library out of sync
@@ -169,6 +171,15 @@ class Context:
         _check(_lib().gcdyn_last_diag(self._h, C.byref(s), C.byref(o), C.byref(nl),
                                       _ptr(err, _p_f64) if n_psets else _p_f64(), int(n_psets)), self._h)
         return dict(steps=s.value, order=o.value, n_launches=nl.value, err_indicator=err[:n_psets])
+
+    def set_profiling(self, on=True):
+        _check(_lib().gcdyn_set_profiling(self._h, 1 if on else 0), self._h)
+
+    def last_kernel_ms(self):
+        """(prep, trajectory, sweep, reduce) durations of the last evaluation, CUDA-event timed."""
+        ms = (C.c_float * 4)()
+        _check(_lib().gcdyn_last_kernel_ms(self._h, ms), self._h)
+        return dict(zip(("prep", "trajectory", "sweep", "reduce"), (float(x) for x in ms)))
 
     def probe_fp64_peak(self):
         v = C.c_double()
@@ -286,6 +297,41 @@ def pack_params(models, response="table"):
                         xscale=xs, xshift=xsh, yscale=ys, yshift=ysh,
                         type_space=np.ascontiguousarray(ts, dtype=np.float64),
                         mu=mu, delta=delta, rho=rho, sigma=sigma, Gamma=Gamma)
+
+
+class DeviceParams:
+    """A parameter batch resident in HBM (`gcdyn_dparams`)."""
+
+    def __init__(self, params: "PackedParams", ctx=None):
+        self.ctx = ctx or Context.default()
+        self.n_psets, self.n_types = params.n_psets, params.n_types
+        ps = params.struct()
+        h = C.c_void_p()
+        _check(_lib().gcdyn_params_upload(self.ctx._h, C.byref(ps), C.byref(h)), self.ctx._h)
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib().gcdyn_dparams_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def evaluate_resident(forest, dparams, present_time, d_out_pset, d_out_tree_pset=0, d_status=0, stream=0,
+                      method="ode", steps=0, order=0, flags=0):
+    """`gcdyn_loglik_batch_resident`: everything already in HBM; `d_*` are raw device addresses
+    (e.g. `tensor.data_ptr()`), `stream` a raw cudaStream_t (e.g. `torch.cuda.current_stream().cuda_stream`).
+    Enqueues and returns without synchronising."""
+    op = Opts(steps=int(steps), order=int(order), tol=0.0, flags=int(flags), reserved=0)
+    _check(_lib().gcdyn_loglik_batch_resident(
+        forest.ctx._h, forest._h, dparams._h, float(present_time if present_time is not None else 0.0),
+        METHOD_CODE[method], C.byref(op), C.c_void_p(d_out_pset), C.c_void_p(d_out_tree_pset or None),
+        C.c_void_p(d_status or None), C.c_void_p(stream or None)), forest.ctx._h)
 
 
 # ----------------------------------------------------------------------------- evaluation

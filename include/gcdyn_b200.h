@@ -168,6 +168,12 @@ int  gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* forest, con
 int  gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_launches,
                      double* err_indicator, int32_t n_psets);
 
+/* Per-kernel timing for the roofline report: when on, every evaluation brackets its kernels with CUDA
+ * events on the launching stream; gcdyn_last_kernel_ms waits for the last evaluation and returns
+ * ms[4] = {prep, trajectory (or Stadler conditioning), sweep (or alternate), reduce}. */
+int  gcdyn_set_profiling(gcdyn_ctx* ctx, int on);
+int  gcdyn_last_kernel_ms(gcdyn_ctx* ctx, float* ms);
+
 /* FP64 FMA peak probe (roofline denominator; not part of the likelihood path): runs a
  * register-resident DFMA loop on every SM and returns achieved TFLOP/s. */
 int  gcdyn_probe_fp64_peak(gcdyn_ctx* ctx, double* tflops);

@@ -424,3 +424,42 @@ def event_counts(trees):
         for n in postorder(tree.children[0]):
             out[t, EVENTS.index(n.event)] += 1
     return out
+
+
+# ------------------------------------------------------------------ vectorised shared-trajectory form on flat arrays
+
+def loglik_flat_shared(flat, par, p, present_time, rtol=1e-13, atol=1e-13):
+    """Per-tree log-likelihoods [T] for parameter set `p` of `par` (dict: lam [P,K], mu, delta, rho, sigma [P],
+    Gamma [P,K,K] or [K,K] row-major) on a flattened forest, by the shared-trajectory formula of
+    `loglikelihood_shared` evaluated for all nodes at once.  Used for parity checks at sizes where the
+    per-branch recursion is too slow.  Ignores `live`/`self_loop` (valid, simulator-made trees only)."""
+    g = lambda name: np.asarray(getattr(flat, name) if hasattr(flat, name) else flat[name])
+    G = np.asarray(par["Gamma"], dtype=np.float64)
+    G = G[p] if G.ndim == 3 else G
+    m = Params(par["lam"][p], par["mu"][p], par["delta"][p], G, par["rho"][p], par["sigma"][p],
+               np.arange(len(par["lam"][p])))
+    K, T = m.K, float(present_time)
+    sol = trajectory(m, T, rtol, atol)
+    ev, x, y = g("event").astype(np.int64), g("btype_idx").astype(np.int64), g("type_idx").astype(np.int64)
+    ts, te = g("t_start"), g("t_end")
+    tree_off = g("tree_off")
+    n = len(ev)
+
+    def I_at(tau, typ):
+        out = np.empty(len(tau))
+        for lo in range(0, len(tau), 65536):
+            sl = slice(lo, lo + 65536)
+            out[sl] = sol.sol(tau[sl])[K + typ[sl], np.arange(len(tau[sl]))]
+        return out
+    Ia, Ib = I_at(T - ts, x), I_at(T - te, x)
+    Lam = m.lam + m.mu + m.delta * -np.diag(m.Gamma)
+    with np.errstate(divide="ignore"):
+        loglam = np.log(m.lam)
+        logG = np.log(m.delta * m.Gamma)
+        term = np.select([ev == 5, ev == 2, ev == 1, ev == 4],
+                         [np.full(n, _log(m.rho)), np.full(n, _log(m.mu) + _log(m.sigma)), loglam[x],
+                          logG[x, np.maximum(y, 0)]], default=np.nan)
+    contrib = term - Lam[x] * (te - ts) + 2.0 * m.lam[x] * (Ia - Ib)
+    sums = np.add.reduceat(contrib, tree_off[:-1]) if n else np.zeros(len(tree_off) - 1)
+    pT = sol.sol(T)[:K]
+    return sums - np.log1p(-pT)[g("root_type_idx")]
