@@ -54,6 +54,7 @@ struct PinBuf {
 struct gcdyn_ctx {
     int device = 0;
     int sm_count = 148;
+    int smem_optin = 232448;
     cudaStream_t stream = nullptr;
     std::string err;
     // workspace (grow-only)
@@ -210,20 +211,24 @@ int normalise_order(int order) {
     return -1;
 }
 
-int auto_steps(double present_time, double rate_max, int M) {
-    double target;
-    switch (M) {
-        case 8: target = 0.055; break;
-        case 12: target = 0.20; break;
-        case 16: target = 0.36; break;
-        case 20: target = 0.50; break;
-        default: target = 0.62; break;
-    }
+int steps_for(double present_time, double rate_max, double target) {
     if (!(rate_max == rate_max) || !(present_time > 0.0)) return 4;
     double s = std::ceil(present_time * rate_max / target);
     if (s < 4.0) s = 4.0;
     if (s > (double)S_CAP) s = (double)S_CAP;
     return (int)s;
+}
+
+// Capacity (in cells) of the per-pset table: 1.5× the step count the calibrated worst case needs.
+int cap_steps(double present_time, double rate_max, int M) {
+    const int safe = steps_for(present_time, rate_max, hrate_target_safe(M));
+    return std::min(S_CAP, ladder_ceil((long long)safe + safe / 2));
+}
+
+// Cells the fastest pset is expected to need (the kernel's own first guess, one rung up): sizes the
+// shared-memory staging buffer of the sweep.
+int expected_steps(double present_time, double rate_max, int M) {
+    return ladder_next(ladder_ceil(steps_for(present_time, rate_max, hrate_target_start(M))));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -233,7 +238,7 @@ int carve_pack(gcdyn_ctx* ctx, int P, int K, PsetPack* pk) {
     const size_t ntw = (size_t)K + (size_t)K * K + 2;
     const size_t PK = (size_t)P * K;
     const size_t n_doubles = PK * 6 + (size_t)P * ntw + (size_t)P;
-    const size_t bytes = n_doubles * 8 + (size_t)P * 4 + 64;
+    const size_t bytes = n_doubles * 8 + (size_t)P * 8 + 64;
     CU_TRY(ctx, ctx->pack.ensure(bytes));
     double* d = ctx->pack.as<double>();
     pk->ntw = (int)ntw;
@@ -246,59 +251,84 @@ int carve_pack(gcdyn_ctx* ctx, int P, int K, PsetPack* pk) {
     pk->nt = d; d += (size_t)P * ntw;
     pk->perr = d; d += P;
     pk->pstatus = reinterpret_cast<int*>(d);
+    pk->S = pk->pstatus + P;
     return GCDYN_OK;
 }
 
-template <int M, int KPL>
-int launch_traj_inst(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, double T, int S, double* tab,
+template <int M, int KP, int KPL>
+int launch_traj_inst(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, double* tab,
                      cudaStream_t st) {
-    const size_t smem = ((size_t)pv.K * pv.K + 2 * (size_t)pv.K) * sizeof(double);
+    const size_t KS = KPL == 1 ? (size_t)KP : (((size_t)pv.K + 3) & ~(size_t)3);
+    const size_t smem = (2 * KS + (KPL == 1 ? 0 : (size_t)pv.K * pv.K)) * sizeof(double);
     if (smem > 48 * 1024)
-        CU_TRY(ctx, cudaFuncSetAttribute(traj_kernel<M, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    traj_kernel<M, KPL><<<pv.P, 32, smem, st>>>(pv, pk, T, S, tab);
+        CU_TRY(ctx, cudaFuncSetAttribute(traj_kernel<M, KP, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    traj_kernel<M, KP, KPL><<<pv.P, 32, smem, st>>>(pv, pk, cfg, tab);
     CU_TRY(ctx, cudaGetLastError());
     return GCDYN_OK;
 }
 
 template <int M>
-int launch_traj_m(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, double T, int S, double* tab,
+int launch_traj_m(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, double* tab,
                   cudaStream_t st) {
-    if (pv.K <= 32) return launch_traj_inst<M, 1>(ctx, pv, pk, T, S, tab, st);
-    if (pv.K <= 64) return launch_traj_inst<M, 2>(ctx, pv, pk, T, S, tab, st);
-    return launch_traj_inst<M, 4>(ctx, pv, pk, T, S, tab, st);
+    const int K = pv.K;
+    if (K <= 8) return launch_traj_inst<M, 8, 1>(ctx, pv, pk, cfg, tab, st);
+    if (K <= 16) return launch_traj_inst<M, 16, 1>(ctx, pv, pk, cfg, tab, st);
+    if (K <= 24) return launch_traj_inst<M, 24, 1>(ctx, pv, pk, cfg, tab, st);
+    if (K <= 32) return launch_traj_inst<M, 32, 1>(ctx, pv, pk, cfg, tab, st);
+    if (K <= 64) return launch_traj_inst<M, 0, 2>(ctx, pv, pk, cfg, tab, st);
+    return launch_traj_inst<M, 0, 4>(ctx, pv, pk, cfg, tab, st);
 }
 
-int launch_traj(gcdyn_ctx* ctx, int M, const ParamsView& pv, const PsetPack& pk, double T, int S, double* tab,
+int launch_traj(gcdyn_ctx* ctx, int M, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, double* tab,
                 cudaStream_t st) {
     switch (M) {
-        case 8: return launch_traj_m<8>(ctx, pv, pk, T, S, tab, st);
-        case 12: return launch_traj_m<12>(ctx, pv, pk, T, S, tab, st);
-        case 16: return launch_traj_m<16>(ctx, pv, pk, T, S, tab, st);
-        case 20: return launch_traj_m<20>(ctx, pv, pk, T, S, tab, st);
-        case 24: return launch_traj_m<24>(ctx, pv, pk, T, S, tab, st);
+        case 8: return launch_traj_m<8>(ctx, pv, pk, cfg, tab, st);
+        case 12: return launch_traj_m<12>(ctx, pv, pk, cfg, tab, st);
+        case 16: return launch_traj_m<16>(ctx, pv, pk, cfg, tab, st);
+        case 20: return launch_traj_m<20>(ctx, pv, pk, cfg, tab, st);
+        case 24: return launch_traj_m<24>(ctx, pv, pk, cfg, tab, st);
     }
     return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
 }
 
-int launch_sweep(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& pk, const double* tab, double T,
-                 int S, int P, double* out_tree, int32_t* status, cudaStream_t st) {
-    dim3 grid((unsigned)f->n_chunks, (unsigned)P);
-    switch (M) {
-        case 8: sweep_kernel<8><<<grid, 256, 0, st>>>(f->v, pk, tab, f->d_chunk_off, T, S, out_tree, status); break;
-        case 12: sweep_kernel<12><<<grid, 256, 0, st>>>(f->v, pk, tab, f->d_chunk_off, T, S, out_tree, status); break;
-        case 16: sweep_kernel<16><<<grid, 256, 0, st>>>(f->v, pk, tab, f->d_chunk_off, T, S, out_tree, status); break;
-        case 20: sweep_kernel<20><<<grid, 256, 0, st>>>(f->v, pk, tab, f->d_chunk_off, T, S, out_tree, status); break;
-        case 24: sweep_kernel<24><<<grid, 256, 0, st>>>(f->v, pk, tab, f->d_chunk_off, T, S, out_tree, status); break;
-        default: return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
-    }
+template <int M>
+int launch_sweep_m(gcdyn_ctx* ctx, const gcdyn_forest* f, const PsetPack& pk, const double* tab, long long tab_stride,
+                   double T, int P, size_t want_smem, double* out_tree, int32_t* status, cudaStream_t st) {
+    // dynamic shared memory = staging buffer for one pset's table (bulk-copied); psets whose table is
+    // larger than the buffer are read from global memory by the same kernel
+    size_t smem = std::min(std::max(want_smem, (size_t)64 * 1024), (size_t)ctx->smem_optin - 2048);
+    smem &= ~(size_t)127;
+    if (smem > 48 * 1024)
+        CU_TRY(ctx, cudaFuncSetAttribute(sweep_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CU_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel<M>, SWEEP_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long long units = (long long)P * f->n_chunks;
+    const long long grid = std::max<long long>(1, std::min<long long>(units, (long long)ctx->sm_count * per_sm));
+    sweep_kernel<M><<<(unsigned)grid, SWEEP_THREADS, smem, st>>>(f->v, pk, tab, tab_stride, f->d_chunk_off, (int)f->n_chunks, P, T,
+                                                      (int)(smem / 8), out_tree, status);
     CU_TRY(ctx, cudaGetLastError());
     return GCDYN_OK;
 }
 
+int launch_sweep(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& pk, const double* tab,
+                 long long tab_stride, double T, int P, size_t want_smem, double* out_tree, int32_t* status,
+                 cudaStream_t st) {
+    switch (M) {
+        case 8: return launch_sweep_m<8>(ctx, f, pk, tab, tab_stride, T, P, want_smem, out_tree, status, st);
+        case 12: return launch_sweep_m<12>(ctx, f, pk, tab, tab_stride, T, P, want_smem, out_tree, status, st);
+        case 16: return launch_sweep_m<16>(ctx, f, pk, tab, tab_stride, T, P, want_smem, out_tree, status, st);
+        case 20: return launch_sweep_m<20>(ctx, f, pk, tab, tab_stride, T, P, want_smem, out_tree, status, st);
+        case 24: return launch_sweep_m<24>(ctx, f, pk, tab, tab_stride, T, P, want_smem, out_tree, status, st);
+    }
+    return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
+}
+
 // Enqueue one evaluation on `st`.  All pointers are device pointers; d_out_tree/d_status may be null.
-int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, double T, int method, int M, int S,
-                 bool run_prep, double* d_out_pset, double* d_out_tree, int32_t* d_status, cudaStream_t st,
-                 PsetPack* pk_out) {
+// S_fixed > 0 pins the number of Taylor cells; otherwise every pset adapts it inside traj_kernel.
+int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, double rate_max, double T, int method,
+                 int M, int S_fixed, double tol, double* d_out_pset, double* d_out_tree, int32_t* d_status,
+                 cudaStream_t st, PsetPack* pk_out) {
     const int P = pv.P, K = pv.K;
     if (P > 65535) return fail(ctx, GCDYN_EUNSUPPORTED, "more than 65535 parameter sets per call");
     PsetPack pk{};
@@ -313,23 +343,33 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
     const bool prof = ctx->profile && ctx->ev[0];
     ctx->ev_valid = false;
     if (prof) cudaEventRecord(ctx->ev[0], st);
-    if (run_prep) {
-        prep_kernel<<<P, 128, 0, st>>>(pv, pk, method);
-        CU_TRY(ctx, cudaGetLastError());
-        ++launches;
-    }
-    if (prof) cudaEventRecord(ctx->ev[1], st);
     if (method == GCDYN_METHOD_ODE) {
-        const size_t tab_bytes = (size_t)P * S * (M + 2) * K * 8;
+        if (prof) cudaEventRecord(ctx->ev[1], st);
+        TrajCfg cfg{};
+        cfg.T = T;
+        cfg.tol = tol;
+        cfg.S_fixed = S_fixed;
+        cfg.S_cap = S_fixed > 0 ? S_fixed : cap_steps(T, rate_max, M);
+        const long long L = M + 2;
+        cfg.tab_stride = (long long)cfg.S_cap * K * L;
+        const size_t tab_bytes = (size_t)P * (size_t)cfg.tab_stride * 8;
         CU_TRY(ctx, ctx->table.ensure(tab_bytes));
-        rc = launch_traj(ctx, M, pv, pk, T, S, ctx->table.as<double>(), st);
+        rc = launch_traj(ctx, M, pv, pk, cfg, ctx->table.as<double>(), st);
         if (rc) return rc;
         ++launches;
         if (prof) cudaEventRecord(ctx->ev[2], st);
-        rc = launch_sweep(ctx, M, f, pk, ctx->table.as<double>(), T, S, P, d_out_tree, d_status, st);
+        const int S_stage = S_fixed > 0 ? S_fixed : std::min(cfg.S_cap, expected_steps(T, rate_max, M));
+        const size_t want_smem = (size_t)S_stage * K * L * 8;
+        rc = launch_sweep(ctx, M, f, pk, ctx->table.as<double>(), cfg.tab_stride, T, P, want_smem, d_out_tree,
+                          d_status, st);
         if (rc) return rc;
         ++launches;
+        ctx->last_steps = cfg.S_cap;
     } else {
+        prep_kernel<<<P, 128, 0, st>>>(pv, pk, method);
+        CU_TRY(ctx, cudaGetLastError());
+        ++launches;
+        if (prof) cudaEventRecord(ctx->ev[1], st);
         if (method == GCDYN_METHOD_STADLER) {
             stadler_cond_kernel<<<P, 128, 0, st>>>(pv, pk, T);
             CU_TRY(ctx, cudaGetLastError());
@@ -340,13 +380,13 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         alt_kernel<<<grid, 256, 0, st>>>(f->v, pv, pk, f->d_chunk_off, T, method, d_out_tree, d_status);
         CU_TRY(ctx, cudaGetLastError());
         ++launches;
+        ctx->last_steps = 0;
     }
     if (prof) cudaEventRecord(ctx->ev[3], st);
     reduce_kernel<<<P, 256, 0, st>>>(d_out_tree, Tn, d_out_pset);
     CU_TRY(ctx, cudaGetLastError());
     ++launches;
     if (prof) { cudaEventRecord(ctx->ev[4], st); ctx->ev_valid = true; }
-    ctx->last_steps = method == GCDYN_METHOD_ODE ? S : 0;
     ctx->last_order = method == GCDYN_METHOD_ODE ? M : 0;
     ctx->last_launches = launches;
     ctx->last_P = P;
@@ -415,13 +455,13 @@ int forest_create_impl(gcdyn_ctx* ctx, const gcdyn_forest_desc* d, gcdyn_forest*
     // ---- lookup items of the regrouped ODE sum
     std::vector<int64_t> item_off(T + 1, 0);
     std::vector<double> it_time;
-    std::vector<int32_t> it_tw, it_aux, n_death(T, 0), n_surv(T, 0);
+    std::vector<int2> it_meta;
+    std::vector<int32_t> n_death(T, 0), n_surv(T, 0);
     std::vector<uint8_t> live_all, loop_all;
-    it_time.reserve(N + T); it_tw.reserve(N + T); it_aux.reserve(N + T);
+    it_time.reserve(N + T); it_meta.reserve(N + T);
     auto push = [&](double tm, int type, int w, int aux) {
         it_time.push_back(tm);
-        it_tw.push_back((int32_t)((uint32_t)type | ((uint32_t)(uint8_t)(int8_t)w << 24)));
-        it_aux.push_back(aux);
+        it_meta.push_back(make_int2((int32_t)((uint32_t)type | ((uint32_t)(uint8_t)(int8_t)w << 24)), aux));
     };
     int64_t max_items = 0;
     for (int64_t t = 0; t < T; ++t) {
@@ -483,8 +523,7 @@ int forest_create_impl(gcdyn_ctx* ctx, const gcdyn_forest_desc* d, gcdyn_forest*
     UP(self_loop, d->self_loop ? d->self_loop : loop_all.data(), T);
     UP(item_off, item_off.data(), T + 1);
     UP(it_time, it_time.data(), n_items);
-    UP(it_tw, it_tw.data(), n_items);
-    UP(it_aux, it_aux.data(), n_items);
+    UP(it_meta, it_meta.data(), n_items);
     UP(n_death, n_death.data(), T);
     UP(n_surv, n_surv.data(), T);
 #undef UP
@@ -525,62 +564,27 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
     CU_TRY(ctx, cudaMemcpyAsync(ctx->params_blob.p, ctx->pin_in.p, L.n_doubles * 8, cudaMemcpyHostToDevice, st));
     const ParamsView pv = view_of(pr, L, ctx->params_blob.as<double>());
 
-    int S = o.steps > 0 ? o.steps : auto_steps(T, rate_max_of(pr), M);
     const bool want_rows = out_tree_pset || status;
     CU_TRY(ctx, ctx->out_pset.ensure((size_t)P * 8));
     if (status) CU_TRY(ctx, ctx->status.ensure((size_t)P * Tn * 4));
-    // pinned result staging: out_pset[P] | perr[P] | pstatus[P]
-    CU_TRY(ctx, ctx->pin_out.ensure((size_t)P * (8 + 8 + 4) + 64));
+    // pinned result staging
+    CU_TRY(ctx, ctx->pin_out.ensure((size_t)P * 8 + 64));
     double* h_out = reinterpret_cast<double*>(ctx->pin_out.p);
-    double* h_err = h_out + P;
-    int* h_pst = reinterpret_cast<int*>(h_err + P);
 
-    int total_launches = 0;
-    bool first = true;
-    std::vector<char> unconverged(P, 0);
-    for (int attempt = 0;; ++attempt) {
-        PsetPack pk{};
-        rc = enqueue_eval(ctx, f, pv, T, method, M, S, first, ctx->out_pset.as<double>(), nullptr,
-                          status ? ctx->status.as<int32_t>() : nullptr, st, &pk);
-        if (rc) return rc;
-        total_launches += ctx->last_launches;
-        first = false;
-        CU_TRY(ctx, cudaMemcpyAsync(h_out, ctx->out_pset.p, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
-        CU_TRY(ctx, cudaMemcpyAsync(h_err, pk.perr, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
-        CU_TRY(ctx, cudaMemcpyAsync(h_pst, pk.pstatus, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
-        CU_TRY(ctx, cudaStreamSynchronize(st));
-        if (method != GCDYN_METHOD_ODE) break;
-        bool need = false;
-        for (int p = 0; p < P; ++p) {
-            unconverged[p] = !(h_err[p] <= tol);
-            // a pset whose p left [0,1] may simply be under-resolved: refine it too
-            if (unconverged[p] || (h_pst[p] & ST_SOLVER)) need = true;
-        }
-        if (!need || (o.flags & GCDYN_FLAG_NO_REFINE) || o.steps > 0 || S >= S_CAP || attempt >= 6) break;
-        S = std::min<int>(S_CAP, S + S / 2 + 1);
-        // pstatus is sticky across attempts: clear it before re-running the trajectory
-        CU_TRY(ctx, cudaMemsetAsync(pk.pstatus, 0, (size_t)P * 4, st));
-    }
-    ctx->last_launches = total_launches;
-    std::memcpy(out_pset, h_out, (size_t)P * 8);
+    // one pass: every pset adapts its own step count inside traj_kernel (or uses opts->steps as given);
+    // a pset that cannot be resolved within the table capacity comes back as a solver failure (-Inf)
+    rc = enqueue_eval(ctx, f, pv, rate_max_of(pr), T, method, M, o.steps, tol, ctx->out_pset.as<double>(), nullptr,
+                      status ? ctx->status.as<int32_t>() : nullptr, st, nullptr);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(h_out, ctx->out_pset.p, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
     if (want_rows) {
         if (out_tree_pset)
             CU_TRY(ctx, cudaMemcpyAsync(out_tree_pset, ctx->out_tree.p, (size_t)P * Tn * 8, cudaMemcpyDeviceToHost, st));
         if (status)
             CU_TRY(ctx, cudaMemcpyAsync(status, ctx->status.p, (size_t)P * Tn * 4, cudaMemcpyDeviceToHost, st));
-        CU_TRY(ctx, cudaStreamSynchronize(st));
     }
-    if (method == GCDYN_METHOD_ODE) {
-        // psets still above tolerance at the cap count as a solver failure: density evaluates to zero
-        for (int p = 0; p < P; ++p) {
-            if (!unconverged[p] || (h_pst[p] & ST_SOLVER)) continue;
-            out_pset[p] = -INFINITY;
-            for (int64_t t = 0; t < Tn; ++t) {
-                if (out_tree_pset) out_tree_pset[(size_t)p * Tn + t] = -INFINITY;
-                if (status) status[(size_t)p * Tn + t] |= ST_SOLVER;
-            }
-        }
-    }
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    std::memcpy(out_pset, h_out, (size_t)P * 8);
     return GCDYN_OK;
 }
 
@@ -630,6 +634,7 @@ int gcdyn_ctx_create(int device, gcdyn_ctx** out) {
     gcdyn_ctx* ctx = new gcdyn_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(none, GCDYN_ECUDA, cudaGetErrorString(e)); }
     *out = ctx;
@@ -745,9 +750,9 @@ int gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcd
     if (M < 0) return fail(ctx, GCDYN_EINVAL, "order must be 0, 8, 12, 16, 20 or 24");
     if (o.steps < 0 || o.steps > S_CAP) return fail(ctx, GCDYN_EINVAL, "steps out of range");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    const int S = o.steps > 0 ? o.steps : auto_steps(present_time, dp->rate_max, M);
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
-    return enqueue_eval(ctx, f, dp->v, present_time, method, M, S, true, d_out_pset, d_out_tree_pset, d_status, st, nullptr);
+    return enqueue_eval(ctx, f, dp->v, dp->rate_max, present_time, method, M, o.steps, o.tol > 0.0 ? o.tol : 1e-11,
+                        d_out_pset, d_out_tree_pset, d_status, st, nullptr);
     GUARD_END(ctx)
 }
 
@@ -755,7 +760,16 @@ int gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_l
                     int32_t n_psets) {
     GUARD_BEGIN
     if (!ctx) return fail(ctx, GCDYN_EINVAL, "ctx is NULL");
-    if (steps) *steps = ctx->last_steps;
+    if (steps) {
+        *steps = ctx->last_steps;
+        if (ctx->last_order > 0 && ctx->last_pack.S && ctx->last_P > 0) {   // largest per-pset step count actually used
+            std::vector<int> hs(ctx->last_P);
+            CU_TRY(ctx, cudaSetDevice(ctx->device));
+            CU_TRY(ctx, cudaDeviceSynchronize());
+            CU_TRY(ctx, cudaMemcpy(hs.data(), ctx->last_pack.S, (size_t)ctx->last_P * 4, cudaMemcpyDeviceToHost));
+            *steps = *std::max_element(hs.begin(), hs.end());
+        }
+    }
     if (order) *order = ctx->last_order;
     if (n_launches) *n_launches = ctx->last_launches;
     if (err_indicator && n_psets > 0) {

@@ -85,6 +85,29 @@ def test_steps_refinement_and_explicit_steps(ctx):
     _check(forest, params, T, "ode", exp["ode_branch"], steps=64, order=16)
 
 
+def test_adaptive_steps_per_pset_and_global_table_path(ctx):
+    """Psets with very different rates in one batch: each adapts its own step count inside traj_kernel.
+    A table too large for shared memory (explicit steps=512) takes the global-memory lookup path."""
+    import oracle
+    rng = np.random.default_rng(15)
+    ts = np.linspace(-2, 2, 8)
+    base = gcdyn.SigmoidalBranchingProcess(1.5, 0.0, 2.5, 0.5, 1.0, 1.0, 0.5, 0.1, ts)
+    trees = gcdyn.rand_tree(base, 3.0, ts[3], 10, rng=rng)
+    models = [base,
+              gcdyn.SigmoidalBranchingProcess(1.5, 0.0, 12.0, 3.0, 6.0, 5.0, 0.5, 0.1, ts),     # fast rates
+              gcdyn.SigmoidalBranchingProcess(1.5, 0.0, 0.3, 0.05, 0.1, 0.1, 0.5, 0.1, ts),     # slow rates
+              gcdyn.SigmoidalBranchingProcess(3.0, 1.0, 6.0, 0.5, 1.0, 2.0, 1.0, 0.02, ts)]     # ρ=1, σ≈0: hardest cells
+    forest = gcdyn.Forest(trees, ts, 3.0, ctx=ctx)
+    want = np.array([oracle.loglikelihood_shared(m, trees, 3.0) for m in models])
+    out, _, st = evaluate(forest, pack_params(models), 3.0)
+    assert not st.any() and rel(out, want) <= SUM_RTOL
+    d = ctx.last_diag(len(models))
+    assert np.all(d["err_indicator"] <= 1e-11)
+    out512, _, st = evaluate(forest, pack_params(models), 3.0, steps=512)
+    assert not st.any() and rel(out512, want) <= SUM_RTOL
+    assert ctx.last_diag()["steps"] == 512
+
+
 def test_public_api_matches_oracle_on_simulated_trees(ctx):
     """The reference-style call `loglikelihood(model, trees, present_time)` on freshly simulated trees."""
     import oracle
