@@ -1,0 +1,292 @@
+// Chebyshev-moment formulation of the per-tree sums.
+//
+// F_x(τ) is smooth on [0, T], so for every parameter set it is represented by ONE Chebyshev series per type,
+//     F_x(τ) ≈ Σ_{d≤D} a[p][d][x] · T_d(u),  u = 2τ/T − 1,
+// and the per-tree sum over lookup items becomes a dense contraction with pset-independent per-tree
+// statistics Mt[t][d][x] = Σ_{items of tree t, type x} w · T_d(u_item):
+//     LL[p][t] = Σ_j A[p][j] · Mt[t][j],   j = [count columns | (d, x) Chebyshev columns]
+// i.e. a [P × J] · [J × T] FP64 GEMM executed with DMMA (mma.sync.m8n8k4.f64).  The count columns carry the
+// node terms of mbp.jl:167-191 (log λ_x per birth, log δΓ_xy per type change, log μ + log σ per sampled death,
+// log ρ per sampled survivor) and −log(1 − p_root(T)) (mbp.jl:244-245).  Psets whose series is not resolved,
+// or whose node-term logs are not finite where the forest needs them, are re-done by sweep_kernel.
+#pragma once
+#include "kernels.cuh"
+
+namespace gcdyn {
+
+struct MomentView {
+    int K;
+    int C;                 // count columns: K (births) + K*K (type changes) + 2 (deaths, survivors) + K (root one-hot)
+    int Dcap;              // moments exist for d = 0..Dcap
+    long long Jst;         // row stride of Mt and A (doubles), multiple of 4
+    const double* Mt;      // [T][Jst]
+    const double* colsum;  // [C] forest-level sums of the count columns
+};
+
+struct ChebCfg {
+    double T;
+    double tol;            // accepted Chebyshev tail (absolute, on F)
+    int D;                 // interpolation degree (≤ Dcap), even
+    long long tab_stride;
+};
+
+// ------------------------------------------------------------------------------------------------
+// moments_kernel: one CTA per tree (run once per forest and present_time).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) moments_kernel(ForestView fv, double T, int Dcap, long long Jst, double* __restrict__ Mt) {
+    extern __shared__ __align__(16) double sm[];
+    const int K = fv.K;
+    const int C = 2 * K + K * K + 2;
+    const int64_t t = blockIdx.x;
+    int* cnt = reinterpret_cast<int*>(sm);                  // [C] integer counts
+    double* acc = sm + ((C + 1) / 2);                       // [(Dcap+1)*K]
+    for (int i = threadIdx.x; i < C; i += blockDim.x) cnt[i] = 0;
+    for (int i = threadIdx.x; i < (Dcap + 1) * K; i += blockDim.x) acc[i] = 0.0;
+    __syncthreads();
+    // node-term counts over live nodes (integer atomics: exact, order-independent)
+    for (int64_t i = fv.tree_off[t] + threadIdx.x; i < fv.tree_off[t + 1]; i += blockDim.x) {
+        if (!fv.live[i]) continue;
+        const int ev = fv.event[i], x = fv.btype_idx[i], y = fv.type_idx[i];
+        if (ev == EV_BIRTH) atomicAdd(&cnt[x], 1);
+        else if (ev == EV_TC) atomicAdd(&cnt[K + x * K + y], 1);
+        else if (ev == EV_SDEATH) atomicAdd(&cnt[K + K * K], 1);
+        else if (ev == EV_SSURV) atomicAdd(&cnt[K + K * K + 1], 1);
+    }
+    if (threadIdx.x == 0) {
+        const int rt = fv.root_type[t];
+        if (rt >= 0) cnt[K + K * K + 2 + rt] = 1;
+    }
+    // Chebyshev moments: thread x owns column x and walks the tree's items in order (deterministic)
+    const int64_t i0 = fv.item_off[t], i1 = fv.item_off[t + 1];
+    for (int x = threadIdx.x; x < K; x += blockDim.x) {
+        for (int64_t i = i0; i < i1; ++i) {
+            const int2 me = fv.it_meta[i];
+            if ((me.x & 0xffffff) != x) continue;
+            const double w = (double)(me.x >> 24);
+            const double u = 2.0 * (T - fv.it_time[i]) / T - 1.0;
+            double tm = 1.0, tc = u;
+            acc[x] += w;
+            for (int d = 1; d <= Dcap; ++d) {
+                acc[d * K + x] = fma(w, tc, acc[d * K + x]);
+                const double tn = fma(2.0 * u, tc, -tm);
+                tm = tc;
+                tc = tn;
+            }
+        }
+    }
+    __syncthreads();
+    double* row = Mt + (size_t)t * Jst;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) row[i] = (double)cnt[i];
+    for (int i = threadIdx.x; i < (Dcap + 1) * K; i += blockDim.x) row[C + i] = acc[i];
+    for (long long i = C + (long long)(Dcap + 1) * K + threadIdx.x; i < Jst; i += blockDim.x) row[i] = 0.0;
+}
+
+// column sums of the count part: colsum[c] = Σ_t Mt[t][c]  (one thread per column, fixed order)
+__global__ void colsum_kernel(const double* __restrict__ Mt, int64_t T, long long Jst, int C, double* __restrict__ colsum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int64_t t = 0; t < T; ++t) s += Mt[(size_t)t * Jst + c];
+    colsum[c] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cheb_kernel: one CTA per pset.  Values of F_x at the D+1 Chebyshev–Gauss–Lobatto nodes from the pset's
+// Taylor table, DCT-I → a[d][x]; effective degree; count-column coefficients; fallback flag.
+//   A[p][c] (c < C)            = node-term logs (non-finite entries the forest uses → flag, stored as 0)
+//   A[p][C + d*K + x]          = a[d][x] for d ≤ D_eff[p], 0 above
+// ------------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(256) cheb_kernel(PsetPack pk, MomentView mv, ChebCfg cfg, const double* __restrict__ tab,
+                                                   double* __restrict__ A, int* __restrict__ need_sweep,
+                                                   int* __restrict__ d_common) {
+    extern __shared__ __align__(16) double sm[];
+    constexpr int L = M + 2;
+    const int p = blockIdx.x;
+    const int K = mv.K, C = mv.C, D = cfg.D;
+    double* costab = sm;                   // [2D]  cos(π m / D)
+    double* V = costab + 2 * D;            // [(D+1)*K] node values, later coefficients
+    double* Acoef = V + (size_t)(D + 1) * K;   // [(D+1)*K]
+    __shared__ int s_deff, s_flag;
+    const int S = pk.S[p];
+    const int pst = pk.pstatus[p];
+    if (threadIdx.x == 0) { s_deff = 8; s_flag = (pst & ST_SOLVER) ? 1 : 0; }
+    for (int m = threadIdx.x; m < 2 * D; m += blockDim.x) costab[m] = cospi((double)m / (double)D);
+    __syncthreads();
+    const double* tp = tab + (size_t)p * cfg.tab_stride;
+    const double scale = (double)S / cfg.T;
+    if (!(pst & ST_SOLVER)) {
+        for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
+            const int k = idx / K, x = idx - k * K;
+            const double tau = cfg.T * (1.0 + costab[k]) * 0.5;
+            const double u = tau * scale;
+            int s = (int)u;
+            s = s > S - 1 ? S - 1 : (s < 0 ? 0 : s);
+            V[idx] = eval_row<M, false>(tp + ((size_t)s * K + x) * L, u - (double)s);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) V[idx] = 0.0;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
+        const int d = idx / K, x = idx - d * K;
+        double s0 = 0.0, s1 = 0.0;
+        int m = 0;                                   // (k*d) mod 2D, advanced incrementally
+        for (int k = 0; k <= D; ++k) {
+            double v = V[k * K + x];
+            if (k == 0 || k == D) v *= 0.5;
+            if (k & 1) s1 = fma(v, costab[m], s1); else s0 = fma(v, costab[m], s0);
+            m += d;
+            if (m >= 2 * D) m -= 2 * D;
+        }
+        double a = (2.0 / (double)D) * (s0 + s1);
+        if (d == 0 || d == D) a *= 0.5;
+        Acoef[idx] = a;
+    }
+    __syncthreads();
+    // effective degree per type: smallest d with Σ_{k>d}|a_k| ≤ tol; unresolved if the last three terms are not small
+    for (int x = threadIdx.x; x < K; x += blockDim.x) {
+        const double last3 = fabs(Acoef[D * K + x]) + fabs(Acoef[(D - 1) * K + x]) + fabs(Acoef[(D - 2) * K + x]);
+        if (!(last3 <= cfg.tol)) atomicExch(&s_flag, 1);
+        double tail = 0.0;
+        int d = D;
+        while (d > 8) {
+            tail += fabs(Acoef[d * K + x]);
+            if (!(tail <= cfg.tol)) break;
+            --d;
+        }
+        atomicMax(&s_deff, d);
+    }
+    __syncthreads();
+    const int deff = s_deff;
+    double* Arow = A + (size_t)p * mv.Jst;
+    for (int idx = threadIdx.x; idx < (mv.Dcap + 1) * K; idx += blockDim.x) {
+        const int d = idx / K;
+        Arow[C + idx] = (d <= deff && d <= D) ? Acoef[idx] : 0.0;
+    }
+    for (long long i = C + (long long)(mv.Dcap + 1) * K + threadIdx.x; i < mv.Jst; i += blockDim.x) Arow[i] = 0.0;
+    // count columns: [log λ_x | log δΓ_xy | log μ + log σ | log ρ | −log(1 − p_x(T))]
+    const double* nt = pk.nt + (size_t)p * pk.ntw;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double v;
+        if (c < K + K * K + 2) v = nt[c];
+        else v = -pk.logcond[(size_t)p * K + (c - (K + K * K + 2))];
+        const bool diag = c >= K && c < K + K * K && ((c - K) / K == (c - K) % K);   // self-loop column: trees using it are −Inf anyway
+        if (!isfinite(v)) {
+            if (!diag && mv.colsum[c] != 0.0) atomicExch(&s_flag, 1);
+            v = 0.0;
+        }
+        Arow[c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        need_sweep[p] = s_flag;
+        if (!s_flag) atomicMax(d_common, deff);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gemm_kernel: out[p][t] = Σ_{j<J} A[p][j]·Mt[t][j] with DMMA.  CTA tile 32(p) × 32(t), 4 warps of 16×16,
+// k-chunks of 32 staged through shared memory with cp.async (2 stages), row stride 36 doubles
+// (conflict-free for the m8n8k4 fragment pattern: row = lane/4, k = lane%4).
+// ------------------------------------------------------------------------------------------------
+constexpr int GT_TILE = 32, GT_KC = 32, GT_LD = 36;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A, const double* __restrict__ Mt, long long Jst,
+                                                   int C, int K, const int* __restrict__ d_common, int P, int64_t T,
+                                                   const int* __restrict__ pstatus, const int* __restrict__ need_sweep,
+                                                   const uint8_t* __restrict__ self_loop, double* __restrict__ out_tree,
+                                                   int32_t* __restrict__ status) {
+    __shared__ __align__(16) double As[2][GT_TILE * GT_LD];
+    __shared__ __align__(16) double Bs[2][GT_TILE * GT_LD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p0 = blockIdx.y * GT_TILE;
+    const int64_t t0 = (int64_t)blockIdx.x * GT_TILE;
+    long long J = C + (long long)(*d_common + 1) * K;
+    J = (J + 3) & ~3LL;
+    if (J > Jst) J = Jst;
+    const int nchunks = (int)((J + GT_KC - 1) / GT_KC);
+    // this thread's cp.async assignments: 32 rows × 16 segments of 16 B per operand = 512 per tile, 4 per thread
+    auto issue = [&](int chunk, int buf) {
+        const long long j0 = (long long)chunk * GT_KC;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int seg = tid + r * 128;
+            const int row = seg >> 4, col = (seg & 15) * 2;          // col in doubles
+            const long long j = j0 + col;
+            const bool inj = j < J;
+            const bool va = inj && (p0 + row) < P;
+            const bool vb = inj && (t0 + row) < T;
+            const double* sa = A + (size_t)(va ? p0 + row : 0) * Jst + (va ? j : 0);
+            const double* sb = Mt + (size_t)(vb ? t0 + row : 0) * Jst + (vb ? j : 0);
+            cp_async16(&As[buf][row * GT_LD + col], sa, va);
+            cp_async16(&Bs[buf][row * GT_LD + col], sb, vb);
+        }
+        cp_async_commit();
+    };
+    double acc[2][2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const int wr = (warp >> 1) * 16, wc = (warp & 1) * 16;     // warp's 16×16 sub-tile (p rows, t cols)
+    const int fr = lane >> 2, fk = lane & 3;
+    if (nchunks > 0) issue(0, 0);
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        if (ch + 1 < nchunks) { issue(ch + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const double* as = As[buf];
+        const double* bs = Bs[buf];
+#pragma unroll
+        for (int kk = 0; kk < GT_KC / 4; ++kk) {
+            const double a0 = as[(wr + fr) * GT_LD + kk * 4 + fk];
+            const double a1 = as[(wr + 8 + fr) * GT_LD + kk * 4 + fk];
+            const double b0 = bs[(wc + fr) * GT_LD + kk * 4 + fk];
+            const double b1 = bs[(wc + 8 + fr) * GT_LD + kk * 4 + fk];
+            dmma_m8n8k4(acc[0][0][0], acc[0][0][1], a0, b0);
+            dmma_m8n8k4(acc[0][1][0], acc[0][1][1], a0, b1);
+            dmma_m8n8k4(acc[1][0][0], acc[1][0][1], a1, b0);
+            dmma_m8n8k4(acc[1][1][0], acc[1][1][1], a1, b1);
+        }
+        __syncthreads();
+    }
+    // epilogue: C fragment (row = lane/4, cols = 2*(lane%4) + {0,1})
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int p = p0 + wr + 8 * a + fr;
+        if (p >= P) continue;
+        const int pst = pstatus[p];
+        if (need_sweep[p] && !(pst & ST_SOLVER)) continue;      // sweep_kernel rewrites this pset's row
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t t = t0 + wc + 8 * b + 2 * fk + e;
+                if (t >= T) continue;
+                double r = acc[a][b][e];
+                int st = pst;
+                if (self_loop[t]) st |= ST_SELF_LOOP;
+                if (st & (ST_SELF_LOOP | ST_SOLVER)) r = -CUDART_INF;
+                else if (r != r) st |= ST_DOMAIN;
+                out_tree[(size_t)p * T + t] = r;
+                if (status) status[(size_t)p * T + t] = st;
+            }
+        }
+    }
+}
+
+}  // namespace gcdyn

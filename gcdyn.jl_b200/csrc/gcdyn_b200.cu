@@ -3,6 +3,7 @@
 // leaves this file: every extern "C" entry point catches and converts to a GCDYN_E* code.
 #include "../../include/gcdyn_b200.h"
 #include "kernels.cuh"
+#include "cheb_gemm.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -58,14 +59,15 @@ struct gcdyn_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     // workspace (grow-only)
-    DevBuf params_blob, pack, table, out_tree, out_pset, status, probe;
+    DevBuf params_blob, pack, table, out_tree, out_pset, status, probe, gemm_a, flags;
     PinBuf pin_in, pin_out;
     // diagnostics of the last evaluation
     int last_steps = 0, last_order = 0, last_launches = 0, last_P = 0;
     PsetPack last_pack{};
     // optional per-kernel timing (CUDA events on the launching stream)
     bool profile = false;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int last_cheb_D = 0;
     bool ev_valid = false;
 };
 
@@ -76,6 +78,11 @@ struct gcdyn_forest {
     int64_t n_chunks = 0;
     int64_t* d_chunk_off = nullptr;
     int64_t max_tree_items = 0;
+    // Chebyshev moments of the forest for one present_time (built lazily, cached)
+    mutable MomentView mom{};
+    mutable double mom_T = -1.0;
+    mutable double* d_Mt = nullptr;
+    mutable double* d_colsum = nullptr;
 };
 
 struct gcdyn_dparams {
@@ -293,7 +300,8 @@ int launch_traj(gcdyn_ctx* ctx, int M, const ParamsView& pv, const PsetPack& pk,
 
 template <int M>
 int launch_sweep_m(gcdyn_ctx* ctx, const gcdyn_forest* f, const PsetPack& pk, const double* tab, long long tab_stride,
-                   double T, int P, size_t want_smem, double* out_tree, int32_t* status, cudaStream_t st) {
+                   double T, int P, size_t want_smem, const int* only_flagged, double* out_tree, int32_t* status,
+                   cudaStream_t st) {
     // dynamic shared memory = staging buffer for one pset's table (bulk-copied); psets whose table is
     // larger than the buffer are read from global memory by the same kernel
     size_t smem = std::min(std::max(want_smem, (size_t)64 * 1024), (size_t)ctx->smem_optin - 2048);
@@ -306,28 +314,91 @@ int launch_sweep_m(gcdyn_ctx* ctx, const gcdyn_forest* f, const PsetPack& pk, co
     const long long units = (long long)P * f->n_chunks;
     const long long grid = std::max<long long>(1, std::min<long long>(units, (long long)ctx->sm_count * per_sm));
     sweep_kernel<M><<<(unsigned)grid, SWEEP_THREADS, smem, st>>>(f->v, pk, tab, tab_stride, f->d_chunk_off, (int)f->n_chunks, P, T,
-                                                      (int)(smem / 8), out_tree, status);
+                                                      (int)(smem / 8), only_flagged, out_tree, status);
     CU_TRY(ctx, cudaGetLastError());
     return GCDYN_OK;
 }
 
 int launch_sweep(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& pk, const double* tab,
-                 long long tab_stride, double T, int P, size_t want_smem, double* out_tree, int32_t* status,
-                 cudaStream_t st) {
+                 long long tab_stride, double T, int P, size_t want_smem, const int* only_flagged, double* out_tree,
+                 int32_t* status, cudaStream_t st) {
     switch (M) {
-        case 8: return launch_sweep_m<8>(ctx, f, pk, tab, tab_stride, T, P, want_smem, out_tree, status, st);
-        case 12: return launch_sweep_m<12>(ctx, f, pk, tab, tab_stride, T, P, want_smem, out_tree, status, st);
-        case 16: return launch_sweep_m<16>(ctx, f, pk, tab, tab_stride, T, P, want_smem, out_tree, status, st);
-        case 20: return launch_sweep_m<20>(ctx, f, pk, tab, tab_stride, T, P, want_smem, out_tree, status, st);
-        case 24: return launch_sweep_m<24>(ctx, f, pk, tab, tab_stride, T, P, want_smem, out_tree, status, st);
+        case 8: return launch_sweep_m<8>(ctx, f, pk, tab, tab_stride, T, P, want_smem, only_flagged, out_tree, status, st);
+        case 12: return launch_sweep_m<12>(ctx, f, pk, tab, tab_stride, T, P, want_smem, only_flagged, out_tree, status, st);
+        case 16: return launch_sweep_m<16>(ctx, f, pk, tab, tab_stride, T, P, want_smem, only_flagged, out_tree, status, st);
+        case 20: return launch_sweep_m<20>(ctx, f, pk, tab, tab_stride, T, P, want_smem, only_flagged, out_tree, status, st);
+        case 24: return launch_sweep_m<24>(ctx, f, pk, tab, tab_stride, T, P, want_smem, only_flagged, out_tree, status, st);
     }
     return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
+}
+
+// Chebyshev interpolation degree for this batch: generous (the kernel trims to the effective degree),
+// even, ≤ the moment cap and small enough for cheb_kernel's shared memory.
+int cheb_degree(double T, double rate_max, int K, int Dcap, int smem_optin) {
+    double want = T * rate_max + 24.0;
+    if (!(want == want)) want = 32.0;
+    const int ladder[] = {24, 32, 48, 64, 96, 128};
+    int D = 128;
+    for (int d : ladder) if ((double)d >= want) { D = d; break; }
+    D = std::min(D, Dcap);
+    while (D > 16 && (2 * (size_t)D + 2 * (size_t)(D + 1) * K) * 8 + 1024 > (size_t)smem_optin) D -= 8;
+    return D & ~1;
+}
+
+template <int M>
+int launch_cheb_m(gcdyn_ctx* ctx, const PsetPack& pk, const MomentView& mv, const ChebCfg& cc, const double* tab, double* A,
+                  int* need_sweep, int* d_common, int P, cudaStream_t st) {
+    const size_t smem = (2 * (size_t)cc.D + 2 * (size_t)(cc.D + 1) * mv.K) * 8;
+    if (smem > 48 * 1024)
+        CU_TRY(ctx, cudaFuncSetAttribute(cheb_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cheb_kernel<M><<<P, 256, smem, st>>>(pk, mv, cc, tab, A, need_sweep, d_common);
+    CU_TRY(ctx, cudaGetLastError());
+    return GCDYN_OK;
+}
+
+int launch_cheb(gcdyn_ctx* ctx, int M, const PsetPack& pk, const MomentView& mv, const ChebCfg& cc, const double* tab,
+                double* A, int* need_sweep, int* d_common, int P, cudaStream_t st) {
+    switch (M) {
+        case 8: return launch_cheb_m<8>(ctx, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
+        case 12: return launch_cheb_m<12>(ctx, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
+        case 16: return launch_cheb_m<16>(ctx, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
+        case 20: return launch_cheb_m<20>(ctx, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
+        case 24: return launch_cheb_m<24>(ctx, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
+    }
+    return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
+}
+
+// Build (once per forest and present_time) the per-tree Chebyshev moments and count columns.
+int ensure_moments(gcdyn_ctx* ctx, const gcdyn_forest* f, double T, cudaStream_t st, int* launches) {
+    if (f->mom.Mt && f->mom_T == T) return GCDYN_OK;
+    const int K = f->v.K;
+    const int Dcap = 128;
+    const int C = 2 * K + K * K + 2;
+    long long Jst = C + (long long)(Dcap + 1) * K;
+    Jst = (Jst + 3) & ~3LL;
+    const int64_t Tn = f->v.n_trees;
+    if (!f->d_Mt) {
+        CU_TRY(ctx, cudaMalloc(&f->d_Mt, std::max<size_t>((size_t)Tn * (size_t)Jst * 8, 8)));
+        CU_TRY(ctx, cudaMalloc(&f->d_colsum, (size_t)C * 8));
+    }
+    const size_t smem = ((size_t)(C + 1) / 2 + (size_t)(Dcap + 1) * K) * 8;
+    if (smem > (size_t)ctx->smem_optin) return fail(ctx, GCDYN_EUNSUPPORTED, "n_types too large for the moment kernel");
+    if (smem > 48 * 1024)
+        CU_TRY(ctx, cudaFuncSetAttribute(moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    moments_kernel<<<(unsigned)Tn, 128, smem, st>>>(f->v, T, Dcap, Jst, f->d_Mt);
+    CU_TRY(ctx, cudaGetLastError());
+    colsum_kernel<<<(C + 127) / 128, 128, 0, st>>>(f->d_Mt, Tn, Jst, C, f->d_colsum);
+    CU_TRY(ctx, cudaGetLastError());
+    *launches += 2;
+    f->mom.K = K; f->mom.C = C; f->mom.Dcap = Dcap; f->mom.Jst = Jst; f->mom.Mt = f->d_Mt; f->mom.colsum = f->d_colsum;
+    f->mom_T = T;
+    return GCDYN_OK;
 }
 
 // Enqueue one evaluation on `st`.  All pointers are device pointers; d_out_tree/d_status may be null.
 // S_fixed > 0 pins the number of Taylor cells; otherwise every pset adapts it inside traj_kernel.
 int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, double rate_max, double T, int method,
-                 int M, int S_fixed, double tol, double* d_out_pset, double* d_out_tree, int32_t* d_status,
+                 int M, int S_fixed, double tol, int flags, double* d_out_pset, double* d_out_tree, int32_t* d_status,
                  cudaStream_t st, PsetPack* pk_out) {
     const int P = pv.P, K = pv.K;
     if (P > 65535) return fail(ctx, GCDYN_EUNSUPPORTED, "more than 65535 parameter sets per call");
@@ -358,10 +429,46 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         if (rc) return rc;
         ++launches;
         if (prof) cudaEventRecord(ctx->ev[2], st);
+        // ---- per-tree sums: Chebyshev-moment GEMM (DMMA), with the item sweep as exact fallback
+        const bool use_gemm = !(flags & GCDYN_FLAG_SWEEP_ONLY) && Tn > 0 &&
+                              (P >= 8 || (f->mom.Mt && f->mom_T == T));
+        const int* only_flagged = nullptr;
+        if (use_gemm) {
+            rc = ensure_moments(ctx, f, T, st, &launches);
+            if (rc) return rc;
+            const MomentView& mv = f->mom;
+            CU_TRY(ctx, ctx->gemm_a.ensure((size_t)P * (size_t)mv.Jst * 8));
+            CU_TRY(ctx, ctx->flags.ensure((size_t)(P + 1) * 4));
+            int* need_sweep = ctx->flags.as<int>();
+            int* d_common = need_sweep + P;
+            CU_TRY(ctx, cudaMemsetAsync(d_common, 0, 4, st));
+            ChebCfg cc{};
+            cc.T = T;
+            cc.tol = 1e-11;
+            cc.tab_stride = cfg.tab_stride;
+            cc.D = cheb_degree(T, rate_max, K, mv.Dcap, ctx->smem_optin);
+            rc = launch_cheb(ctx, M, pk, mv, cc, ctx->table.as<double>(), ctx->gemm_a.as<double>(), need_sweep, d_common,
+                             P, st);
+            if (rc) return rc;
+            ++launches;
+            if (prof) cudaEventRecord(ctx->ev[3], st);
+            dim3 grid((unsigned)((Tn + GT_TILE - 1) / GT_TILE), (unsigned)((P + GT_TILE - 1) / GT_TILE));
+            gemm_kernel<<<grid, 128, 0, st>>>(ctx->gemm_a.as<double>(), mv.Mt, mv.Jst, mv.C, K, d_common, P, Tn, pk.pstatus,
+                                              need_sweep, f->v.self_loop, d_out_tree, d_status);
+            CU_TRY(ctx, cudaGetLastError());
+            ++launches;
+            only_flagged = need_sweep;
+            ctx->last_cheb_D = cc.D;
+
+        } else {
+            ctx->last_cheb_D = 0;
+            if (prof) cudaEventRecord(ctx->ev[3], st);
+        }
+        if (prof) cudaEventRecord(ctx->ev[4], st);
         const int S_stage = S_fixed > 0 ? S_fixed : std::min(cfg.S_cap, expected_steps(T, rate_max, M));
         const size_t want_smem = (size_t)S_stage * K * L * 8;
-        rc = launch_sweep(ctx, M, f, pk, ctx->table.as<double>(), cfg.tab_stride, T, P, want_smem, d_out_tree,
-                          d_status, st);
+        rc = launch_sweep(ctx, M, f, pk, ctx->table.as<double>(), cfg.tab_stride, T, P, want_smem, only_flagged,
+                          d_out_tree, d_status, st);
         if (rc) return rc;
         ++launches;
         ctx->last_steps = cfg.S_cap;
@@ -375,18 +482,18 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             CU_TRY(ctx, cudaGetLastError());
             ++launches;
         }
-        if (prof) cudaEventRecord(ctx->ev[2], st);
+        if (prof) { cudaEventRecord(ctx->ev[2], st); cudaEventRecord(ctx->ev[3], st); cudaEventRecord(ctx->ev[4], st); }
         dim3 grid((unsigned)f->n_chunks, (unsigned)P);
         alt_kernel<<<grid, 256, 0, st>>>(f->v, pv, pk, f->d_chunk_off, T, method, d_out_tree, d_status);
         CU_TRY(ctx, cudaGetLastError());
         ++launches;
         ctx->last_steps = 0;
     }
-    if (prof) cudaEventRecord(ctx->ev[3], st);
+    if (prof) cudaEventRecord(ctx->ev[5], st);
     reduce_kernel<<<P, 256, 0, st>>>(d_out_tree, Tn, d_out_pset);
     CU_TRY(ctx, cudaGetLastError());
     ++launches;
-    if (prof) { cudaEventRecord(ctx->ev[4], st); ctx->ev_valid = true; }
+    if (prof) { cudaEventRecord(ctx->ev[6], st); ctx->ev_valid = true; }
     ctx->last_order = method == GCDYN_METHOD_ODE ? M : 0;
     ctx->last_launches = launches;
     ctx->last_P = P;
@@ -411,6 +518,8 @@ void free_forest(gcdyn_forest* f) {
     cudaGetDevice(&prev);
     cudaSetDevice(f->device);
     for (void* p : f->allocs) cudaFree(p);
+    if (f->d_Mt) cudaFree(f->d_Mt);
+    if (f->d_colsum) cudaFree(f->d_colsum);
     cudaSetDevice(prev);
     delete f;
 }
@@ -573,7 +682,7 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
 
     // one pass: every pset adapts its own step count inside traj_kernel (or uses opts->steps as given);
     // a pset that cannot be resolved within the table capacity comes back as a solver failure (-Inf)
-    rc = enqueue_eval(ctx, f, pv, rate_max_of(pr), T, method, M, o.steps, tol, ctx->out_pset.as<double>(), nullptr,
+    rc = enqueue_eval(ctx, f, pv, rate_max_of(pr), T, method, M, o.steps, tol, o.flags, ctx->out_pset.as<double>(), nullptr,
                       status ? ctx->status.as<int32_t>() : nullptr, st, nullptr);
     if (rc) return rc;
     CU_TRY(ctx, cudaMemcpyAsync(h_out, ctx->out_pset.p, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
@@ -650,7 +759,7 @@ void gcdyn_ctx_destroy(gcdyn_ctx* ctx) {
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     ctx->params_blob.release(); ctx->pack.release(); ctx->table.release(); ctx->out_tree.release();
-    ctx->out_pset.release(); ctx->status.release(); ctx->probe.release();
+    ctx->out_pset.release(); ctx->status.release(); ctx->probe.release(); ctx->gemm_a.release(); ctx->flags.release();
     ctx->pin_in.release(); ctx->pin_out.release();
     cudaSetDevice(prev);
     delete ctx;
@@ -752,7 +861,7 @@ int gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcd
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
     return enqueue_eval(ctx, f, dp->v, dp->rate_max, present_time, method, M, o.steps, o.tol > 0.0 ? o.tol : 1e-11,
-                        d_out_pset, d_out_tree_pset, d_status, st, nullptr);
+                        o.flags, d_out_pset, d_out_tree_pset, d_status, st, nullptr);
     GUARD_END(ctx)
 }
 
@@ -782,6 +891,25 @@ int gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_l
     GUARD_END(ctx)
 }
 
+int gcdyn_last_cheb_degree(gcdyn_ctx* ctx, int32_t* interp_degree, int32_t* effective_degree, int32_t* n_fallback) {
+    GUARD_BEGIN
+    if (!ctx) return fail(ctx, GCDYN_EINVAL, "ctx is NULL");
+    if (interp_degree) *interp_degree = ctx->last_cheb_D;
+    if ((effective_degree || n_fallback) && ctx->last_cheb_D > 0 && ctx->flags.p && ctx->last_P > 0) {
+        std::vector<int> h(ctx->last_P + 1);
+        CU_TRY(ctx, cudaSetDevice(ctx->device));
+        CU_TRY(ctx, cudaDeviceSynchronize());
+        CU_TRY(ctx, cudaMemcpy(h.data(), ctx->flags.p, (size_t)(ctx->last_P + 1) * 4, cudaMemcpyDeviceToHost));
+        if (effective_degree) *effective_degree = h[ctx->last_P];
+        if (n_fallback) { int n = 0; for (int p = 0; p < ctx->last_P; ++p) n += h[p] != 0; *n_fallback = n; }
+    } else {
+        if (effective_degree) *effective_degree = 0;
+        if (n_fallback) *n_fallback = 0;
+    }
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
 int gcdyn_set_profiling(gcdyn_ctx* ctx, int on) {
     GUARD_BEGIN
     if (!ctx) return fail(ctx, GCDYN_EINVAL, "ctx is NULL");
@@ -799,8 +927,8 @@ int gcdyn_last_kernel_ms(gcdyn_ctx* ctx, float* ms) {
     if (!ctx || !ms) return fail(ctx, GCDYN_EINVAL, "NULL argument");
     if (!ctx->ev_valid) return fail(ctx, GCDYN_EINVAL, "no profiled evaluation to report on");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    CU_TRY(ctx, cudaEventSynchronize(ctx->ev[4]));
-    for (int i = 0; i < 4; ++i) CU_TRY(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
+    CU_TRY(ctx, cudaEventSynchronize(ctx->ev[6]));
+    for (int i = 0; i < 6; ++i) CU_TRY(ctx, cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]));
     return GCDYN_OK;
     GUARD_END(ctx)
 }

@@ -453,7 +453,9 @@ template <int M>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(ForestView fv, PsetPack pk, const double* __restrict__ tab,
                                                     long long tab_stride, const int64_t* __restrict__ chunk_off,
                                                     int n_chunks, int P, double T, int smem_doubles,
+                                                    const int* __restrict__ only_flagged,
                                                     double* __restrict__ out_tree, int32_t* __restrict__ status) {
+    // only_flagged != nullptr: fallback mode — redo just the psets the Chebyshev/GEMM path could not take
     extern __shared__ __align__(128) double stab[];
     __shared__ __align__(8) uint64_t mbar;
     constexpr int L = M + 2;
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(ForestView fv, 
     if (threadIdx.x == 0) mbar_init(&mbar, 1);
     __syncthreads();
     uint32_t parity = 0;
-    int cur_p = -1, S = 1, pst = 0;
+    int cur_p = -1, S = 1, pst = 0, flag_p = -1, flag_v = 0;
     bool in_smem = false;
     const double* tp = nullptr;
     const double* nt = nullptr;
@@ -472,6 +474,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(ForestView fv, 
     for (long long u = u_lo; u < u_hi; ++u) {
         const int p = (int)(u / n_chunks);
         const int ch = (int)(u - (long long)p * n_chunks);
+        if (only_flagged) {                                  // CTA-uniform; one flag load per pset, not per unit
+            if (p != flag_p) { flag_p = p; flag_v = only_flagged[p]; }
+            if (!flag_v) { u = (long long)(p + 1) * n_chunks - 1; continue; }   // jump to the next pset's units
+        }
         if (p != cur_p) {
             __syncthreads();                       // every warp is done with the previous table
             cur_p = p;

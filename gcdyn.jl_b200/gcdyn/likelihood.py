@@ -25,7 +25,7 @@ __all__ = ["loglikelihood", "naive_loglikelihood", "stadler_appx_loglikelihood",
 
 METHOD_CODE = {"ode": 0, "naive": 1, "stadler": 2, "stadler_unconditioned": 3}
 STATUS_SELF_LOOP, STATUS_SOLVER, STATUS_DOMAIN = 1, 2, 4
-FLAG_NO_REFINE, FLAG_TOTALS_VIA_MOMENTS = 1, 2
+FLAG_NO_REFINE, FLAG_SWEEP_ONLY = 1, 4
 
 _ERRNAMES = {-1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "EUNSUPPORTED", -5: "ENODEVICE",
              -6: "ENOTCONVERGED"}
@@ -110,6 +110,7 @@ def _lib():
                                                   vp, vp, vp, vp]),
         "gcdyn_last_diag": (C.c_int, [vp, _p_i32, _p_i32, _p_i32, _p_f64, C.c_int32]),
         "gcdyn_probe_fp64_peak": (C.c_int, [vp, _p_f64]),
+        "gcdyn_last_cheb_degree": (C.c_int, [vp, _p_i32, _p_i32, _p_i32]),
         "gcdyn_set_profiling": (C.c_int, [vp, C.c_int]),
         "gcdyn_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     }
@@ -172,14 +173,20 @@ class Context:
                                       _ptr(err, _p_f64) if n_psets else _p_f64(), int(n_psets)), self._h)
         return dict(steps=s.value, order=o.value, n_launches=nl.value, err_indicator=err[:n_psets])
 
+    def last_cheb(self):
+        """Chebyshev/GEMM stage of the last ODE evaluation (all zeros if it did not run)."""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        _check(_lib().gcdyn_last_cheb_degree(self._h, C.byref(a), C.byref(b), C.byref(c)), self._h)
+        return dict(interp_degree=a.value, effective_degree=b.value, n_fallback=c.value)
+
     def set_profiling(self, on=True):
         _check(_lib().gcdyn_set_profiling(self._h, 1 if on else 0), self._h)
 
     def last_kernel_ms(self):
         """(prep, trajectory, sweep, reduce) durations of the last evaluation, CUDA-event timed."""
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 6)()
         _check(_lib().gcdyn_last_kernel_ms(self._h, ms), self._h)
-        return dict(zip(("prep", "trajectory", "sweep", "reduce"), (float(x) for x in ms)))
+        return dict(zip(("prep", "trajectory", "chebyshev", "gemm", "sweep", "reduce"), (float(x) for x in ms)))
 
     def probe_fp64_peak(self):
         v = C.c_double()

@@ -125,7 +125,7 @@ typedef struct {
 } gcdyn_opts;
 
 #define GCDYN_FLAG_NO_REFINE 1  /* do not re-run with more steps when the indicator exceeds tol */
-#define GCDYN_FLAG_TOTALS_VIA_MOMENTS 2  /* out_pset from forest moments (no per-tree pass)      */
+#define GCDYN_FLAG_SWEEP_ONLY 4 /* per-tree sums by the item sweep only (skip the Chebyshev-moment GEMM) */
 
 int  gcdyn_version(void);
 int  gcdyn_device_count(void);
@@ -168,9 +168,13 @@ int  gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* forest, con
 int  gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_launches,
                      double* err_indicator, int32_t n_psets);
 
+/* Chebyshev/GEMM stage of the last ODE evaluation: interpolation degree, effective degree used by the
+ * GEMM (max over psets), and how many psets fell back to the item sweep.  All 0 if the stage did not run. */
+int  gcdyn_last_cheb_degree(gcdyn_ctx* ctx, int32_t* interp_degree, int32_t* effective_degree, int32_t* n_fallback);
+
 /* Per-kernel timing for the roofline report: when on, every evaluation brackets its kernels with CUDA
  * events on the launching stream; gcdyn_last_kernel_ms waits for the last evaluation and returns
- * ms[4] = {prep, trajectory (or Stadler conditioning), sweep (or alternate), reduce}. */
+ * ms[6] = {prep, trajectory (or Stadler conditioning), chebyshev, gemm, sweep (or alternate), reduce}. */
 int  gcdyn_set_profiling(gcdyn_ctx* ctx, int on);
 int  gcdyn_last_kernel_ms(gcdyn_ctx* ctx, float* ms);
 

@@ -157,3 +157,64 @@ def moments(items, present_time, S, M, K):
         np.add.at(Mom, (s, n, items["type"]), pw)
         pw = pw * th
     return Mom
+
+
+# ------------------------------------------------------------------ Chebyshev-moment (GEMM) formulation
+
+def cheb_tree_moments(flat, items, present_time, D):
+    """Pset-independent per-tree statistics: Mt[t, d, x] = Σ_{items of tree t with type x} w · T_d(u),
+    u = 2τ/T − 1, d = 0..D (Chebyshev polynomials by the three-term recurrence)."""
+    T = float(present_time)
+    nT, K = flat.n_trees, flat.n_types
+    u = 2.0 * (T - items["time"]) / T - 1.0
+    tree_of = np.repeat(np.arange(nT), np.diff(items["item_off"]))
+    Mt = np.zeros((nT, D + 1, K))
+    Tm, Tc = np.ones_like(u), u.copy()
+    for d in range(D + 1):
+        cur = Tm if d == 0 else Tc
+        np.add.at(Mt, (tree_of, d, items["type"]), items["w"] * cur)
+        if d >= 1:
+            Tm, Tc = Tc, 2.0 * u * Tc - Tm
+    return Mt
+
+
+def cheb_coeffs_from_table(Fc, present_time, D):
+    """Chebyshev interpolation coefficients a[d, x] of F_x on [0, T] from its piecewise Taylor table:
+    values at the D+1 Chebyshev–Gauss–Lobatto nodes, then a DCT-I.  Returns (a, tail) where
+    tail = max_x Σ of the last three |a|."""
+    S, L, K = Fc.shape
+    T = float(present_time)
+    k = np.arange(D + 1)
+    tau = T * (1.0 + np.cos(np.pi * k / D)) / 2.0
+    uu = tau * (S / T)
+    s = np.minimum(uu.astype(np.int64), S - 1)
+    th = uu - s
+    V = np.zeros((D + 1, K))
+    for n in range(L - 1, -1, -1):
+        V = V * th[:, None] + Fc[s, n, :]
+    wk = np.ones(D + 1); wk[0] = wk[-1] = 0.5
+    a = np.zeros((D + 1, K))
+    for d in range(D + 1):
+        a[d] = (2.0 / D) * ((wk * np.cos(np.pi * k * d / D))[:, None] * V).sum(axis=0)
+    a[0] *= 0.5
+    a[-1] *= 0.5
+    tail = np.abs(a[-3:]).sum(axis=0).max()
+    return a, tail
+
+
+def loglik_per_tree_cheb(flat, items, Mt, lam, mu, delta, Gamma, rho, sigma, present_time, S, M, D):
+    """Per-tree log-likelihoods as the GEMM path forms them: Σ_{d,x} a[d,x]·Mt[t,d,x] + count terms."""
+    Fc, pT, err, bad = taylor_table(lam, mu, delta, Gamma, rho, sigma, present_time, S, M)
+    a, tail = cheb_coeffs_from_table(Fc, present_time, D)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        loglam = np.log(np.asarray(lam, float))
+        logG = np.log(delta * np.asarray(Gamma, float)).reshape(-1)
+        logmusig = np.log(mu) + np.log(sigma)
+        logrho = np.log(rho)
+        logcond = np.log1p(-pT)
+    out = np.einsum("tdx,dx->t", Mt[:, :D + 1, :], a)
+    out = out + _xlogy_count(items["nb"], loglam).sum(axis=1) + _xlogy_count(items["ntc"], logG).sum(axis=1)
+    out = out + _xlogy_count(items["nd"], logmusig) + _xlogy_count(items["ns"], logrho)
+    out = out - logcond[flat.root_type_idx]
+    out = np.where(flat.self_loop != 0, -np.inf, out)
+    return out, tail

@@ -108,6 +108,70 @@ def test_adaptive_steps_per_pset_and_global_table_path(ctx):
     assert ctx.last_diag()["steps"] == 512
 
 
+def _tile(params, reps):
+    """The same parameter sets repeated `reps` times (batches of ≥ 8 psets take the Chebyshev/GEMM path)."""
+    from gcdyn.likelihood import PackedParams
+    rep = lambda a, per: None if a is None else np.ascontiguousarray(np.tile(a.reshape(params.n_psets, per), (reps, 1))).reshape(-1)
+    K = params.n_types
+    lam_per = K if params.response == 0 else 1
+    return PackedParams(n_psets=params.n_psets * reps, n_types=K, response=params.response,
+                        gamma_pset_stride=params.gamma_pset_stride, lam=rep(params.lam.reshape(-1), lam_per),
+                        xscale=None, xshift=None, yscale=None, yshift=None, type_space=params.type_space,
+                        mu=rep(params.mu, 1), delta=rep(params.delta, 1), rho=rep(params.rho, 1), sigma=rep(params.sigma, 1),
+                        Gamma=params.Gamma if params.gamma_pset_stride == 0 else rep(params.Gamma, K * K))
+
+
+@pytest.mark.parametrize("name,key", [("g1_config1", "ode_closed"), ("g2_config2", "ode_branch"),
+                                      ("g3_fully_observed", "naive"), ("g4_no_extinction", "stadler"),
+                                      ("g5_batched_discrete", "ode_shared")])
+def test_chebyshev_gemm_path_against_golden_and_sweep(ctx, name, key):
+    """P ≥ 8 takes the DMMA GEMM over per-tree Chebyshev moments; it must agree with the golden values and,
+    to rounding, with the item sweep (flags = SWEEP_ONLY) on the same inputs."""
+    flat, params, T, exp, _ = load_golden(name)
+    forest = gcdyn.Forest(flat, None, T, ctx=ctx)
+    reps = -(-8 // params.n_psets)
+    big = _tile(params, reps)
+    out_g, tp_g, st_g = evaluate(forest, big, T, per_tree=True)
+    cheb = ctx.last_cheb()
+    assert cheb["interp_degree"] >= 24 and 8 <= cheb["effective_degree"] <= cheb["interp_degree"] and cheb["n_fallback"] == 0
+    out_s, tp_s, st_s = evaluate(forest, big, T, per_tree=True, flags=4)
+    assert ctx.last_cheb()["interp_degree"] == 0
+    assert not st_g.any() and not st_s.any()
+    want = np.tile(exp[key], (reps, 1)) if exp[key].shape[0] == params.n_psets else None
+    if want is None:
+        want = np.tile(exp[key], (1, 1))
+    n = want.shape[0]
+    assert rel(tp_g[:n], want) <= TREE_RTOL and rel(out_g[:n], want.sum(axis=1)) <= SUM_RTOL
+    assert rel(tp_g, tp_s) <= 1e-10 and rel(out_g, out_s) <= 1e-12
+    assert rel(out_g, tp_g.sum(axis=1)) <= 1e-13
+
+
+def test_gemm_path_falls_back_per_pset(ctx):
+    """Psets the GEMM cannot take — a non-finite node-term log the forest needs (σ = 0 with sampled deaths),
+    or a trajectory too sharp for degree 128 — are redone by the item sweep inside the same call."""
+    import oracle
+    rng = np.random.default_rng(16)
+    ts = np.linspace(-2, 2, 6)
+    mk = lambda ys, mu, sig: gcdyn.SigmoidalBranchingProcess(1.5, 0.0, ys, 0.5, mu, 1.0, 0.5, sig, ts)
+    base = mk(2.5, 1.0, 0.1)
+    trees = gcdyn.rand_tree(base, 3.0, ts[2], 12, rng=rng)
+    models = [mk(2.5 * f, 1.0, 0.1) for f in np.linspace(0.8, 1.2, 8)]
+    models[3] = mk(2.5, 1.0, 0.0)          # log σ = -Inf, forest has sampled deaths
+    models[5] = mk(60.0, 30.0, 0.1)        # T·rate ≈ 300: needs more than degree 128
+    forest = gcdyn.Forest(trees, ts, 3.0, ctx=ctx)
+    out, tp, st = evaluate(forest, pack_params(models), 3.0, per_tree=True)
+    assert ctx.last_cheb()["n_fallback"] >= 1
+    flat = forest.flat
+    has_death = flat.event_counts[:, 2] > 0
+    assert np.all(np.isneginf(tp[3][has_death])) and np.all(np.isfinite(tp[3][~has_death]))
+    for p in (0, 5, 7):
+        want = np.array([oracle.loglikelihood_shared(models[p], t, 3.0) for t in trees])
+        assert rel(tp[p], want) <= TREE_RTOL, p
+    out_s, tp_s, _ = evaluate(forest, pack_params(models), 3.0, per_tree=True, flags=4)
+    finite = np.isfinite(tp_s)
+    assert np.array_equal(finite, np.isfinite(tp)) and rel(tp[finite], tp_s[finite]) <= 1e-10
+
+
 def test_public_api_matches_oracle_on_simulated_trees(ctx):
     """The reference-style call `loglikelihood(model, trees, present_time)` on freshly simulated trees."""
     import oracle
