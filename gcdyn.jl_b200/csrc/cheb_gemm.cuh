@@ -128,17 +128,31 @@ __global__ void __launch_bounds__(256) cheb_kernel(PsetPack pk, MomentView mv, C
         for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) V[idx] = 0.0;
     }
     __syncthreads();
+    // DCT-I with the symmetry cos(π(D−k)d/D) = (−1)^d cos(πkd/D): fold the node values into an even and an
+    // odd half, E_k = w_k (V_k + V_{D−k}), O_k = w_k (V_k − V_{D−k}), k = 0..D/2, w_0 = w_{D/2} = 1/2.
+    const int H = D / 2;
+    double* EO = Acoef + (size_t)(D + 1) * K;        // [2][(H+1)*K]
+    for (int idx = threadIdx.x; idx < (H + 1) * K; idx += blockDim.x) {
+        const int k = idx / K, x = idx - k * K;
+        const double w = (k == 0 || k == H) ? 0.5 : 1.0;
+        const double a = V[k * K + x], b = V[(D - k) * K + x];
+        EO[idx] = w * (a + b);
+        EO[(H + 1) * K + idx] = w * (a - b);
+    }
+    __syncthreads();
     for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
         const int d = idx / K, x = idx - d * K;
+        const double* src = EO + (size_t)(d & 1) * (H + 1) * K + x;
         double s0 = 0.0, s1 = 0.0;
         int m = 0;                                   // (k*d) mod 2D, advanced incrementally
-        for (int k = 0; k <= D; ++k) {
-            double v = V[k * K + x];
-            if (k == 0 || k == D) v *= 0.5;
-            if (k & 1) s1 = fma(v, costab[m], s1); else s0 = fma(v, costab[m], s0);
-            m += d;
-            if (m >= 2 * D) m -= 2 * D;
+        int k = 0;
+        for (; k + 1 <= H; k += 2) {
+            s0 = fma(src[k * K], costab[m], s0);
+            m += d; m -= (m >= 2 * D) ? 2 * D : 0;
+            s1 = fma(src[(k + 1) * K], costab[m], s1);
+            m += d; m -= (m >= 2 * D) ? 2 * D : 0;
         }
+        if (k <= H) s0 = fma(src[k * K], costab[m], s0);
         double a = (2.0 / (double)D) * (s0 + s1);
         if (d == 0 || d == D) a *= 0.5;
         Acoef[idx] = a;

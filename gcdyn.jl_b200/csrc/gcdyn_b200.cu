@@ -335,20 +335,20 @@ int launch_sweep(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& p
 // Chebyshev interpolation degree for this batch: generous (the kernel trims to the effective degree),
 // even, ≤ the moment cap and small enough for cheb_kernel's shared memory.
 int cheb_degree(double T, double rate_max, int K, int Dcap, int smem_optin) {
-    double want = T * rate_max + 24.0;
+    double want = T * rate_max + 12.0;
     if (!(want == want)) want = 32.0;
     const int ladder[] = {24, 32, 48, 64, 96, 128};
     int D = 128;
     for (int d : ladder) if ((double)d >= want) { D = d; break; }
     D = std::min(D, Dcap);
-    while (D > 16 && (2 * (size_t)D + 2 * (size_t)(D + 1) * K) * 8 + 1024 > (size_t)smem_optin) D -= 8;
+    while (D > 16 && (2 * (size_t)D + (3 * (size_t)D + 4) * K) * 8 + 1024 > (size_t)smem_optin) D -= 8;
     return D & ~1;
 }
 
 template <int M>
 int launch_cheb_m(gcdyn_ctx* ctx, const PsetPack& pk, const MomentView& mv, const ChebCfg& cc, const double* tab, double* A,
                   int* need_sweep, int* d_common, int P, cudaStream_t st) {
-    const size_t smem = (2 * (size_t)cc.D + 2 * (size_t)(cc.D + 1) * mv.K) * 8;
+    const size_t smem = (2 * (size_t)cc.D + (3 * (size_t)cc.D + 4) * mv.K) * 8;
     if (smem > 48 * 1024)
         CU_TRY(ctx, cudaFuncSetAttribute(cheb_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cheb_kernel<M><<<P, 256, smem, st>>>(pk, mv, cc, tab, A, need_sweep, d_common);

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(32) traj_kernel(ParamsView pv, PsetPack pk, Tr
     double* tabp = tab + (size_t)p * cfg.tab_stride;
     double pcur[KPL], Fcur[KPL];
     double errmax = 0.0;
-    bool bad = false, failed = false;
+    bool bad = false, failed = false, pilot = true, resized = false;
     for (;;) {
         const double h = cfg.T / (double)S;
 #pragma unroll
@@ -332,10 +332,23 @@ __global__ void __launch_bounds__(32) traj_kernel(ParamsView pv, PsetPack pk, Tr
                 }
             }
             if (adaptive && __any_sync(FULL, over)) { restart = true; break; }
+            if (adaptive && pilot && s == 0) {
+                // Pilot: the indicator peaks in the first cell(s) (the transient away from p(0) = 1 − ρ) and
+                // scales like h^M, so one cell is enough to size the grid; re-start on the right rung.
+                pilot = false;
+                const double w0 = warp_max_nan(errmax);
+                double f = 1.1 * pow(w0 / cfg.tol, 1.0 / (double)M);
+                if (!(f >= 0.0)) f = 1.0;
+                int Sp = ladder_ceil((long long)ceil((double)S * f));
+                if (Sp > cfg.S_cap) Sp = cfg.S_cap;
+                if (Sp < S) { S = Sp; resized = true; break; }
+            }
         }
+        if (resized) { resized = false; continue; }
         if (!restart) break;
         if (S >= cfg.S_cap) { failed = true; break; }
         // under-resolved: the indicator scales like h^M, so grow the step count accordingly and start over
+        pilot = false;
         const double worst = warp_max_nan(errmax);
         double grow = 2.0;
         if (worst == worst && !isinf(worst)) grow = 1.1 * pow(worst / cfg.tol, 1.0 / (double)M);
