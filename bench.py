@@ -320,7 +320,7 @@ def run_gpu(args):
         pass
     # algorithmic FLOPs per launch
     cheb = ctx.last_cheb()
-    C = 2 * K + K * K + 2
+    C = 2 * K + 4          # count columns (shared Γ: type changes are a per-tree constant, not K² columns)
     J = C + (cheb["effective_degree"] + 1) * K if cheb["interp_degree"] else 0
     Dn = cheb["interp_degree"]
     flops = {"sweep": n_items * P * (2.0 * (M + 1) + 8.0) * (cheb["n_fallback"] / P if Dn else 1.0),

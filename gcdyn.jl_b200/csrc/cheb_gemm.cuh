@@ -1,14 +1,22 @@
-// Chebyshev-moment formulation of the per-tree sums (DESIGN.md §5b).
+// Chebyshev-moment formulation of the per-tree sums (DESIGN.md §5).
 //
 // F_x(τ) is smooth on [0, T], so for every parameter set it is represented by ONE Chebyshev series per type,
 //     F_x(τ) ≈ Σ_{d≤D} a[p][d][x] · T_d(u),  u = 2τ/T − 1,
 // and the per-tree sum over lookup items becomes a dense contraction with pset-independent per-tree
 // statistics Mt[t][d][x] = Σ_{items of tree t, type x} w · T_d(u_item):
-//     LL[p][t] = Σ_j A[p][j] · Mt[t][j],   j = [count columns | (d, x) Chebyshev columns]
-// i.e. a [P × J] · [J × T] FP64 GEMM executed with DMMA (mma.sync.m8n8k4.f64).  The count columns carry the
-// node terms of mbp.jl:167-191 (log λ_x per birth, log δΓ_xy per type change, log μ + log σ per sampled death,
-// log ρ per sampled survivor) and −log(1 − p_root(T)) (mbp.jl:244-245).  Psets whose series is not resolved,
-// or whose node-term logs are not finite where the forest needs them, are re-done by sweep_kernel.
+//     LL[p][t] = Σ_j A[p][j] · Mt[t][j]
+// i.e. a [P × J] · [J × T] FP64 GEMM executed with DMMA (mma.sync.m8n8k4.f64).  Column space j:
+//     [0, K)            births by branch type            ×  log λ_x                      (mbp.jl:175)
+//     K, K+1            sampled deaths, sampled survivors ×  log μ + log σ,  log ρ        (mbp.jl:168,171)
+//     [K+2, 2K+2)       root type one-hot                 ×  −log(1 − p_x(T))             (mbp.jl:244-245)
+//     2K+2              number of type changes            ×  log δ   (only when Γ is shared by all psets)
+//     2K+3              padding
+//     [C1, C1+(Dcap+1)K)  Chebyshev moments, degree-major ×  a[d][x]
+//     [Jtc, Jtc+K²)     type changes x→y                  ×  log δΓ_xy  (only when every pset has its own Γ;
+//                                                            with a shared Γ the Σ count·log Γ_xy part is a
+//                                                            per-tree constant added in the GEMM epilogue)
+// Psets whose series is not resolved, or whose node-term logs are not finite where the forest needs them,
+// are re-done by sweep_kernel (exact item sums).
 #pragma once
 #include "kernels.cuh"
 
@@ -16,31 +24,35 @@ namespace gcdyn {
 
 struct MomentView {
     int K;
-    int C;                 // count columns: K (births) + K*K (type changes) + 2 (deaths, survivors) + K (root one-hot)
+    int C1;                // 2K + 4: start of the Chebyshev block
     int Dcap;              // moments exist for d = 0..Dcap
+    long long Jtc;         // start of the K² type-change block
     long long Jst;         // row stride of Mt and A (doubles), multiple of 4
     const double* Mt;      // [T][Jst]
-    const double* colsum;  // [C] forest-level sums of the count columns
+    const double* colsum;  // [Jst] forest-level column sums (only count columns are consulted)
 };
 
 struct ChebCfg {
     double T;
     double tol;            // accepted Chebyshev tail (absolute, on F)
     int D;                 // interpolation degree (≤ Dcap), even
+    int compact_tc;        // 1: Γ shared — log δ column + per-tree constant; 0: K² type-change columns
     long long tab_stride;
 };
 
 // ------------------------------------------------------------------------------------------------
 // moments_kernel: one CTA per tree (run once per forest and present_time).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) moments_kernel(ForestView fv, double T, int Dcap, long long Jst, double* __restrict__ Mt) {
+__global__ void __launch_bounds__(128) moments_kernel(ForestView fv, double T, int Dcap, long long Jtc, long long Jst,
+                                                      double* __restrict__ Mt) {
     extern __shared__ __align__(16) double sm[];
     const int K = fv.K;
-    const int C = 2 * K + K * K + 2;
+    const int C1 = 2 * K + 4;
+    const int NC = C1 + K * K;                              // integer counters: count columns + type-change block
     const int64_t t = blockIdx.x;
-    int* cnt = reinterpret_cast<int*>(sm);                  // [C] integer counts
-    double* acc = sm + ((C + 1) / 2);                       // [(Dcap+1)*K]
-    for (int i = threadIdx.x; i < C; i += blockDim.x) cnt[i] = 0;
+    int* cnt = reinterpret_cast<int*>(sm);
+    double* acc = sm + ((NC + 1) / 2);                      // [(Dcap+1)*K]
+    for (int i = threadIdx.x; i < NC; i += blockDim.x) cnt[i] = 0;
     for (int i = threadIdx.x; i < (Dcap + 1) * K; i += blockDim.x) acc[i] = 0.0;
     __syncthreads();
     // node-term counts over live nodes (integer atomics: exact, order-independent)
@@ -48,13 +60,13 @@ __global__ void __launch_bounds__(128) moments_kernel(ForestView fv, double T, i
         if (!fv.live[i]) continue;
         const int ev = fv.event[i], x = fv.btype_idx[i], y = fv.type_idx[i];
         if (ev == EV_BIRTH) atomicAdd(&cnt[x], 1);
-        else if (ev == EV_TC) atomicAdd(&cnt[K + x * K + y], 1);
-        else if (ev == EV_SDEATH) atomicAdd(&cnt[K + K * K], 1);
-        else if (ev == EV_SSURV) atomicAdd(&cnt[K + K * K + 1], 1);
+        else if (ev == EV_TC) { atomicAdd(&cnt[C1 + x * K + y], 1); atomicAdd(&cnt[2 * K + 2], 1); }
+        else if (ev == EV_SDEATH) atomicAdd(&cnt[K], 1);
+        else if (ev == EV_SSURV) atomicAdd(&cnt[K + 1], 1);
     }
     if (threadIdx.x == 0) {
         const int rt = fv.root_type[t];
-        if (rt >= 0) cnt[K + K * K + 2 + rt] = 1;
+        if (rt >= 0) cnt[K + 2 + rt] = 1;
     }
     // Chebyshev moments: thread x owns column x and walks the tree's items in order (deterministic)
     const int64_t i0 = fv.item_off[t], i1 = fv.item_off[t + 1];
@@ -76,37 +88,60 @@ __global__ void __launch_bounds__(128) moments_kernel(ForestView fv, double T, i
     }
     __syncthreads();
     double* row = Mt + (size_t)t * Jst;
-    for (int i = threadIdx.x; i < C; i += blockDim.x) row[i] = (double)cnt[i];
-    for (int i = threadIdx.x; i < (Dcap + 1) * K; i += blockDim.x) row[C + i] = acc[i];
-    for (long long i = C + (long long)(Dcap + 1) * K + threadIdx.x; i < Jst; i += blockDim.x) row[i] = 0.0;
+    for (long long i = threadIdx.x; i < Jst; i += blockDim.x) {
+        double v = 0.0;
+        if (i < C1) v = (double)cnt[i];
+        else if (i < C1 + (long long)(Dcap + 1) * K) v = acc[i - C1];
+        else if (i >= Jtc && i < Jtc + (long long)K * K) v = (double)cnt[C1 + (i - Jtc)];
+        row[i] = v;
+    }
 }
 
-// column sums of the count part: colsum[c] = Σ_t Mt[t][c]  (one thread per column, fixed order)
-__global__ void colsum_kernel(const double* __restrict__ Mt, int64_t T, long long Jst, int C, double* __restrict__ colsum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+// column sums: colsum[c] = Σ_t Mt[t][c]  (one thread per column, fixed order)
+__global__ void colsum_kernel(const double* __restrict__ Mt, int64_t T, long long Jst, double* __restrict__ colsum) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Jst) return;
     double s = 0.0;
     for (int64_t t = 0; t < T; ++t) s += Mt[(size_t)t * Jst + c];
     colsum[c] = s;
 }
 
+// Shared Γ: per-tree constant Σ_{x→y} count · log Γ_xy (the pset-independent part of Σ log δΓ_xy), one warp per tree.
+__global__ void tc_const_kernel(MomentView mv, int64_t T, const double* __restrict__ Gamma /*col-major*/,
+                                double* __restrict__ tree_const) {
+    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const int K = mv.K;
+    const double* cnt = mv.Mt + (size_t)t * mv.Jst + mv.Jtc;
+    double acc = 0.0;
+    for (int e = lane; e < K * K; e += 32) {
+        const double n = cnt[e];
+        if (n != 0.0) {
+            const int x = e / K, y = e - x * K;
+            acc += n * log(Gamma[x + (size_t)y * K]);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) tree_const[t] = acc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // cheb_kernel: one CTA per pset.  Values of F_x at the D+1 Chebyshev–Gauss–Lobatto nodes from the pset's
 // Taylor table, DCT-I → a[d][x]; effective degree; count-column coefficients; fallback flag.
-//   A[p][c] (c < C)            = node-term logs (non-finite entries the forest uses → flag, stored as 0)
-//   A[p][C + d*K + x]          = a[d][x] for d ≤ D_eff[p], 0 above
 // ------------------------------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(256) cheb_kernel(PsetPack pk, MomentView mv, ChebCfg cfg, const double* __restrict__ tab,
-                                                   double* __restrict__ A, int* __restrict__ need_sweep,
-                                                   int* __restrict__ d_common) {
+__global__ void __launch_bounds__(512) cheb_kernel(ParamsView pv, PsetPack pk, MomentView mv, ChebCfg cfg,
+                                                   const double* __restrict__ tab, double* __restrict__ A,
+                                                   int* __restrict__ need_sweep, int* __restrict__ d_common) {
     extern __shared__ __align__(16) double sm[];
     constexpr int L = M + 2;
     const int p = blockIdx.x;
-    const int K = mv.K, C = mv.C, D = cfg.D;
+    const int K = mv.K, C1 = mv.C1, D = cfg.D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     double* costab = sm;                   // [2D]  cos(π m / D)
-    double* V = costab + 2 * D;            // [(D+1)*K] node values, later coefficients
-    double* Acoef = V + (size_t)(D + 1) * K;   // [(D+1)*K]
+    double* V = costab + 2 * D;            // [(D+1)*K] node values
+    double* Acoef = V + (size_t)(D + 1) * K;   // [(D+1)*K] coefficients
     __shared__ int s_deff, s_flag;
     const int S = pk.S[p];
     const int pst = pk.pstatus[p];
@@ -158,39 +193,77 @@ __global__ void __launch_bounds__(256) cheb_kernel(PsetPack pk, MomentView mv, C
         Acoef[idx] = a;
     }
     __syncthreads();
-    // effective degree per type: smallest d with Σ_{k>d}|a_k| ≤ tol; unresolved if the last three terms are not small
-    for (int x = threadIdx.x; x < K; x += blockDim.x) {
-        const double last3 = fabs(Acoef[D * K + x]) + fabs(Acoef[(D - 1) * K + x]) + fabs(Acoef[(D - 2) * K + x]);
-        if (!(last3 <= cfg.tol)) atomicExch(&s_flag, 1);
-        double tail = 0.0;
-        int d = D;
-        while (d > 8) {
-            tail += fabs(Acoef[d * K + x]);
-            if (!(tail <= cfg.tol)) break;
-            --d;
+    // effective degree per type (a warp per type, lanes over degrees): the smallest d with Σ_{k>d}|a_k| ≤ tol;
+    // the series counts as unresolved if its last three terms are not small
+    for (int x = warp; x < K; x += nwarps) {
+        // lane owns the contiguous degrees [lo, hi); suffix sums of |a| are combined across lanes
+        const int per = (D + 1 + 31) / 32;
+        const int lo = lane * per, hi = min(D + 1, lo + per);
+        double mine = 0.0;
+        for (int d = lo; d < hi; ++d) mine += fabs(Acoef[d * K + x]);
+        double above = 0.0;                        // Σ over lanes > lane
+        {
+            double run = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_down_sync(FULL, run, o);
+                if (lane + o < 32) run += v;
+            }
+            above = run - mine;
         }
-        atomicMax(&s_deff, d);
+        int found = 8;
+        double tail = above;
+        for (int d = hi - 1; d >= lo && d > 8; --d) {
+            tail += fabs(Acoef[d * K + x]);
+            if (!(tail <= cfg.tol)) { found = d; break; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) found = max(found, __shfl_xor_sync(FULL, found, o));
+        if (lane == 0) {
+            const double last3 = fabs(Acoef[D * K + x]) + fabs(Acoef[(D - 1) * K + x]) + fabs(Acoef[(D - 2) * K + x]);
+            if (!(last3 <= cfg.tol)) atomicExch(&s_flag, 1);
+            atomicMax(&s_deff, found);
+        }
     }
     __syncthreads();
     const int deff = s_deff;
     double* Arow = A + (size_t)p * mv.Jst;
-    for (int idx = threadIdx.x; idx < (mv.Dcap + 1) * K; idx += blockDim.x) {
+    for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
         const int d = idx / K;
-        Arow[C + idx] = (d <= deff && d <= D) ? Acoef[idx] : 0.0;
+        Arow[C1 + idx] = d <= deff ? Acoef[idx] : 0.0;
     }
-    for (long long i = C + (long long)(mv.Dcap + 1) * K + threadIdx.x; i < mv.Jst; i += blockDim.x) Arow[i] = 0.0;
-    // count columns: [log λ_x | log δΓ_xy | log μ + log σ | log ρ | −log(1 − p_x(T))]
+    // the GEMM rounds its column ranges up to multiples of 4: keep the padding finite
+    if (threadIdx.x < 4) {
+        const long long j = C1 + (long long)(D + 1) * K + threadIdx.x;
+        if (j < mv.Jtc) Arow[j] = 0.0;
+        const long long j2 = mv.Jtc + (long long)K * K + threadIdx.x;
+        if (j2 < mv.Jst) Arow[j2] = 0.0;
+    }
+    // count columns
     const double* nt = pk.nt + (size_t)p * pk.ntw;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        double v;
-        if (c < K + K * K + 2) v = nt[c];
-        else v = -pk.logcond[(size_t)p * K + (c - (K + K * K + 2))];
-        const bool diag = c >= K && c < K + K * K && ((c - K) / K == (c - K) % K);   // self-loop column: trees using it are −Inf anyway
+    for (int c = threadIdx.x; c < C1; c += blockDim.x) {
+        double v = 0.0;
+        if (c < K) v = nt[c];                                         // log λ_x
+        else if (c == K) v = nt[K + K * K];                           // log μ + log σ
+        else if (c == K + 1) v = nt[K + K * K + 1];                   // log ρ
+        else if (c < 2 * K + 2) v = -pk.logcond[(size_t)p * K + (c - K - 2)];
+        else if (c == 2 * K + 2) v = cfg.compact_tc ? log(pv.delta[p]) : 0.0;
         if (!isfinite(v)) {
-            if (!diag && mv.colsum[c] != 0.0) atomicExch(&s_flag, 1);
+            if (mv.colsum[c] != 0.0) atomicExch(&s_flag, 1);
             v = 0.0;
         }
         Arow[c] = v;
+    }
+    if (!cfg.compact_tc) {
+        for (int e = threadIdx.x; e < K * K; e += blockDim.x) {
+            double v = nt[K + e];
+            const bool diag = (e / K) == (e % K);          // self-loop column: trees using it are −Inf anyway
+            if (!isfinite(v)) {
+                if (!diag && mv.colsum[mv.Jtc + e] != 0.0) atomicExch(&s_flag, 1);
+                v = 0.0;
+            }
+            Arow[mv.Jtc + e] = v;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -200,9 +273,9 @@ __global__ void __launch_bounds__(256) cheb_kernel(PsetPack pk, MomentView mv, C
 }
 
 // ------------------------------------------------------------------------------------------------
-// gemm_kernel: out[p][t] = Σ_{j<J} A[p][j]·Mt[t][j] with DMMA.  CTA tile 32(p) × 32(t), 4 warps of 16×16,
-// k-chunks of 32 staged through shared memory with cp.async (2 stages), row stride 36 doubles
-// (conflict-free for the m8n8k4 fragment pattern: row = lane/4, k = lane%4).
+// gemm_kernel: out[p][t] = Σ_j A[p][j]·Mt[t][j] (+ tree_const[t]) with DMMA over up to two column segments.
+// CTA tile 32(p) × 32(t), 4 warps of 16×16, k-chunks of 32 staged through shared memory with cp.async
+// (2 stages), row stride 36 doubles (conflict-free for the m8n8k4 fragment pattern: row = lane/4, k = lane%4).
 // ------------------------------------------------------------------------------------------------
 constexpr int GT_TILE = 32, GT_KC = 32, GT_LD = 36;
 
@@ -218,8 +291,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A, const double* __restrict__ Mt, long long Jst,
-                                                   int C, int K, const int* __restrict__ d_common, int P, int64_t T,
+__global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A, MomentView mv, int use_tc_block,
+                                                   const int* __restrict__ d_common, int P, int64_t T,
+                                                   const double* __restrict__ tree_const,
                                                    const int* __restrict__ pstatus, const int* __restrict__ need_sweep,
                                                    const uint8_t* __restrict__ self_loop, double* __restrict__ out_tree,
                                                    int32_t* __restrict__ status) {
@@ -228,19 +302,28 @@ __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int p0 = blockIdx.y * GT_TILE;
     const int64_t t0 = (int64_t)blockIdx.x * GT_TILE;
-    long long J = C + (long long)(*d_common + 1) * K;
-    J = (J + 3) & ~3LL;
-    if (J > Jst) J = Jst;
-    const int nchunks = (int)((J + GT_KC - 1) / GT_KC);
+    const long long Jst = mv.Jst;
+    const double* Mt = mv.Mt;
+    // segment 1: count columns + Chebyshev columns up to the batch's effective degree; segment 2: K² block
+    long long J1 = mv.C1 + (long long)(*d_common + 1) * mv.K;
+    J1 = (J1 + 3) & ~3LL;
+    const long long J1max = (mv.C1 + (long long)(mv.Dcap + 1) * mv.K + 3) & ~3LL;
+    if (J1 > J1max) J1 = J1max;
+    const int n1 = (int)((J1 + GT_KC - 1) / GT_KC);
+    const long long J2 = use_tc_block ? ((long long)mv.K * mv.K + 3) & ~3LL : 0;
+    const int n2 = (int)((J2 + GT_KC - 1) / GT_KC);
+    const int nchunks = n1 + n2;
     // this thread's cp.async assignments: 32 rows × 16 segments of 16 B per operand = 512 per tile, 4 per thread
     auto issue = [&](int chunk, int buf) {
-        const long long j0 = (long long)chunk * GT_KC;
+        long long j0, jend;
+        if (chunk < n1) { j0 = (long long)chunk * GT_KC; jend = J1; }
+        else { j0 = mv.Jtc + (long long)(chunk - n1) * GT_KC; jend = mv.Jtc + J2; if (jend > Jst) jend = Jst; }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int seg = tid + r * 128;
             const int row = seg >> 4, col = (seg & 15) * 2;          // col in doubles
             const long long j = j0 + col;
-            const bool inj = j < J;
+            const bool inj = j < jend;
             const bool va = inj && (p0 + row) < P;
             const bool vb = inj && (t0 + row) < T;
             const double* sa = A + (size_t)(va ? p0 + row : 0) * Jst + (va ? j : 0);
@@ -292,6 +375,7 @@ __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A,
                 const int64_t t = t0 + wc + 8 * b + 2 * fk + e;
                 if (t >= T) continue;
                 double r = acc[a][b][e];
+                if (tree_const) r += tree_const[t];
                 int st = pst;
                 if (self_loop[t]) st |= ST_SELF_LOOP;
                 if (st & (ST_SELF_LOOP | ST_SOLVER)) r = -CUDART_INF;

@@ -83,6 +83,9 @@ struct gcdyn_forest {
     mutable double mom_T = -1.0;
     mutable double* d_Mt = nullptr;
     mutable double* d_colsum = nullptr;
+    // shared-Γ constant Σ count·log Γ_xy per tree, cached for the last Γ seen
+    mutable double* d_tree_const = nullptr;
+    mutable std::vector<double> tc_gamma;
 };
 
 struct gcdyn_dparams {
@@ -90,6 +93,7 @@ struct gcdyn_dparams {
     void* blob = nullptr;
     ParamsView v{};
     double rate_max = 0.0;   // max over psets and types of λ_i + μ + γ_i, from the host copy
+    std::vector<double> host_gamma;   // the shared Γ (column-major), empty when every pset has its own
 };
 
 namespace {
@@ -337,7 +341,7 @@ int launch_sweep(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& p
 int cheb_degree(double T, double rate_max, int K, int Dcap, int smem_optin) {
     double want = T * rate_max + 12.0;
     if (!(want == want)) want = 32.0;
-    const int ladder[] = {24, 32, 48, 64, 96, 128};
+    const int ladder[] = {32, 48, 64, 96, 128};
     int D = 128;
     for (int d : ladder) if ((double)d >= want) { D = d; break; }
     D = std::min(D, Dcap);
@@ -346,24 +350,24 @@ int cheb_degree(double T, double rate_max, int K, int Dcap, int smem_optin) {
 }
 
 template <int M>
-int launch_cheb_m(gcdyn_ctx* ctx, const PsetPack& pk, const MomentView& mv, const ChebCfg& cc, const double* tab, double* A,
-                  int* need_sweep, int* d_common, int P, cudaStream_t st) {
+int launch_cheb_m(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const MomentView& mv, const ChebCfg& cc,
+                  const double* tab, double* A, int* need_sweep, int* d_common, int P, cudaStream_t st) {
     const size_t smem = (2 * (size_t)cc.D + (3 * (size_t)cc.D + 4) * mv.K) * 8;
     if (smem > 48 * 1024)
         CU_TRY(ctx, cudaFuncSetAttribute(cheb_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cheb_kernel<M><<<P, 256, smem, st>>>(pk, mv, cc, tab, A, need_sweep, d_common);
+    cheb_kernel<M><<<P, 512, smem, st>>>(pv, pk, mv, cc, tab, A, need_sweep, d_common);
     CU_TRY(ctx, cudaGetLastError());
     return GCDYN_OK;
 }
 
-int launch_cheb(gcdyn_ctx* ctx, int M, const PsetPack& pk, const MomentView& mv, const ChebCfg& cc, const double* tab,
-                double* A, int* need_sweep, int* d_common, int P, cudaStream_t st) {
+int launch_cheb(gcdyn_ctx* ctx, int M, const ParamsView& pv, const PsetPack& pk, const MomentView& mv, const ChebCfg& cc,
+                const double* tab, double* A, int* need_sweep, int* d_common, int P, cudaStream_t st) {
     switch (M) {
-        case 8: return launch_cheb_m<8>(ctx, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
-        case 12: return launch_cheb_m<12>(ctx, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
-        case 16: return launch_cheb_m<16>(ctx, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
-        case 20: return launch_cheb_m<20>(ctx, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
-        case 24: return launch_cheb_m<24>(ctx, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
+        case 8: return launch_cheb_m<8>(ctx, pv, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
+        case 12: return launch_cheb_m<12>(ctx, pv, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
+        case 16: return launch_cheb_m<16>(ctx, pv, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
+        case 20: return launch_cheb_m<20>(ctx, pv, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
+        case 24: return launch_cheb_m<24>(ctx, pv, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
     }
     return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
 }
@@ -373,33 +377,37 @@ int ensure_moments(gcdyn_ctx* ctx, const gcdyn_forest* f, double T, cudaStream_t
     if (f->mom.Mt && f->mom_T == T) return GCDYN_OK;
     const int K = f->v.K;
     const int Dcap = 128;
-    const int C = 2 * K + K * K + 2;
-    long long Jst = C + (long long)(Dcap + 1) * K;
+    const int C1 = 2 * K + 4;
+    long long Jtc = C1 + (long long)(Dcap + 1) * K;
+    Jtc = (Jtc + 3) & ~3LL;
+    long long Jst = Jtc + (long long)K * K;
     Jst = (Jst + 3) & ~3LL;
     const int64_t Tn = f->v.n_trees;
     if (!f->d_Mt) {
         CU_TRY(ctx, cudaMalloc(&f->d_Mt, std::max<size_t>((size_t)Tn * (size_t)Jst * 8, 8)));
-        CU_TRY(ctx, cudaMalloc(&f->d_colsum, (size_t)C * 8));
+        CU_TRY(ctx, cudaMalloc(&f->d_colsum, (size_t)Jst * 8));
     }
-    const size_t smem = ((size_t)(C + 1) / 2 + (size_t)(Dcap + 1) * K) * 8;
+    const size_t smem = ((size_t)(C1 + K * K + 1) / 2 + (size_t)(Dcap + 1) * K) * 8;
     if (smem > (size_t)ctx->smem_optin) return fail(ctx, GCDYN_EUNSUPPORTED, "n_types too large for the moment kernel");
     if (smem > 48 * 1024)
         CU_TRY(ctx, cudaFuncSetAttribute(moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    moments_kernel<<<(unsigned)Tn, 128, smem, st>>>(f->v, T, Dcap, Jst, f->d_Mt);
+    moments_kernel<<<(unsigned)Tn, 128, smem, st>>>(f->v, T, Dcap, Jtc, Jst, f->d_Mt);
     CU_TRY(ctx, cudaGetLastError());
-    colsum_kernel<<<(C + 127) / 128, 128, 0, st>>>(f->d_Mt, Tn, Jst, C, f->d_colsum);
+    colsum_kernel<<<(unsigned)((Jst + 127) / 128), 128, 0, st>>>(f->d_Mt, Tn, Jst, f->d_colsum);
     CU_TRY(ctx, cudaGetLastError());
     *launches += 2;
-    f->mom.K = K; f->mom.C = C; f->mom.Dcap = Dcap; f->mom.Jst = Jst; f->mom.Mt = f->d_Mt; f->mom.colsum = f->d_colsum;
+    f->mom.K = K; f->mom.C1 = C1; f->mom.Dcap = Dcap; f->mom.Jtc = Jtc; f->mom.Jst = Jst;
+    f->mom.Mt = f->d_Mt; f->mom.colsum = f->d_colsum;
     f->mom_T = T;
+    f->tc_gamma.clear();
     return GCDYN_OK;
 }
 
 // Enqueue one evaluation on `st`.  All pointers are device pointers; d_out_tree/d_status may be null.
 // S_fixed > 0 pins the number of Taylor cells; otherwise every pset adapts it inside traj_kernel.
 int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, double rate_max, double T, int method,
-                 int M, int S_fixed, double tol, int flags, double* d_out_pset, double* d_out_tree, int32_t* d_status,
-                 cudaStream_t st, PsetPack* pk_out) {
+                 int M, int S_fixed, double tol, int flags, const double* host_gamma_shared, double* d_out_pset,
+                 double* d_out_tree, int32_t* d_status, cudaStream_t st, PsetPack* pk_out) {
     const int P = pv.P, K = pv.K;
     if (P > 65535) return fail(ctx, GCDYN_EUNSUPPORTED, "more than 65535 parameter sets per call");
     PsetPack pk{};
@@ -447,14 +455,32 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             cc.tol = 1e-11;
             cc.tab_stride = cfg.tab_stride;
             cc.D = cheb_degree(T, rate_max, K, mv.Dcap, ctx->smem_optin);
-            rc = launch_cheb(ctx, M, pk, mv, cc, ctx->table.as<double>(), ctx->gemm_a.as<double>(), need_sweep, d_common,
-                             P, st);
+            cc.compact_tc = pv.gamma_stride == 0 ? 1 : 0;
+            const double* tree_const = nullptr;
+            if (cc.compact_tc) {
+                // shared Γ: Σ count·log Γ_xy is the same for every pset — one constant per tree, recomputed only
+                // when Γ (or the moments it is built from) changed since the last call on this forest
+                const size_t kk = (size_t)K * K;
+                if (!f->d_tree_const) CU_TRY(ctx, cudaMalloc(&f->d_tree_const, std::max<size_t>((size_t)Tn * 8, 8)));
+                const bool same = host_gamma_shared && f->tc_gamma.size() == kk &&
+                                  std::memcmp(f->tc_gamma.data(), host_gamma_shared, kk * 8) == 0;
+                if (!same) {
+                    tc_const_kernel<<<(unsigned)((Tn + 7) / 8), 256, 0, st>>>(mv, Tn, pv.Gamma, f->d_tree_const);
+                    CU_TRY(ctx, cudaGetLastError());
+                    ++launches;
+                    if (host_gamma_shared) f->tc_gamma.assign(host_gamma_shared, host_gamma_shared + kk);
+                    else f->tc_gamma.clear();
+                }
+                tree_const = f->d_tree_const;
+            }
+            rc = launch_cheb(ctx, M, pv, pk, mv, cc, ctx->table.as<double>(), ctx->gemm_a.as<double>(), need_sweep,
+                             d_common, P, st);
             if (rc) return rc;
             ++launches;
             if (prof) cudaEventRecord(ctx->ev[3], st);
             dim3 grid((unsigned)((Tn + GT_TILE - 1) / GT_TILE), (unsigned)((P + GT_TILE - 1) / GT_TILE));
-            gemm_kernel<<<grid, 128, 0, st>>>(ctx->gemm_a.as<double>(), mv.Mt, mv.Jst, mv.C, K, d_common, P, Tn, pk.pstatus,
-                                              need_sweep, f->v.self_loop, d_out_tree, d_status);
+            gemm_kernel<<<grid, 128, 0, st>>>(ctx->gemm_a.as<double>(), mv, cc.compact_tc ? 0 : 1, d_common, P, Tn,
+                                              tree_const, pk.pstatus, need_sweep, f->v.self_loop, d_out_tree, d_status);
             CU_TRY(ctx, cudaGetLastError());
             ++launches;
             only_flagged = need_sweep;
@@ -520,6 +546,7 @@ void free_forest(gcdyn_forest* f) {
     for (void* p : f->allocs) cudaFree(p);
     if (f->d_Mt) cudaFree(f->d_Mt);
     if (f->d_colsum) cudaFree(f->d_colsum);
+    if (f->d_tree_const) cudaFree(f->d_tree_const);
     cudaSetDevice(prev);
     delete f;
 }
@@ -682,7 +709,8 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
 
     // one pass: every pset adapts its own step count inside traj_kernel (or uses opts->steps as given);
     // a pset that cannot be resolved within the table capacity comes back as a solver failure (-Inf)
-    rc = enqueue_eval(ctx, f, pv, rate_max_of(pr), T, method, M, o.steps, tol, o.flags, ctx->out_pset.as<double>(), nullptr,
+    rc = enqueue_eval(ctx, f, pv, rate_max_of(pr), T, method, M, o.steps, tol, o.flags,
+                      pr->gamma_pset_stride == 0 ? pr->Gamma : nullptr, ctx->out_pset.as<double>(), nullptr,
                       status ? ctx->status.as<int32_t>() : nullptr, st, nullptr);
     if (rc) return rc;
     CU_TRY(ctx, cudaMemcpyAsync(h_out, ctx->out_pset.p, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
@@ -829,6 +857,7 @@ int gcdyn_params_upload(gcdyn_ctx* ctx, const gcdyn_params* pr, gcdyn_dparams** 
     }
     dp->v = view_of(pr, L, reinterpret_cast<const double*>(dp->blob));
     dp->rate_max = rate_max_of(pr);
+    if (pr->gamma_pset_stride == 0) dp->host_gamma.assign(pr->Gamma, pr->Gamma + (size_t)pr->n_types * pr->n_types);
     *out = dp;
     return GCDYN_OK;
     GUARD_END(ctx)
@@ -861,7 +890,8 @@ int gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcd
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
     return enqueue_eval(ctx, f, dp->v, dp->rate_max, present_time, method, M, o.steps, o.tol > 0.0 ? o.tol : 1e-11,
-                        o.flags, d_out_pset, d_out_tree_pset, d_status, st, nullptr);
+                        o.flags, dp->host_gamma.empty() ? nullptr : dp->host_gamma.data(), d_out_pset, d_out_tree_pset,
+                        d_status, st, nullptr);
     GUARD_END(ctx)
 }
 
