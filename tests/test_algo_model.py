@@ -51,3 +51,22 @@ def test_item_count_is_below_node_count():
     c = exp["event_counts"].sum(axis=0)
     assert len(items["time"]) == c[1] + c[2] + 2 * c[4] + flat.n_trees
     assert len(items["time"]) < flat.n_nodes
+
+
+@pytest.mark.parametrize("name,key", [("g1_config1", "ode_closed"), ("g2_config2", "ode_branch"),
+                                      ("g4_no_extinction", "stadler"), ("g5_batched_discrete", "ode_shared")])
+def test_chebyshev_moment_model_matches_oracle(name, key):
+    """The GEMM formulation: one Chebyshev series of F_x per pset × pset-independent per-tree Chebyshev
+    moments.  Degree 32 already reproduces the golden per-tree values; the tail of the series bounds the error."""
+    flat, params, T, exp, par = load_golden(name)
+    items = am.build_items(flat, T)
+    Mt = am.cheb_tree_moments(flat, items, T, 64)
+    for p in range(exp[key].shape[0]):
+        S = am.auto_steps(T, par["lam"][p], par["mu"][p], par["delta"][p], par["Gamma"][p], 16)
+        coarse, tail16 = am.loglik_per_tree_cheb(flat, items, Mt, par["lam"][p], par["mu"][p], par["delta"][p],
+                                                 par["Gamma"][p], par["rho"][p], par["sigma"][p], T, S, 16, 16)
+        out, tail = am.loglik_per_tree_cheb(flat, items, Mt, par["lam"][p], par["mu"][p], par["delta"][p],
+                                            par["Gamma"][p], par["rho"][p], par["sigma"][p], T, S, 16, 48)
+        assert tail <= 1e-11 and rel(out, exp[key][p]) <= 1e-10
+        # an unresolved series announces itself through its tail (what triggers the sweep fallback on the GPU)
+        assert tail16 > 1e-9 and rel(coarse, exp[key][p]) > rel(out, exp[key][p])

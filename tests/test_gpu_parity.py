@@ -146,6 +146,27 @@ def test_chebyshev_gemm_path_against_golden_and_sweep(ctx, name, key):
     assert rel(out_g, tp_g.sum(axis=1)) <= 1e-13
 
 
+def test_config5_like_k50_batched(ctx):
+    """BASELINE config 5 in miniature: K = 50 types (two types per lane in traj_kernel, K² = 2500 type-change
+    pairs folded into the per-tree constant), 24 jittered parameter sets, GEMM path vs oracle and vs sweep."""
+    import oracle
+    import workloads
+    flat = workloads.flat_forest("C5s", 0, 40)
+    models = workloads.jittered_models("C5s", 24)
+    T = workloads.CONFIGS["C5s"]["T"]
+    forest = gcdyn.Forest(flat, None, T, ctx=ctx)
+    params = pack_params(models)
+    out, tp, st = evaluate(forest, params, T, per_tree=True)
+    cheb = ctx.last_cheb()
+    assert cheb["interp_degree"] > 0 and cheb["n_fallback"] == 0 and not st.any()
+    par = workloads.par_dict(models)
+    for p in (0, 11, 23):
+        want = oracle.loglik_flat_shared(flat, par, p, T)
+        assert rel(tp[p], want) <= TREE_RTOL and abs(out[p] - want.sum()) <= SUM_RTOL * abs(want.sum())
+    out_s, tp_s, _ = evaluate(forest, params, T, per_tree=True, flags=4)
+    assert rel(tp, tp_s) <= 1e-10 and rel(out, out_s) <= 1e-12
+
+
 def test_gemm_path_falls_back_per_pset(ctx):
     """Psets the GEMM cannot take — a non-finite node-term log the forest needs (σ = 0 with sampled deaths),
     or a trajectory too sharp for degree 128 — are redone by the item sweep inside the same call."""
