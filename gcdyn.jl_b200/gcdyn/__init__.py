@@ -15,6 +15,7 @@ from .likelihood import (loglikelihood, naive_loglikelihood, stadler_appx_loglik
                          stadler_appx_unconditioned_loglikelihood, Forest, Context,
                          pack_params, DeviceParams, evaluate, evaluate_resident,
                          GcdynError, library_path)
+from .mcmc import random_walk_metropolis, MetropolisResult
 
 __all__ = [
     # reference exports (gcdyn.jl:15-33)
