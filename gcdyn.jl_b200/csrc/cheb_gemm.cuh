@@ -37,6 +37,7 @@ struct ChebCfg {
     double tol;            // accepted Chebyshev tail (absolute, on F)
     int D;                 // interpolation degree (≤ Dcap), even
     int compact_tc;        // 1: Γ shared — log δ column + per-tree constant; 0: K² type-change columns
+    int S_cap, grid_doubles;   // layout of a pset's table block: [τ_s | 1/h_s | pad][rows]
     long long tab_stride;
 };
 
@@ -149,15 +150,14 @@ __global__ void __launch_bounds__(512) cheb_kernel(ParamsView pv, PsetPack pk, M
     for (int m = threadIdx.x; m < 2 * D; m += blockDim.x) costab[m] = cospi((double)m / (double)D);
     __syncthreads();
     const double* tp = tab + (size_t)p * cfg.tab_stride;
-    const double scale = (double)S / cfg.T;
+    const double* invh = tp + (cfg.S_cap + 1);
+    const double* rows = tp + cfg.grid_doubles;
     if (!(pst & ST_SOLVER)) {
         for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
             const int k = idx / K, x = idx - k * K;
             const double tau = cfg.T * (1.0 + costab[k]) * 0.5;
-            const double u = tau * scale;
-            int s = (int)u;
-            s = s > S - 1 ? S - 1 : (s < 0 ? 0 : s);
-            V[idx] = eval_row<M, false>(tp + ((size_t)s * K + x) * L, u - (double)s);
+            const int s = find_cell(tp, S, tau);
+            V[idx] = eval_row<M, false>(rows + ((size_t)s * K + x) * L, (tau - tp[s]) * invh[s]);
         }
     } else {
         for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) V[idx] = 0.0;

@@ -304,8 +304,8 @@ int launch_traj(gcdyn_ctx* ctx, int M, const ParamsView& pv, const PsetPack& pk,
 
 template <int M>
 int launch_sweep_m(gcdyn_ctx* ctx, const gcdyn_forest* f, const PsetPack& pk, const double* tab, long long tab_stride,
-                   double T, int P, size_t want_smem, const int* only_flagged, double* out_tree, int32_t* status,
-                   cudaStream_t st) {
+                   int S_cap, int grid_doubles, double T, int P, size_t want_smem, const int* only_flagged,
+                   double* out_tree, int32_t* status, cudaStream_t st) {
     // dynamic shared memory = staging buffer for one pset's table (bulk-copied); psets whose table is
     // larger than the buffer are read from global memory by the same kernel
     size_t smem = std::min(std::max(want_smem, (size_t)64 * 1024), (size_t)ctx->smem_optin - 2048);
@@ -317,21 +317,22 @@ int launch_sweep_m(gcdyn_ctx* ctx, const gcdyn_forest* f, const PsetPack& pk, co
     if (per_sm < 1) per_sm = 1;
     const long long units = (long long)P * f->n_chunks;
     const long long grid = std::max<long long>(1, std::min<long long>(units, (long long)ctx->sm_count * per_sm));
-    sweep_kernel<M><<<(unsigned)grid, SWEEP_THREADS, smem, st>>>(f->v, pk, tab, tab_stride, f->d_chunk_off, (int)f->n_chunks, P, T,
+    sweep_kernel<M><<<(unsigned)grid, SWEEP_THREADS, smem, st>>>(f->v, pk, tab, tab_stride, S_cap, grid_doubles,
+                                                      f->d_chunk_off, (int)f->n_chunks, P, T,
                                                       (int)(smem / 8), only_flagged, out_tree, status);
     CU_TRY(ctx, cudaGetLastError());
     return GCDYN_OK;
 }
 
 int launch_sweep(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& pk, const double* tab,
-                 long long tab_stride, double T, int P, size_t want_smem, const int* only_flagged, double* out_tree,
-                 int32_t* status, cudaStream_t st) {
+                 long long tab_stride, int S_cap, int grid_doubles, double T, int P, size_t want_smem,
+                 const int* only_flagged, double* out_tree, int32_t* status, cudaStream_t st) {
     switch (M) {
-        case 8: return launch_sweep_m<8>(ctx, f, pk, tab, tab_stride, T, P, want_smem, only_flagged, out_tree, status, st);
-        case 12: return launch_sweep_m<12>(ctx, f, pk, tab, tab_stride, T, P, want_smem, only_flagged, out_tree, status, st);
-        case 16: return launch_sweep_m<16>(ctx, f, pk, tab, tab_stride, T, P, want_smem, only_flagged, out_tree, status, st);
-        case 20: return launch_sweep_m<20>(ctx, f, pk, tab, tab_stride, T, P, want_smem, only_flagged, out_tree, status, st);
-        case 24: return launch_sweep_m<24>(ctx, f, pk, tab, tab_stride, T, P, want_smem, only_flagged, out_tree, status, st);
+        case 8: return launch_sweep_m<8>(ctx, f, pk, tab, tab_stride, S_cap, grid_doubles, T, P, want_smem, only_flagged, out_tree, status, st);
+        case 12: return launch_sweep_m<12>(ctx, f, pk, tab, tab_stride, S_cap, grid_doubles, T, P, want_smem, only_flagged, out_tree, status, st);
+        case 16: return launch_sweep_m<16>(ctx, f, pk, tab, tab_stride, S_cap, grid_doubles, T, P, want_smem, only_flagged, out_tree, status, st);
+        case 20: return launch_sweep_m<20>(ctx, f, pk, tab, tab_stride, S_cap, grid_doubles, T, P, want_smem, only_flagged, out_tree, status, st);
+        case 24: return launch_sweep_m<24>(ctx, f, pk, tab, tab_stride, S_cap, grid_doubles, T, P, want_smem, only_flagged, out_tree, status, st);
     }
     return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
 }
@@ -430,7 +431,8 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         cfg.S_fixed = S_fixed;
         cfg.S_cap = S_fixed > 0 ? S_fixed : cap_steps(T, rate_max, M);
         const long long L = M + 2;
-        cfg.tab_stride = (long long)cfg.S_cap * K * L;
+        cfg.grid_doubles = 2 * cfg.S_cap + 2;
+        cfg.tab_stride = cfg.grid_doubles + (long long)cfg.S_cap * K * L;
         const size_t tab_bytes = (size_t)P * (size_t)cfg.tab_stride * 8;
         CU_TRY(ctx, ctx->table.ensure(tab_bytes));
         rc = launch_traj(ctx, M, pv, pk, cfg, ctx->table.as<double>(), st);
@@ -454,6 +456,8 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             cc.T = T;
             cc.tol = 1e-11;
             cc.tab_stride = cfg.tab_stride;
+            cc.S_cap = cfg.S_cap;
+            cc.grid_doubles = cfg.grid_doubles;
             cc.D = cheb_degree(T, rate_max, K, mv.Dcap, ctx->smem_optin);
             cc.compact_tc = pv.gamma_stride == 0 ? 1 : 0;
             const double* tree_const = nullptr;
@@ -492,8 +496,9 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         }
         if (prof) cudaEventRecord(ctx->ev[4], st);
         const int S_stage = S_fixed > 0 ? S_fixed : std::min(cfg.S_cap, expected_steps(T, rate_max, M));
-        const size_t want_smem = (size_t)S_stage * K * L * 8;
-        rc = launch_sweep(ctx, M, f, pk, ctx->table.as<double>(), cfg.tab_stride, T, P, want_smem, only_flagged,
+        const size_t want_smem = ((size_t)cfg.grid_doubles + (size_t)S_stage * K * L) * 8;
+        rc = launch_sweep(ctx, M, f, pk, ctx->table.as<double>(), cfg.tab_stride, cfg.S_cap, cfg.grid_doubles, T, P,
+                          want_smem, only_flagged,
                           d_out_tree, d_status, st);
         if (rc) return rc;
         ++launches;

@@ -76,7 +76,8 @@ struct TrajCfg {
     double tol;                  // accepted error indicator
     int S_fixed;                 // > 0: use exactly this many cells for every pset (no adaptivity)
     int S_cap;                   // table capacity in cells (adaptive mode never exceeds it)
-    long long tab_stride;        // doubles per pset in the table
+    int grid_doubles;            // doubles reserved per pset for [τ_s | 1/h_s] ahead of the rows (even)
+    long long tab_stride;        // doubles per pset in the table (grid block + rows)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -163,8 +164,10 @@ __global__ void stadler_cond_kernel(ParamsView pv, PsetPack pk, double present_t
 //
 // Taylor recurrence for the h-scaled coefficients ĉ_n of p(τ_s + θh) = Σ ĉ_n θ^n:
 //   ĉ_{n+1} = h/(n+1) · [ −(λ+μ) ĉ_n + [n=0] μ(1−σ) + λ Σ_{m≤n} ĉ_m ĉ_{n−m} + δ Γ ĉ_n ]
-// which is dp_dt! (mbp.jl:266-278) expanded order by order.  Table row for (cell s, type x), L = M+2:
-//   row[0] = F(τ_s),  row[1] = h(2λĉ_0 − Λ),  row[n+1] = 2hλ ĉ_n/(n+1);   tab[p*stride + (s*K + x)*L + n].
+// which is dp_dt! (mbp.jl:266-278) expanded order by order.  Cells are NON-uniform: after every cell the
+// width is re-sized from the error indicator (|ĉ_M| + |ĉ_{M−1}| ~ h^M), a cell above tol is redone smaller.
+// Table row for (cell s, type x), L = M+2, θ = (τ − τ_s)/h_s:
+//   row[0] = F(τ_s),  row[1] = h(2λĉ_0 − Λ),  row[n+1] = 2hλ ĉ_n/(n+1).
 // KPL == 1 (K ≤ KP ≤ 32): the lane's row of δΓ lives in registers, ĉ_n is broadcast through shared memory.
 // KPL  > 1: δΓ is staged transposed in shared memory (lane-contiguous rows).
 // ------------------------------------------------------------------------------------------------
@@ -212,167 +215,180 @@ __global__ void __launch_bounds__(32) traj_kernel(ParamsView pv, PsetPack pk, Tr
     __syncwarp();
 
     const bool adaptive = cfg.S_fixed <= 0;
-    int S;
-    if (!adaptive) S = cfg.S_fixed;
-    else {
-        double want = ceil(cfg.T * rate / hrate_target_start(M));
-        if (!(want >= 4.0)) want = 4.0;                      // also catches NaN
-        if (want > (double)cfg.S_cap) want = (double)cfg.S_cap;
-        S = ladder_ceil((long long)want);
-        if (S > cfg.S_cap) S = cfg.S_cap;
-    }
-
+    // per-pset block of the table: [τ_s, s = 0..S_cap | 1/h_s, s < S_cap | pad][rows (cell, type) of L doubles]
     double* tabp = tab + (size_t)p * cfg.tab_stride;
+    double* gridp = tabp;
+    double* invhp = tabp + (cfg.S_cap + 1);
+    double* rowsp = tabp + cfg.grid_doubles;
     double pcur[KPL], Fcur[KPL];
-    double errmax = 0.0;
-    bool bad = false, failed = false, pilot = true, resized = false;
+#pragma unroll
+    for (int q = 0; q < KPL; ++q) { pcur[q] = own[q] ? 1.0 - rho : 0.0; Fcur[q] = 0.0; }   // p(0) = 1 − ρ, mbp.jl:130,141,226
+    // first cell width: optimistic guess from the fastest rate; the controller below corrects it
+    double h = adaptive ? hrate_target_start(M) / rate : cfg.T / (double)cfg.S_fixed;
+    if (!(h > 0.0) || !(h <= 0.25 * cfg.T)) h = adaptive ? 0.25 * cfg.T : cfg.T / (double)cfg.S_fixed;
+    double tau = 0.0;
+    float errmax = 0.0f;
+    // tolerance seen by the controller, a hair inside the double value so float rounding can only be stricter
+    const float tol_f = (float)cfg.tol * (1.0f - 1e-6f);
+    const float decade = exp2f(__log2f(0.1f) * (1.0f / (float)M));      // 0.1^(1/M)
+    bool bad = false, failed = false;
+    int s = 0, rejects = 0;
     for (;;) {
-        const double h = cfg.T / (double)S;
+        double hc = h;
+        bool last = false;
+        if (adaptive) { const double rem = cfg.T - tau; if (hc >= rem * (1.0 - 1e-3)) { hc = rem; last = true; } }
+        else if (s + 1 >= cfg.S_fixed) { hc = cfg.T - tau; last = true; }
+        double c[M + 1][KPL];
 #pragma unroll
-        for (int q = 0; q < KPL; ++q) { pcur[q] = own[q] ? 1.0 - rho : 0.0; Fcur[q] = 0.0; }   // p(0) = 1 − ρ, mbp.jl:130,141,226
-        errmax = 0.0;
-        bad = false;
-        bool restart = false;
-        for (int s = 0; s < S; ++s) {
-            double c[M + 1][KPL];
+        for (int q = 0; q < KPL; ++q) c[0][q] = pcur[q];
 #pragma unroll
-            for (int q = 0; q < KPL; ++q) c[0][q] = pcur[q];
+        for (int n = 0; n < M; ++n) {
+            double* buf = cb + (n & 1) * KS;
 #pragma unroll
-            for (int n = 0; n < M; ++n) {
-                double* buf = cb + (n & 1) * KS;
+            for (int q = 0; q < KPL; ++q)
+                if (own[q]) buf[lane + 32 * q] = c[n][q];
+            __syncwarp();
+            double dot[KPL];
+            if constexpr (KPL == 1) {
+                double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
-                for (int q = 0; q < KPL; ++q)
-                    if (own[q]) buf[lane + 32 * q] = c[n][q];
-                __syncwarp();
-                double dot[KPL];
-                if constexpr (KPL == 1) {
-                    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+                for (int j = 0; j < KP; j += 4) {
+                    const double2 v01 = *reinterpret_cast<const double2*>(buf + j);
+                    const double2 v23 = *reinterpret_cast<const double2*>(buf + j + 2);
+                    d0 = fma(g[j], v01.x, d0);
+                    d1 = fma(g[j + 1], v01.y, d1);
+                    d2 = fma(g[j + 2], v23.x, d2);
+                    d3 = fma(g[j + 3], v23.y, d3);
+                }
+                dot[0] = (d0 + d1) + (d2 + d3);
+            } else {
+                double d[KPL][2];
 #pragma unroll
-                    for (int j = 0; j < KP; j += 4) {
-                        const double2 v01 = *reinterpret_cast<const double2*>(buf + j);
-                        const double2 v23 = *reinterpret_cast<const double2*>(buf + j + 2);
-                        d0 = fma(g[j], v01.x, d0);
-                        d1 = fma(g[j + 1], v01.y, d1);
-                        d2 = fma(g[j + 2], v23.x, d2);
-                        d3 = fma(g[j + 3], v23.y, d3);
-                    }
-                    dot[0] = (d0 + d1) + (d2 + d3);
-                } else {
-                    double d[KPL][2];
+                for (int q = 0; q < KPL; ++q) d[q][0] = d[q][1] = 0.0;
+                int irow[KPL];
 #pragma unroll
-                    for (int q = 0; q < KPL; ++q) d[q][0] = d[q][1] = 0.0;
-                    int irow[KPL];
-#pragma unroll
-                    for (int q = 0; q < KPL; ++q) irow[q] = own[q] ? lane + 32 * q : 0;
-                    int j = 0;
+                for (int q = 0; q < KPL; ++q) irow[q] = own[q] ? lane + 32 * q : 0;
+                int j = 0;
 #pragma unroll 4
-                    for (; j + 1 < K; j += 2) {
-                        const double2 v = *reinterpret_cast<const double2*>(buf + j);
-                        const double* r0 = GT + (size_t)j * K;
+                for (; j + 1 < K; j += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(buf + j);
+                    const double* r0 = GT + (size_t)j * K;
 #pragma unroll
-                        for (int q = 0; q < KPL; ++q) {
-                            d[q][0] = fma(r0[irow[q]], v.x, d[q][0]);
-                            d[q][1] = fma(r0[K + irow[q]], v.y, d[q][1]);
-                        }
+                    for (int q = 0; q < KPL; ++q) {
+                        d[q][0] = fma(r0[irow[q]], v.x, d[q][0]);
+                        d[q][1] = fma(r0[K + irow[q]], v.y, d[q][1]);
                     }
-                    if (j < K) {
-                        const double v0 = buf[j];
-#pragma unroll
-                        for (int q = 0; q < KPL; ++q) d[q][0] = fma(GT[(size_t)j * K + irow[q]], v0, d[q][0]);
-                    }
-#pragma unroll
-                    for (int q = 0; q < KPL; ++q) dot[q] = d[q][0] + d[q][1];
                 }
-                const double hn = h * (1.0 / (double)(n + 1));
+                if (j < K) {
+                    const double v0 = buf[j];
 #pragma unroll
-                for (int q = 0; q < KPL; ++q) {
-                    // Σ_{m≤n} ĉ_m ĉ_{n−m} = 2 Σ_{m<n/2} ĉ_m ĉ_{n−m} (+ ĉ_{n/2}² when n is even)
-                    double cv0 = 0.0, cv1 = 0.0;
-#pragma unroll
-                    for (int m = 0; 2 * m < n; ++m) {
-                        if (m & 1) cv1 = fma(c[m][q], c[n - m][q], cv1);
-                        else cv0 = fma(c[m][q], c[n - m][q], cv0);
-                    }
-                    double conv = 2.0 * (cv0 + cv1);
-                    if ((n & 1) == 0) conv = fma(c[n / 2][q], c[n / 2][q], conv);
-                    double rhs = fma(lam[q], conv, dot[q]);
-                    rhs = fma(-a[q], c[n][q], rhs);
-                    if (n == 0) rhs += b;
-                    c[n + 1][q] = rhs * hn;
+                    for (int q = 0; q < KPL; ++q) d[q][0] = fma(GT[(size_t)j * K + irow[q]], v0, d[q][0]);
                 }
+#pragma unroll
+                for (int q = 0; q < KPL; ++q) dot[q] = d[q][0] + d[q][1];
             }
-            // emit the F polynomial of this cell, advance p and F to the next grid point
-            bool over = false;
+            const double hn = hc * (1.0 / (double)(n + 1));
 #pragma unroll
             for (int q = 0; q < KPL; ++q) {
-                const int i = lane + 32 * q;
-                double row[L];
-                row[0] = Fcur[q];
-                row[1] = h * (2.0 * lam[q] * c[0][q] - Lam[q]);
-                const double h2l = 2.0 * h * lam[q];
-                double psum = 0.0, fsum = 0.0;
+                // Σ_{m≤n} ĉ_m ĉ_{n−m} = 2 Σ_{m<n/2} ĉ_m ĉ_{n−m} (+ ĉ_{n/2}² when n is even)
+                double cv0 = 0.0, cv1 = 0.0;
 #pragma unroll
-                for (int n = M; n >= 1; --n) {
-                    row[n + 1] = (h2l * (1.0 / (double)(n + 1))) * c[n][q];
-                    fsum += row[n + 1];
-                    psum += c[n][q];
+                for (int m = 0; 2 * m < n; ++m) {
+                    if (m & 1) cv1 = fma(c[m][q], c[n - m][q], cv1);
+                    else cv0 = fma(c[m][q], c[n - m][q], cv0);
                 }
-                if (own[q]) {
-                    double2* dst = reinterpret_cast<double2*>(tabp + ((size_t)s * K + i) * L);
-#pragma unroll
-                    for (int n = 0; n < L; n += 2) dst[n >> 1] = make_double2(row[n], row[n + 1]);
-                }
-                Fcur[q] += fsum + row[1];
-                pcur[q] = psum + c[0][q];
-                const double ind = fabs(c[M][q]) + fabs(c[M - 1][q]);
-                if (own[q]) {
-                    if (!(ind <= errmax)) errmax = ind;                 // NaN-propagating max
-                    if (!(ind <= cfg.tol)) over = true;
-                    if (!(pcur[q] >= -1e-9 && pcur[q] <= 1.0 + 1e-9)) bad = true;   // isoutofdomain, mbp.jl:146,204,231
-                }
-            }
-            if (adaptive && __any_sync(FULL, over)) { restart = true; break; }
-            if (adaptive && pilot && s == 0) {
-                // Pilot: the indicator peaks in the first cell(s) (the transient away from p(0) = 1 − ρ) and
-                // scales like h^M, so one cell is enough to size the grid; re-start on the right rung.
-                pilot = false;
-                const double w0 = warp_max_nan(errmax);
-                double f = 1.1 * pow(w0 / cfg.tol, 1.0 / (double)M);
-                if (!(f >= 0.0)) f = 1.0;
-                int Sp = ladder_ceil((long long)ceil((double)S * f));
-                if (Sp > cfg.S_cap) Sp = cfg.S_cap;
-                if (Sp < S) { S = Sp; resized = true; break; }
+                double conv = 2.0 * (cv0 + cv1);
+                if ((n & 1) == 0) conv = fma(c[n / 2][q], c[n / 2][q], conv);
+                double rhs = fma(lam[q], conv, dot[q]);
+                rhs = fma(-a[q], c[n][q], rhs);
+                if (n == 0) rhs += b;
+                c[n + 1][q] = rhs * hn;
             }
         }
-        if (resized) { resized = false; continue; }
-        if (!restart) break;
-        if (S >= cfg.S_cap) { failed = true; break; }
-        // under-resolved: the indicator scales like h^M, so grow the step count accordingly and start over
-        pilot = false;
-        const double worst = warp_max_nan(errmax);
-        double grow = 2.0;
-        if (worst == worst && !isinf(worst)) grow = 1.1 * pow(worst / cfg.tol, 1.0 / (double)M);
-        if (!(grow >= 1.0)) grow = 1.25;
-        if (grow > 8.0) grow = 8.0;
-        int Snew = ladder_ceil((long long)ceil((double)S * grow));
-        if (Snew <= S) Snew = ladder_next(S);
-        if (Snew > cfg.S_cap) Snew = cfg.S_cap;
-        S = Snew;
+        // error indicator of this cell: the last two Taylor terms, maximum over the pset's types
+        double ind = 0.0;
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+            const double v = fabs(c[M][q]) + fabs(c[M - 1][q]);
+            if (own[q] && !(v <= ind)) ind = v;
+        }
+        // Warp maximum through the float image of the indicator (one REDUX on its bit pattern; non-negative
+        // floats order like their bits and NaN sorts above +Inf).  Single precision is ample for step control,
+        // and every lane sees the same value, so accept/reject decisions are warp-uniform and deterministic.
+        const float ind_f = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fabsf((float)ind))));
+        // (tol/ind)^(1/M) in single precision: the controller needs two digits, not sixteen
+        const float ratio = exp2f(__log2f(tol_f / ind_f) * (1.0f / (float)M));
+        if (adaptive && !(ind_f <= tol_f)) {
+            // reject: the indicator scales like h^M — shrink the cell accordingly and redo it
+            float f = 0.9f * ratio;
+            if (!(f >= 0.2f)) f = 0.2f;
+            if (f > 0.9f) f = 0.9f;
+            h = hc * (double)f;
+            if (++rejects > 200 || !(h > cfg.T * 1e-10)) { failed = true; break; }
+            continue;
+        }
+        if (s >= cfg.S_cap) { failed = true; break; }
+        // accept: emit the F polynomial of this cell, advance p and F to the next grid point
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+            const int i = lane + 32 * q;
+            double row[L];
+            row[0] = Fcur[q];
+            row[1] = hc * (2.0 * lam[q] * c[0][q] - Lam[q]);
+            const double h2l = 2.0 * hc * lam[q];
+            double psum = 0.0, fsum = 0.0;
+#pragma unroll
+            for (int n = M; n >= 1; --n) {
+                row[n + 1] = (h2l * (1.0 / (double)(n + 1))) * c[n][q];
+                fsum += row[n + 1];
+                psum += c[n][q];
+            }
+            if (own[q]) {
+                double2* dst = reinterpret_cast<double2*>(rowsp + ((size_t)s * K + i) * L);
+#pragma unroll
+                for (int n = 0; n < L; n += 2) dst[n >> 1] = make_double2(row[n], row[n + 1]);
+            }
+            Fcur[q] += fsum + row[1];
+            pcur[q] = psum + c[0][q];
+            if (own[q] && !(pcur[q] >= -1e-9 && pcur[q] <= 1.0 + 1e-9)) bad = true;   // isoutofdomain, mbp.jl:146,204,231
+        }
+        if (lane == 0) { gridp[s] = tau; invhp[s] = 1.0 / hc; }
+        if (!(ind_f <= errmax)) errmax = ind_f;
+        ++s;
+        if (last) break;
+        tau += hc;
+        if (adaptive) {
+            // next cell: aim a decade below tol; never more than double, never less than half
+            float f = 0.9f * decade * ratio;
+            if (!(f <= 2.0f)) f = 2.0f;            // also ind == 0 → +Inf, NaN
+            if (f < 0.5f) f = 0.5f;
+            h = hc * (double)f;
+        }
     }
+    if (lane == 0) gridp[s] = cfg.T;
     // conditioning term and diagnostics
 #pragma unroll
     for (int q = 0; q < KPL; ++q) {
         const int i = lane + 32 * q;
         if (own[q]) pk.logcond[(size_t)p * K + i] = log1p(-pcur[q]);   // log(1 − p_i(T)), mbp.jl:244-245
     }
-    errmax = warp_max_nan(errmax);
-    const bool unresolved = failed || !(errmax <= cfg.tol);
+    const bool unresolved = failed || !(errmax <= tol_f);
     const bool anybad = __any_sync(FULL, bad) || unresolved;
     if (lane == 0) {
-        pk.perr[p] = errmax;
-        pk.S[p] = S;
+        pk.perr[p] = (double)errmax;
+        pk.S[p] = s > 0 ? s : 1;
         if (anybad) pk.pstatus[p] |= ST_SOLVER;
     }
+}
+
+// Cell containing τ on a pset's (non-uniform) grid: largest s < S with grid[s] ≤ τ.
+__device__ __forceinline__ int find_cell(const double* __restrict__ grid, int S, double tau) {
+    int lo = 0, hi = S - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (grid[mid] <= tau) lo = mid; else hi = mid - 1;
+    }
+    return lo;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -428,8 +444,9 @@ __device__ __forceinline__ double eval_row(const double* __restrict__ row, doubl
 
 template <int M, bool SMEM>
 __device__ __forceinline__ double tree_items_sum(const ForestView& fv, const double* __restrict__ tp,
-                                                 const double* __restrict__ nt, int K, int S, double T, double scale,
-                                                 int64_t i0, int64_t i1, int lane) {
+                                                 const double* __restrict__ nt, int K, int S, int S_cap, int grid_doubles,
+                                                 double T, int64_t i0, int64_t i1, int lane) {
+    // tp = the pset's block: [τ_s | 1/h_s | pad][rows]
     constexpr int L = M + 2;
     double acc0 = 0.0, acc1 = 0.0;
     for (int64_t i = i0 + lane; i < i1; i += 64) {
@@ -439,12 +456,12 @@ __device__ __forceinline__ double tree_items_sum(const ForestView& fv, const dou
         const int2 me0 = fv.it_meta[i];
         const double tm1 = has2 ? fv.it_time[j] : tm0;
         const int2 me1 = has2 ? fv.it_meta[j] : me0;
-        const double u0 = (T - tm0) * scale, u1 = (T - tm1) * scale;
-        int s0 = (int)u0, s1 = (int)u1;
-        s0 = s0 > S - 1 ? S - 1 : (s0 < 0 ? 0 : s0);
-        s1 = s1 > S - 1 ? S - 1 : (s1 < 0 ? 0 : s1);
-        const double f0 = eval_row<M, SMEM>(tp + ((size_t)s0 * K + (me0.x & 0xffffff)) * L, u0 - (double)s0);
-        const double f1 = eval_row<M, SMEM>(tp + ((size_t)s1 * K + (me1.x & 0xffffff)) * L, u1 - (double)s1);
+        const double ta0 = T - tm0, ta1 = T - tm1;
+        const int s0 = find_cell(tp, S, ta0), s1 = find_cell(tp, S, ta1);
+        const double* invh = tp + (S_cap + 1);
+        const double* rows = tp + grid_doubles;
+        const double f0 = eval_row<M, SMEM>(rows + ((size_t)s0 * K + (me0.x & 0xffffff)) * L, (ta0 - tp[s0]) * invh[s0]);
+        const double f1 = eval_row<M, SMEM>(rows + ((size_t)s1 * K + (me1.x & 0xffffff)) * L, (ta1 - tp[s1]) * invh[s1]);
         acc0 = fma((double)(me0.x >> 24), f0, acc0);
         if (me0.y >= 0) acc0 += __ldg(nt + me0.y);
         if (has2) {
@@ -464,7 +481,8 @@ constexpr int SWEEP_THREADS = 768;   // 24 warps share one staged table; one CTA
 
 template <int M>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(ForestView fv, PsetPack pk, const double* __restrict__ tab,
-                                                    long long tab_stride, const int64_t* __restrict__ chunk_off,
+                                                    long long tab_stride, int S_cap, int grid_doubles,
+                                                    const int64_t* __restrict__ chunk_off,
                                                     int n_chunks, int P, double T, int smem_doubles,
                                                     const int* __restrict__ only_flagged,
                                                     double* __restrict__ out_tree, int32_t* __restrict__ status) {
@@ -483,7 +501,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(ForestView fv, 
     bool in_smem = false;
     const double* tp = nullptr;
     const double* nt = nullptr;
-    double lmusig = 0.0, lrho = 0.0, scale = 0.0;
+    double lmusig = 0.0, lrho = 0.0;
     for (long long u = u_lo; u < u_hi; ++u) {
         const int p = (int)(u / n_chunks);
         const int ch = (int)(u - (long long)p * n_chunks);
@@ -499,9 +517,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(ForestView fv, 
             nt = pk.nt + (size_t)p * pk.ntw;
             lmusig = nt[K + K * K];
             lrho = nt[K + K * K + 1];
-            scale = (double)S / T;
             const double* src = tab + (size_t)p * tab_stride;
-            const long long n = (long long)S * K * L;
+            const long long n = grid_doubles + (long long)S * K * L;      // grid block + the cells actually used
             in_smem = n <= smem_doubles && !(pst & ST_SOLVER);
             if (in_smem) {
                 if (threadIdx.x == 0) {
@@ -527,8 +544,8 @@ __global__ void __launch_bounds__(SWEEP_THREADS, 1) sweep_kernel(ForestView fv, 
             const int64_t i0 = fv.item_off[t], i1 = fv.item_off[t + 1];
             double acc;
             if (pst & ST_SOLVER) acc = 0.0;
-            else if (in_smem) acc = tree_items_sum<M, true>(fv, tp, nt, K, S, T, scale, i0, i1, lane);
-            else acc = tree_items_sum<M, false>(fv, tp, nt, K, S, T, scale, i0, i1, lane);
+            else if (in_smem) acc = tree_items_sum<M, true>(fv, tp, nt, K, S, S_cap, grid_doubles, T, i0, i1, lane);
+            else acc = tree_items_sum<M, false>(fv, tp, nt, K, S, S_cap, grid_doubles, T, i0, i1, lane);
             if (lane == 0) {
                 const int rt = fv.root_type[t];
                 double r = acc + count_times_log(fv.n_death[t], lmusig) + count_times_log(fv.n_surv[t], lrho)

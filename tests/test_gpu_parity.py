@@ -72,7 +72,7 @@ def test_every_taylor_order_converges(ctx, order):
     forest = gcdyn.Forest(flat, None, T, ctx=ctx)
     _check(forest, params, T, "ode", exp["ode_branch"], order=order)
     d = ctx.last_diag(params.n_psets)
-    assert d["order"] == order and d["steps"] >= 4 and np.all(d["err_indicator"] <= 1e-11)
+    assert d["order"] == order and d["steps"] >= 2 and np.all(d["err_indicator"] <= 1e-11)
 
 
 def test_steps_refinement_and_explicit_steps(ctx):
