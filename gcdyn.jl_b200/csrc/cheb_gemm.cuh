@@ -150,14 +150,19 @@ __global__ void __launch_bounds__(512) cheb_kernel(ParamsView pv, PsetPack pk, M
     for (int m = threadIdx.x; m < 2 * D; m += blockDim.x) costab[m] = cospi((double)m / (double)D);
     __syncthreads();
     const double* tp = tab + (size_t)p * cfg.tab_stride;
-    const double* invh = tp + (cfg.S_cap + 1);
     const double* rows = tp + cfg.grid_doubles;
+    // the pset's grid [τ_s | 1/h_s] goes to shared memory first: the cell search is then a few LDS, not L2 round trips
+    double* sgrid = Acoef + (size_t)(D + 1) * K + 2 * (size_t)(D / 2 + 1) * K;   // [S+1], then [S]
+    double* sinvh = sgrid + (S + 1);
+    for (int i = threadIdx.x; i <= S; i += blockDim.x) sgrid[i] = tp[i];
+    for (int i = threadIdx.x; i < S; i += blockDim.x) sinvh[i] = tp[cfg.S_cap + 1 + i];
+    __syncthreads();
     if (!(pst & ST_SOLVER)) {
         for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
             const int k = idx / K, x = idx - k * K;
             const double tau = cfg.T * (1.0 + costab[k]) * 0.5;
-            const int s = find_cell(tp, S, tau);
-            V[idx] = eval_row<M, false>(rows + ((size_t)s * K + x) * L, (tau - tp[s]) * invh[s]);
+            const int s = find_cell(sgrid, S, tau);
+            V[idx] = eval_row<M, false>(rows + ((size_t)s * K + x) * L, (tau - sgrid[s]) * sinvh[s]);
         }
     } else {
         for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) V[idx] = 0.0;
@@ -277,7 +282,8 @@ __global__ void __launch_bounds__(512) cheb_kernel(ParamsView pv, PsetPack pk, M
 // CTA tile 32(p) × 32(t), 4 warps of 16×16, k-chunks of 32 staged through shared memory with cp.async
 // (2 stages), row stride 36 doubles (conflict-free for the m8n8k4 fragment pattern: row = lane/4, k = lane%4).
 // ------------------------------------------------------------------------------------------------
-constexpr int GT_TILE = 32, GT_KC = 32, GT_LD = 36;
+constexpr int GT_TILE = 32, GT_KC = 32, GT_LD = 36, GT_STAGES = 4;
+constexpr int GT_SMEM_BYTES = GT_STAGES * 2 * GT_TILE * GT_LD * 8;
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
     const int n = valid ? 16 : 0;
@@ -297,8 +303,9 @@ __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A,
                                                    const int* __restrict__ pstatus, const int* __restrict__ need_sweep,
                                                    const uint8_t* __restrict__ self_loop, double* __restrict__ out_tree,
                                                    int32_t* __restrict__ status) {
-    __shared__ __align__(16) double As[2][GT_TILE * GT_LD];
-    __shared__ __align__(16) double Bs[2][GT_TILE * GT_LD];
+    extern __shared__ __align__(16) double gsm[];          // GT_STAGES × (A tile | B tile)
+    auto As = [&](int st) { return gsm + (size_t)st * 2 * GT_TILE * GT_LD; };
+    auto Bs = [&](int st) { return gsm + (size_t)st * 2 * GT_TILE * GT_LD + GT_TILE * GT_LD; };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int p0 = blockIdx.y * GT_TILE;
     const int64_t t0 = (int64_t)blockIdx.x * GT_TILE;
@@ -328,8 +335,8 @@ __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A,
             const bool vb = inj && (t0 + row) < T;
             const double* sa = A + (size_t)(va ? p0 + row : 0) * Jst + (va ? j : 0);
             const double* sb = Mt + (size_t)(vb ? t0 + row : 0) * Jst + (vb ? j : 0);
-            cp_async16(&As[buf][row * GT_LD + col], sa, va);
-            cp_async16(&Bs[buf][row * GT_LD + col], sb, vb);
+            cp_async16(As(buf) + row * GT_LD + col, sa, va);
+            cp_async16(Bs(buf) + row * GT_LD + col, sb, vb);
         }
         cp_async_commit();
     };
@@ -340,14 +347,18 @@ __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A,
         for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
     const int wr = (warp >> 1) * 16, wc = (warp & 1) * 16;     // warp's 16×16 sub-tile (p rows, t cols)
     const int fr = lane >> 2, fk = lane & 3;
-    if (nchunks > 0) issue(0, 0);
+    // multi-stage cp.async pipeline: GT_STAGES−1 chunks in flight, one barrier per chunk
+#pragma unroll
+    for (int st = 0; st < GT_STAGES - 1; ++st) {
+        if (st < nchunks) issue(st, st); else cp_async_commit();
+    }
     for (int ch = 0; ch < nchunks; ++ch) {
-        const int buf = ch & 1;
-        if (ch + 1 < nchunks) { issue(ch + 1, buf ^ 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
-        const double* as = As[buf];
-        const double* bs = Bs[buf];
+        cp_async_wait<GT_STAGES - 2>();
+        __syncthreads();                      // chunk ch has landed for everyone; buffer (ch−1) % STAGES is free
+        const int nxt = ch + GT_STAGES - 1;
+        if (nxt < nchunks) issue(nxt, nxt % GT_STAGES); else cp_async_commit();
+        const double* as = As(ch % GT_STAGES);
+        const double* bs = Bs(ch % GT_STAGES);
 #pragma unroll
         for (int kk = 0; kk < GT_KC / 4; ++kk) {
             const double a0 = as[(wr + fr) * GT_LD + kk * 4 + fk];
@@ -359,7 +370,6 @@ __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A,
             dmma_m8n8k4(acc[1][0][0], acc[1][0][1], a1, b0);
             dmma_m8n8k4(acc[1][1][0], acc[1][1][1], a1, b1);
         }
-        __syncthreads();
     }
     // epilogue: C fragment (row = lane/4, cols = 2*(lane%4) + {0,1})
 #pragma unroll

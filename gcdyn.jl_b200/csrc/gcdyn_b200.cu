@@ -68,6 +68,7 @@ struct gcdyn_ctx {
     bool profile = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int last_cheb_D = 0;
+    bool gemm_attr_set = false;
     bool ev_valid = false;
 };
 
@@ -282,9 +283,13 @@ template <int M>
 int launch_traj_m(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, double* tab,
                   cudaStream_t st) {
     const int K = pv.K;
+    if (K <= 4) return launch_traj_inst<M, 4, 1>(ctx, pv, pk, cfg, tab, st);
     if (K <= 8) return launch_traj_inst<M, 8, 1>(ctx, pv, pk, cfg, tab, st);
+    if (K <= 12) return launch_traj_inst<M, 12, 1>(ctx, pv, pk, cfg, tab, st);
     if (K <= 16) return launch_traj_inst<M, 16, 1>(ctx, pv, pk, cfg, tab, st);
+    if (K <= 20) return launch_traj_inst<M, 20, 1>(ctx, pv, pk, cfg, tab, st);
     if (K <= 24) return launch_traj_inst<M, 24, 1>(ctx, pv, pk, cfg, tab, st);
+    if (K <= 28) return launch_traj_inst<M, 28, 1>(ctx, pv, pk, cfg, tab, st);
     if (K <= 32) return launch_traj_inst<M, 32, 1>(ctx, pv, pk, cfg, tab, st);
     if (K <= 64) return launch_traj_inst<M, 0, 2>(ctx, pv, pk, cfg, tab, st);
     return launch_traj_inst<M, 0, 4>(ctx, pv, pk, cfg, tab, st);
@@ -339,21 +344,21 @@ int launch_sweep(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& p
 
 // Chebyshev interpolation degree for this batch: generous (the kernel trims to the effective degree),
 // even, ≤ the moment cap and small enough for cheb_kernel's shared memory.
-int cheb_degree(double T, double rate_max, int K, int Dcap, int smem_optin) {
+int cheb_degree(double T, double rate_max, int K, int Dcap, int S_cap, int smem_optin) {
     double want = T * rate_max + 12.0;
     if (!(want == want)) want = 32.0;
     const int ladder[] = {32, 48, 64, 96, 128};
     int D = 128;
     for (int d : ladder) if ((double)d >= want) { D = d; break; }
     D = std::min(D, Dcap);
-    while (D > 16 && (2 * (size_t)D + (3 * (size_t)D + 4) * K) * 8 + 1024 > (size_t)smem_optin) D -= 8;
+    while (D > 16 && (2 * (size_t)D + (3 * (size_t)D + 4) * K + 2 * (size_t)S_cap + 8) * 8 + 1024 > (size_t)smem_optin) D -= 8;
     return D & ~1;
 }
 
 template <int M>
 int launch_cheb_m(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const MomentView& mv, const ChebCfg& cc,
                   const double* tab, double* A, int* need_sweep, int* d_common, int P, cudaStream_t st) {
-    const size_t smem = (2 * (size_t)cc.D + (3 * (size_t)cc.D + 4) * mv.K) * 8;
+    const size_t smem = (2 * (size_t)cc.D + (3 * (size_t)cc.D + 4) * mv.K + 2 * (size_t)cc.S_cap + 8) * 8;
     if (smem > 48 * 1024)
         CU_TRY(ctx, cudaFuncSetAttribute(cheb_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cheb_kernel<M><<<P, 512, smem, st>>>(pv, pk, mv, cc, tab, A, need_sweep, d_common);
@@ -458,7 +463,7 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             cc.tab_stride = cfg.tab_stride;
             cc.S_cap = cfg.S_cap;
             cc.grid_doubles = cfg.grid_doubles;
-            cc.D = cheb_degree(T, rate_max, K, mv.Dcap, ctx->smem_optin);
+            cc.D = cheb_degree(T, rate_max, K, mv.Dcap, cfg.S_cap, ctx->smem_optin);
             cc.compact_tc = pv.gamma_stride == 0 ? 1 : 0;
             const double* tree_const = nullptr;
             if (cc.compact_tc) {
@@ -483,7 +488,11 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             ++launches;
             if (prof) cudaEventRecord(ctx->ev[3], st);
             dim3 grid((unsigned)((Tn + GT_TILE - 1) / GT_TILE), (unsigned)((P + GT_TILE - 1) / GT_TILE));
-            gemm_kernel<<<grid, 128, 0, st>>>(ctx->gemm_a.as<double>(), mv, cc.compact_tc ? 0 : 1, d_common, P, Tn,
+            if (!ctx->gemm_attr_set) {
+                CU_TRY(ctx, cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
+                ctx->gemm_attr_set = true;
+            }
+            gemm_kernel<<<grid, 128, GT_SMEM_BYTES, st>>>(ctx->gemm_a.as<double>(), mv, cc.compact_tc ? 0 : 1, d_common, P, Tn,
                                               tree_const, pk.pstatus, need_sweep, f->v.self_loop, d_out_tree, d_status);
             CU_TRY(ctx, cudaGetLastError());
             ++launches;
