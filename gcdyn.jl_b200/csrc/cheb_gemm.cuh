@@ -22,25 +22,6 @@
 
 namespace gcdyn {
 
-struct MomentView {
-    int K;
-    int C1;                // 2K + 4: start of the Chebyshev block
-    int Dcap;              // moments exist for d = 0..Dcap
-    long long Jtc;         // start of the K² type-change block
-    long long Jst;         // row stride of Mt and A (doubles), multiple of 4
-    const double* Mt;      // [T][Jst]
-    const double* colsum;  // [Jst] forest-level column sums (only count columns are consulted)
-};
-
-struct ChebCfg {
-    double T;
-    double tol;            // accepted Chebyshev tail (absolute, on F)
-    int D;                 // interpolation degree (≤ Dcap), even
-    int compact_tc;        // 1: Γ shared — log δ column + per-tree constant; 0: K² type-change columns
-    int S_cap, grid_doubles;   // layout of a pset's table block: [τ_s | 1/h_s | pad][rows]
-    long long tab_stride;
-};
-
 // ------------------------------------------------------------------------------------------------
 // moments_kernel: one CTA per tree (run once per forest and present_time).
 // ------------------------------------------------------------------------------------------------
@@ -125,156 +106,6 @@ __global__ void tc_const_kernel(MomentView mv, int64_t T, const double* __restri
     }
     acc = warp_sum(acc);
     if (lane == 0) tree_const[t] = acc;
-}
-
-// ------------------------------------------------------------------------------------------------
-// cheb_kernel: one CTA per pset.  Values of F_x at the D+1 Chebyshev–Gauss–Lobatto nodes from the pset's
-// Taylor table, DCT-I → a[d][x]; effective degree; count-column coefficients; fallback flag.
-// ------------------------------------------------------------------------------------------------
-template <int M>
-__global__ void __launch_bounds__(512) cheb_kernel(ParamsView pv, PsetPack pk, MomentView mv, ChebCfg cfg,
-                                                   const double* __restrict__ tab, double* __restrict__ A,
-                                                   int* __restrict__ need_sweep, int* __restrict__ d_common) {
-    extern __shared__ __align__(16) double sm[];
-    constexpr int L = M + 2;
-    const int p = blockIdx.x;
-    const int K = mv.K, C1 = mv.C1, D = cfg.D;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    double* costab = sm;                   // [2D]  cos(π m / D)
-    double* V = costab + 2 * D;            // [(D+1)*K] node values
-    double* Acoef = V + (size_t)(D + 1) * K;   // [(D+1)*K] coefficients
-    __shared__ int s_deff, s_flag;
-    const int S = pk.S[p];
-    const int pst = pk.pstatus[p];
-    if (threadIdx.x == 0) { s_deff = 8; s_flag = (pst & ST_SOLVER) ? 1 : 0; }
-    for (int m = threadIdx.x; m < 2 * D; m += blockDim.x) costab[m] = cospi((double)m / (double)D);
-    __syncthreads();
-    const double* tp = tab + (size_t)p * cfg.tab_stride;
-    const double* rows = tp + cfg.grid_doubles;
-    // the pset's grid [τ_s | 1/h_s] goes to shared memory first: the cell search is then a few LDS, not L2 round trips
-    double* sgrid = Acoef + (size_t)(D + 1) * K + 2 * (size_t)(D / 2 + 1) * K;   // [S+1], then [S]
-    double* sinvh = sgrid + (S + 1);
-    for (int i = threadIdx.x; i <= S; i += blockDim.x) sgrid[i] = tp[i];
-    for (int i = threadIdx.x; i < S; i += blockDim.x) sinvh[i] = tp[cfg.S_cap + 1 + i];
-    __syncthreads();
-    if (!(pst & ST_SOLVER)) {
-        for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
-            const int k = idx / K, x = idx - k * K;
-            const double tau = cfg.T * (1.0 + costab[k]) * 0.5;
-            const int s = find_cell(sgrid, S, tau);
-            V[idx] = eval_row<M, false>(rows + ((size_t)s * K + x) * L, (tau - sgrid[s]) * sinvh[s]);
-        }
-    } else {
-        for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) V[idx] = 0.0;
-    }
-    __syncthreads();
-    // DCT-I with the symmetry cos(π(D−k)d/D) = (−1)^d cos(πkd/D): fold the node values into an even and an
-    // odd half, E_k = w_k (V_k + V_{D−k}), O_k = w_k (V_k − V_{D−k}), k = 0..D/2, w_0 = w_{D/2} = 1/2.
-    const int H = D / 2;
-    double* EO = Acoef + (size_t)(D + 1) * K;        // [2][(H+1)*K]
-    for (int idx = threadIdx.x; idx < (H + 1) * K; idx += blockDim.x) {
-        const int k = idx / K, x = idx - k * K;
-        const double w = (k == 0 || k == H) ? 0.5 : 1.0;
-        const double a = V[k * K + x], b = V[(D - k) * K + x];
-        EO[idx] = w * (a + b);
-        EO[(H + 1) * K + idx] = w * (a - b);
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
-        const int d = idx / K, x = idx - d * K;
-        const double* src = EO + (size_t)(d & 1) * (H + 1) * K + x;
-        double s0 = 0.0, s1 = 0.0;
-        int m = 0;                                   // (k*d) mod 2D, advanced incrementally
-        int k = 0;
-        for (; k + 1 <= H; k += 2) {
-            s0 = fma(src[k * K], costab[m], s0);
-            m += d; m -= (m >= 2 * D) ? 2 * D : 0;
-            s1 = fma(src[(k + 1) * K], costab[m], s1);
-            m += d; m -= (m >= 2 * D) ? 2 * D : 0;
-        }
-        if (k <= H) s0 = fma(src[k * K], costab[m], s0);
-        double a = (2.0 / (double)D) * (s0 + s1);
-        if (d == 0 || d == D) a *= 0.5;
-        Acoef[idx] = a;
-    }
-    __syncthreads();
-    // effective degree per type (a warp per type, lanes over degrees): the smallest d with Σ_{k>d}|a_k| ≤ tol;
-    // the series counts as unresolved if its last three terms are not small
-    for (int x = warp; x < K; x += nwarps) {
-        // lane owns the contiguous degrees [lo, hi); suffix sums of |a| are combined across lanes
-        const int per = (D + 1 + 31) / 32;
-        const int lo = lane * per, hi = min(D + 1, lo + per);
-        double mine = 0.0;
-        for (int d = lo; d < hi; ++d) mine += fabs(Acoef[d * K + x]);
-        double above = 0.0;                        // Σ over lanes > lane
-        {
-            double run = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double v = __shfl_down_sync(FULL, run, o);
-                if (lane + o < 32) run += v;
-            }
-            above = run - mine;
-        }
-        int found = 8;
-        double tail = above;
-        for (int d = hi - 1; d >= lo && d > 8; --d) {
-            tail += fabs(Acoef[d * K + x]);
-            if (!(tail <= cfg.tol)) { found = d; break; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) found = max(found, __shfl_xor_sync(FULL, found, o));
-        if (lane == 0) {
-            const double last3 = fabs(Acoef[D * K + x]) + fabs(Acoef[(D - 1) * K + x]) + fabs(Acoef[(D - 2) * K + x]);
-            if (!(last3 <= cfg.tol)) atomicExch(&s_flag, 1);
-            atomicMax(&s_deff, found);
-        }
-    }
-    __syncthreads();
-    const int deff = s_deff;
-    double* Arow = A + (size_t)p * mv.Jst;
-    for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
-        const int d = idx / K;
-        Arow[C1 + idx] = d <= deff ? Acoef[idx] : 0.0;
-    }
-    // the GEMM rounds its column ranges up to multiples of 4: keep the padding finite
-    if (threadIdx.x < 4) {
-        const long long j = C1 + (long long)(D + 1) * K + threadIdx.x;
-        if (j < mv.Jtc) Arow[j] = 0.0;
-        const long long j2 = mv.Jtc + (long long)K * K + threadIdx.x;
-        if (j2 < mv.Jst) Arow[j2] = 0.0;
-    }
-    // count columns
-    const double* nt = pk.nt + (size_t)p * pk.ntw;
-    for (int c = threadIdx.x; c < C1; c += blockDim.x) {
-        double v = 0.0;
-        if (c < K) v = nt[c];                                         // log λ_x
-        else if (c == K) v = nt[K + K * K];                           // log μ + log σ
-        else if (c == K + 1) v = nt[K + K * K + 1];                   // log ρ
-        else if (c < 2 * K + 2) v = -pk.logcond[(size_t)p * K + (c - K - 2)];
-        else if (c == 2 * K + 2) v = cfg.compact_tc ? log(pv.delta[p]) : 0.0;
-        if (!isfinite(v)) {
-            if (mv.colsum[c] != 0.0) atomicExch(&s_flag, 1);
-            v = 0.0;
-        }
-        Arow[c] = v;
-    }
-    if (!cfg.compact_tc) {
-        for (int e = threadIdx.x; e < K * K; e += blockDim.x) {
-            double v = nt[K + e];
-            const bool diag = (e / K) == (e % K);          // self-loop column: trees using it are −Inf anyway
-            if (!isfinite(v)) {
-                if (!diag && mv.colsum[mv.Jtc + e] != 0.0) atomicExch(&s_flag, 1);
-                v = 0.0;
-            }
-            Arow[mv.Jtc + e] = v;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        need_sweep[p] = s_flag;
-        if (!s_flag) atomicMax(d_common, deff);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -267,42 +267,50 @@ int carve_pack(gcdyn_ctx* ctx, int P, int K, PsetPack* pk) {
     return GCDYN_OK;
 }
 
+// Dynamic shared memory of traj_kernel: [ĉ broadcast buffer | δΓ (K > 32 only)] for the integrating warp, then the
+// Chebyshev stage's scratch [cos table | node values | coefficients | folded halves | grid].  Mirrors the kernel.
+size_t traj_smem_bytes(int K, int D, int S_cap) {
+    const size_t KS = ((size_t)K + 3) & ~(size_t)3;
+    size_t n = 2 * KS + (K <= 32 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
+    if (D > 0) n += 2 * (size_t)D + (3 * (size_t)D + 4) * K + 2 * (size_t)S_cap + 8;
+    return n * sizeof(double);
+}
+
 template <int M, int KP, int KPL>
-int launch_traj_inst(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, double* tab,
-                     cudaStream_t st) {
-    const size_t KS = KPL == 1 ? (size_t)KP : (((size_t)pv.K + 3) & ~(size_t)3);
-    const size_t smem = (2 * KS + (KPL == 1 ? 0 : (size_t)pv.K * pv.K)) * sizeof(double);
+int launch_traj_inst(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, const ChebCfg& cc,
+                     double* tab, cudaStream_t st) {
+    const size_t smem = traj_smem_bytes(pv.K, cc.D, cfg.S_cap);
     if (smem > 48 * 1024)
         CU_TRY(ctx, cudaFuncSetAttribute(traj_kernel<M, KP, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    traj_kernel<M, KP, KPL><<<pv.P, 32, smem, st>>>(pv, pk, cfg, tab);
+    traj_kernel<M, KP, KPL><<<pv.P, TRAJ_THREADS, smem, st>>>(pv, pk, cfg, cc, tab);
     CU_TRY(ctx, cudaGetLastError());
     return GCDYN_OK;
 }
 
 template <int M>
-int launch_traj_m(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, double* tab,
-                  cudaStream_t st) {
+int launch_traj_m(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, const ChebCfg& cc,
+                  double* tab, cudaStream_t st) {
     const int K = pv.K;
-    if (K <= 4) return launch_traj_inst<M, 4, 1>(ctx, pv, pk, cfg, tab, st);
-    if (K <= 8) return launch_traj_inst<M, 8, 1>(ctx, pv, pk, cfg, tab, st);
-    if (K <= 12) return launch_traj_inst<M, 12, 1>(ctx, pv, pk, cfg, tab, st);
-    if (K <= 16) return launch_traj_inst<M, 16, 1>(ctx, pv, pk, cfg, tab, st);
-    if (K <= 20) return launch_traj_inst<M, 20, 1>(ctx, pv, pk, cfg, tab, st);
-    if (K <= 24) return launch_traj_inst<M, 24, 1>(ctx, pv, pk, cfg, tab, st);
-    if (K <= 28) return launch_traj_inst<M, 28, 1>(ctx, pv, pk, cfg, tab, st);
-    if (K <= 32) return launch_traj_inst<M, 32, 1>(ctx, pv, pk, cfg, tab, st);
-    if (K <= 64) return launch_traj_inst<M, 0, 2>(ctx, pv, pk, cfg, tab, st);
-    return launch_traj_inst<M, 0, 4>(ctx, pv, pk, cfg, tab, st);
+    if (K <= 4) return launch_traj_inst<M, 4, 1>(ctx, pv, pk, cfg, cc, tab, st);
+    if (K <= 8) return launch_traj_inst<M, 8, 1>(ctx, pv, pk, cfg, cc, tab, st);
+    if (K <= 12) return launch_traj_inst<M, 12, 1>(ctx, pv, pk, cfg, cc, tab, st);
+    if (K <= 16) return launch_traj_inst<M, 16, 1>(ctx, pv, pk, cfg, cc, tab, st);
+    if (K <= 20) return launch_traj_inst<M, 20, 1>(ctx, pv, pk, cfg, cc, tab, st);
+    if (K <= 24) return launch_traj_inst<M, 24, 1>(ctx, pv, pk, cfg, cc, tab, st);
+    if (K <= 28) return launch_traj_inst<M, 28, 1>(ctx, pv, pk, cfg, cc, tab, st);
+    if (K <= 32) return launch_traj_inst<M, 32, 1>(ctx, pv, pk, cfg, cc, tab, st);
+    if (K <= 64) return launch_traj_inst<M, 0, 2>(ctx, pv, pk, cfg, cc, tab, st);
+    return launch_traj_inst<M, 0, 4>(ctx, pv, pk, cfg, cc, tab, st);
 }
 
-int launch_traj(gcdyn_ctx* ctx, int M, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, double* tab,
-                cudaStream_t st) {
+int launch_traj(gcdyn_ctx* ctx, int M, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, const ChebCfg& cc,
+                double* tab, cudaStream_t st) {
     switch (M) {
-        case 8: return launch_traj_m<8>(ctx, pv, pk, cfg, tab, st);
-        case 12: return launch_traj_m<12>(ctx, pv, pk, cfg, tab, st);
-        case 16: return launch_traj_m<16>(ctx, pv, pk, cfg, tab, st);
-        case 20: return launch_traj_m<20>(ctx, pv, pk, cfg, tab, st);
-        case 24: return launch_traj_m<24>(ctx, pv, pk, cfg, tab, st);
+        case 8: return launch_traj_m<8>(ctx, pv, pk, cfg, cc, tab, st);
+        case 12: return launch_traj_m<12>(ctx, pv, pk, cfg, cc, tab, st);
+        case 16: return launch_traj_m<16>(ctx, pv, pk, cfg, cc, tab, st);
+        case 20: return launch_traj_m<20>(ctx, pv, pk, cfg, cc, tab, st);
+        case 24: return launch_traj_m<24>(ctx, pv, pk, cfg, cc, tab, st);
     }
     return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
 }
@@ -351,31 +359,8 @@ int cheb_degree(double T, double rate_max, int K, int Dcap, int S_cap, int smem_
     int D = 128;
     for (int d : ladder) if ((double)d >= want) { D = d; break; }
     D = std::min(D, Dcap);
-    while (D > 16 && (2 * (size_t)D + (3 * (size_t)D + 4) * K + 2 * (size_t)S_cap + 8) * 8 + 1024 > (size_t)smem_optin) D -= 8;
+    while (D > 16 && traj_smem_bytes(K, D, S_cap) + 1024 > (size_t)smem_optin) D -= 16;
     return D & ~1;
-}
-
-template <int M>
-int launch_cheb_m(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const MomentView& mv, const ChebCfg& cc,
-                  const double* tab, double* A, int* need_sweep, int* d_common, int P, cudaStream_t st) {
-    const size_t smem = (2 * (size_t)cc.D + (3 * (size_t)cc.D + 4) * mv.K + 2 * (size_t)cc.S_cap + 8) * 8;
-    if (smem > 48 * 1024)
-        CU_TRY(ctx, cudaFuncSetAttribute(cheb_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cheb_kernel<M><<<P, 512, smem, st>>>(pv, pk, mv, cc, tab, A, need_sweep, d_common);
-    CU_TRY(ctx, cudaGetLastError());
-    return GCDYN_OK;
-}
-
-int launch_cheb(gcdyn_ctx* ctx, int M, const ParamsView& pv, const PsetPack& pk, const MomentView& mv, const ChebCfg& cc,
-                const double* tab, double* A, int* need_sweep, int* d_common, int P, cudaStream_t st) {
-    switch (M) {
-        case 8: return launch_cheb_m<8>(ctx, pv, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
-        case 12: return launch_cheb_m<12>(ctx, pv, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
-        case 16: return launch_cheb_m<16>(ctx, pv, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
-        case 20: return launch_cheb_m<20>(ctx, pv, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
-        case 24: return launch_cheb_m<24>(ctx, pv, pk, mv, cc, tab, A, need_sweep, d_common, P, st);
-    }
-    return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
 }
 
 // Build (once per forest and present_time) the per-tree Chebyshev moments and count columns.
@@ -440,31 +425,40 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         cfg.tab_stride = cfg.grid_doubles + (long long)cfg.S_cap * K * L;
         const size_t tab_bytes = (size_t)P * (size_t)cfg.tab_stride * 8;
         CU_TRY(ctx, ctx->table.ensure(tab_bytes));
-        rc = launch_traj(ctx, M, pv, pk, cfg, ctx->table.as<double>(), st);
-        if (rc) return rc;
-        ++launches;
-        if (prof) cudaEventRecord(ctx->ev[2], st);
-        // ---- per-tree sums: Chebyshev-moment GEMM (DMMA), with the item sweep as exact fallback
+        // ---- per-tree sums: Chebyshev-moment GEMM (DMMA), with the item sweep as exact fallback.  The Chebyshev
+        //      stage (node values, DCT, coefficient row, fallback flag) runs as the tail of traj_kernel.
         const bool use_gemm = !(flags & GCDYN_FLAG_SWEEP_ONLY) && Tn > 0 &&
                               (P >= 8 || (f->mom.Mt && f->mom_T == T));
         const int* only_flagged = nullptr;
+        ChebCfg cc{};
+        int* need_sweep = nullptr;
+        int* d_common = nullptr;
         if (use_gemm) {
             rc = ensure_moments(ctx, f, T, st, &launches);
             if (rc) return rc;
-            const MomentView& mv = f->mom;
-            CU_TRY(ctx, ctx->gemm_a.ensure((size_t)P * (size_t)mv.Jst * 8));
+            CU_TRY(ctx, ctx->gemm_a.ensure((size_t)P * (size_t)f->mom.Jst * 8));
             CU_TRY(ctx, ctx->flags.ensure((size_t)(P + 1) * 4));
-            int* need_sweep = ctx->flags.as<int>();
-            int* d_common = need_sweep + P;
+            need_sweep = ctx->flags.as<int>();
+            d_common = need_sweep + P;
             CU_TRY(ctx, cudaMemsetAsync(d_common, 0, 4, st));
-            ChebCfg cc{};
             cc.T = T;
             cc.tol = 1e-11;
             cc.tab_stride = cfg.tab_stride;
             cc.S_cap = cfg.S_cap;
             cc.grid_doubles = cfg.grid_doubles;
-            cc.D = cheb_degree(T, rate_max, K, mv.Dcap, cfg.S_cap, ctx->smem_optin);
+            cc.D = cheb_degree(T, rate_max, K, f->mom.Dcap, cfg.S_cap, ctx->smem_optin);
             cc.compact_tc = pv.gamma_stride == 0 ? 1 : 0;
+            cc.mv = f->mom;
+            cc.A = ctx->gemm_a.as<double>();
+            cc.need_sweep = need_sweep;
+            cc.d_common = d_common;
+        }
+        rc = launch_traj(ctx, M, pv, pk, cfg, cc, ctx->table.as<double>(), st);
+        if (rc) return rc;
+        ++launches;
+        if (prof) { cudaEventRecord(ctx->ev[2], st); cudaEventRecord(ctx->ev[3], st); }
+        if (use_gemm) {
+            const MomentView& mv = f->mom;
             const double* tree_const = nullptr;
             if (cc.compact_tc) {
                 // shared Γ: Σ count·log Γ_xy is the same for every pset — one constant per tree, recomputed only
@@ -482,11 +476,6 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
                 }
                 tree_const = f->d_tree_const;
             }
-            rc = launch_cheb(ctx, M, pv, pk, mv, cc, ctx->table.as<double>(), ctx->gemm_a.as<double>(), need_sweep,
-                             d_common, P, st);
-            if (rc) return rc;
-            ++launches;
-            if (prof) cudaEventRecord(ctx->ev[3], st);
             dim3 grid((unsigned)((Tn + GT_TILE - 1) / GT_TILE), (unsigned)((P + GT_TILE - 1) / GT_TILE));
             if (!ctx->gemm_attr_set) {
                 CU_TRY(ctx, cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
@@ -498,10 +487,8 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             ++launches;
             only_flagged = need_sweep;
             ctx->last_cheb_D = cc.D;
-
         } else {
             ctx->last_cheb_D = 0;
-            if (prof) cudaEventRecord(ctx->ev[3], st);
         }
         if (prof) cudaEventRecord(ctx->ev[4], st);
         const int S_stage = S_fixed > 0 ? S_fixed : std::min(cfg.S_cap, expected_steps(T, rate_max, M));

@@ -71,6 +71,8 @@ struct ForestView {
     const int32_t* n_surv;       // [T]
 };
 
+constexpr int TRAJ_THREADS = 128;   // warp 0 integrates; all four warps run the Chebyshev stage
+
 struct TrajCfg {
     double T;                    // present_time
     double tol;                  // accepted error indicator
@@ -159,8 +161,217 @@ __global__ void stadler_cond_kernel(ParamsView pv, PsetPack pk, double present_t
     }
 }
 
+struct MomentView {
+    int K;
+    int C1;                // 2K + 4: start of the Chebyshev block
+    int Dcap;              // moments exist for d = 0..Dcap
+    long long Jtc;         // start of the K² type-change block
+    long long Jst;         // row stride of Mt and A (doubles), multiple of 4
+    const double* Mt;      // [T][Jst]
+    const double* colsum;  // [Jst] forest-level column sums (only count columns are consulted)
+};
+
+struct ChebCfg {
+    double T;
+    double tol;            // accepted Chebyshev tail (absolute, on F)
+    int D;                 // interpolation degree (≤ Dcap), even
+    int compact_tc;        // 1: Γ shared — log δ column + per-tree constant; 0: K² type-change columns
+    int S_cap, grid_doubles;   // layout of a pset's table block: [τ_s | 1/h_s | pad][rows]
+    long long tab_stride;
+    MomentView mv;
+    double* A;             // [P][Jst] coefficient rows of the GEMM
+    int* need_sweep;       // [P] fallback flags
+    int* d_common;         // [1] max effective degree over the psets the GEMM takes
+};
+
+// Cell containing τ on a pset's (non-uniform) grid: largest s < S with grid[s] ≤ τ.
+__device__ __forceinline__ int find_cell(const double* __restrict__ grid, int S, double tau) {
+    int lo = 0, hi = S - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (grid[mid] <= tau) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// F_x(τ) from a table row of L = M+2 coefficients: even/odd split halves the dependent FMA chain.
+template <int M, bool SMEM>
+__device__ __forceinline__ double eval_row(const double* __restrict__ row, double th) {
+    constexpr int L = M + 2;
+    double co[L];
+#pragma unroll
+    for (int n = 0; n < L; n += 2) {
+        double2 v;
+        if constexpr (SMEM) v = *reinterpret_cast<const double2*>(row + n);
+        else v = __ldg(reinterpret_cast<const double2*>(row + n));
+        co[n] = v.x;
+        co[n + 1] = v.y;
+    }
+    const double t2 = th * th;
+    double ev = co[L - 2], od = co[L - 1];
+#pragma unroll
+    for (int n = L - 4; n >= 0; n -= 2) {
+        ev = fma(ev, t2, co[n]);
+        od = fma(od, t2, co[n + 1]);
+    }
+    return fma(od, th, ev);
+}
+
 // ------------------------------------------------------------------------------------------------
-// traj_kernel: one warp per pset; lane l owns types l, l+32, … (KPL per lane).
+// cheb_stage: the Chebyshev stage of one pset, executed by the whole CTA of traj_kernel once warp 0 has
+// integrated the trajectory (psets that finish early do this while others still integrate).  Values of F_x
+// at the D+1 Chebyshev–Gauss–Lobatto nodes from the pset's Taylor table, DCT-I → a[d][x]; effective degree;
+// count-column coefficients; fallback flag.  `sm` = this stage's shared-memory scratch.
+// ------------------------------------------------------------------------------------------------
+template <int M>
+__device__ __forceinline__ void cheb_stage(const ParamsView& pv, const PsetPack& pk, const ChebCfg& cfg, int p,
+                                           const double* __restrict__ tab, double* __restrict__ sm) {
+    const MomentView& mv = cfg.mv;
+    double* __restrict__ A = cfg.A;
+    int* __restrict__ need_sweep = cfg.need_sweep;
+    int* __restrict__ d_common = cfg.d_common;
+    constexpr int L = M + 2;
+    const int K = mv.K, C1 = mv.C1, D = cfg.D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    double* costab = sm;                   // [2D]  cos(π m / D)
+    double* V = costab + 2 * D;            // [(D+1)*K] node values
+    double* Acoef = V + (size_t)(D + 1) * K;   // [(D+1)*K] coefficients
+    __shared__ int s_deff, s_flag;
+    const int S = pk.S[p];
+    const int pst = pk.pstatus[p];
+    if (threadIdx.x == 0) { s_deff = 8; s_flag = (pst & ST_SOLVER) ? 1 : 0; }
+    for (int m = threadIdx.x; m < 2 * D; m += blockDim.x) costab[m] = cospi((double)m / (double)D);
+    __syncthreads();
+    const double* tp = tab + (size_t)p * cfg.tab_stride;
+    const double* rows = tp + cfg.grid_doubles;
+    // the pset's grid [τ_s | 1/h_s] goes to shared memory first: the cell search is then a few LDS, not L2 round trips
+    double* sgrid = Acoef + (size_t)(D + 1) * K + 2 * (size_t)(D / 2 + 1) * K;   // [S+1], then [S]
+    double* sinvh = sgrid + (S + 1);
+    for (int i = threadIdx.x; i <= S; i += blockDim.x) sgrid[i] = tp[i];
+    for (int i = threadIdx.x; i < S; i += blockDim.x) sinvh[i] = tp[cfg.S_cap + 1 + i];
+    __syncthreads();
+    if (!(pst & ST_SOLVER)) {
+        for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
+            const int k = idx / K, x = idx - k * K;
+            const double tau = cfg.T * (1.0 + costab[k]) * 0.5;
+            const int s = find_cell(sgrid, S, tau);
+            V[idx] = eval_row<M, false>(rows + ((size_t)s * K + x) * L, (tau - sgrid[s]) * sinvh[s]);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) V[idx] = 0.0;
+    }
+    __syncthreads();
+    // DCT-I with the symmetry cos(π(D−k)d/D) = (−1)^d cos(πkd/D): fold the node values into an even and an
+    // odd half, E_k = w_k (V_k + V_{D−k}), O_k = w_k (V_k − V_{D−k}), k = 0..D/2, w_0 = w_{D/2} = 1/2.
+    const int H = D / 2;
+    double* EO = Acoef + (size_t)(D + 1) * K;        // [2][(H+1)*K]
+    for (int idx = threadIdx.x; idx < (H + 1) * K; idx += blockDim.x) {
+        const int k = idx / K, x = idx - k * K;
+        const double w = (k == 0 || k == H) ? 0.5 : 1.0;
+        const double a = V[k * K + x], b = V[(D - k) * K + x];
+        EO[idx] = w * (a + b);
+        EO[(H + 1) * K + idx] = w * (a - b);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
+        const int d = idx / K, x = idx - d * K;
+        const double* src = EO + (size_t)(d & 1) * (H + 1) * K + x;
+        double s0 = 0.0, s1 = 0.0;
+        int m = 0;                                   // (k*d) mod 2D, advanced incrementally
+        int k = 0;
+        for (; k + 1 <= H; k += 2) {
+            s0 = fma(src[k * K], costab[m], s0);
+            m += d; m -= (m >= 2 * D) ? 2 * D : 0;
+            s1 = fma(src[(k + 1) * K], costab[m], s1);
+            m += d; m -= (m >= 2 * D) ? 2 * D : 0;
+        }
+        if (k <= H) s0 = fma(src[k * K], costab[m], s0);
+        double a = (2.0 / (double)D) * (s0 + s1);
+        if (d == 0 || d == D) a *= 0.5;
+        Acoef[idx] = a;
+    }
+    __syncthreads();
+    // effective degree per type (a warp per type, lanes over degrees): the smallest d with Σ_{k>d}|a_k| ≤ tol;
+    // the series counts as unresolved if its last three terms are not small
+    for (int x = warp; x < K; x += nwarps) {
+        // lane owns the contiguous degrees [lo, hi); suffix sums of |a| are combined across lanes
+        const int per = (D + 1 + 31) / 32;
+        const int lo = lane * per, hi = min(D + 1, lo + per);
+        double mine = 0.0;
+        for (int d = lo; d < hi; ++d) mine += fabs(Acoef[d * K + x]);
+        double above = 0.0;                        // Σ over lanes > lane
+        {
+            double run = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_down_sync(FULL, run, o);
+                if (lane + o < 32) run += v;
+            }
+            above = run - mine;
+        }
+        int found = 8;
+        double tail = above;
+        for (int d = hi - 1; d >= lo && d > 8; --d) {
+            tail += fabs(Acoef[d * K + x]);
+            if (!(tail <= cfg.tol)) { found = d; break; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) found = max(found, __shfl_xor_sync(FULL, found, o));
+        if (lane == 0) {
+            const double last3 = fabs(Acoef[D * K + x]) + fabs(Acoef[(D - 1) * K + x]) + fabs(Acoef[(D - 2) * K + x]);
+            if (!(last3 <= cfg.tol)) atomicExch(&s_flag, 1);
+            atomicMax(&s_deff, found);
+        }
+    }
+    __syncthreads();
+    const int deff = s_deff;
+    double* Arow = A + (size_t)p * mv.Jst;
+    for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
+        Arow[C1 + idx] = Acoef[idx];          // all interpolation coefficients are valid; the GEMM stops at d_common
+    }
+    // the GEMM rounds its column ranges up to multiples of 4: keep the padding finite
+    if (threadIdx.x < 4) {
+        const long long j = C1 + (long long)(D + 1) * K + threadIdx.x;
+        if (j < mv.Jtc) Arow[j] = 0.0;
+        const long long j2 = mv.Jtc + (long long)K * K + threadIdx.x;
+        if (j2 < mv.Jst) Arow[j2] = 0.0;
+    }
+    // count columns
+    const double* nt = pk.nt + (size_t)p * pk.ntw;
+    for (int c = threadIdx.x; c < C1; c += blockDim.x) {
+        double v = 0.0;
+        if (c < K) v = nt[c];                                         // log λ_x
+        else if (c == K) v = nt[K + K * K];                           // log μ + log σ
+        else if (c == K + 1) v = nt[K + K * K + 1];                   // log ρ
+        else if (c < 2 * K + 2) v = -pk.logcond[(size_t)p * K + (c - K - 2)];
+        else if (c == 2 * K + 2) v = cfg.compact_tc ? log(pv.delta[p]) : 0.0;
+        if (!isfinite(v)) {
+            if (mv.colsum[c] != 0.0) atomicExch(&s_flag, 1);
+            v = 0.0;
+        }
+        Arow[c] = v;
+    }
+    if (!cfg.compact_tc) {
+        for (int e = threadIdx.x; e < K * K; e += blockDim.x) {
+            double v = nt[K + e];
+            const bool diag = (e / K) == (e % K);          // self-loop column: trees using it are −Inf anyway
+            if (!isfinite(v)) {
+                if (!diag && mv.colsum[mv.Jtc + e] != 0.0) atomicExch(&s_flag, 1);
+                v = 0.0;
+            }
+            Arow[mv.Jtc + e] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        need_sweep[p] = s_flag;
+        if (!s_flag) atomicMax(d_common, deff);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// traj_kernel: one CTA of 4 warps per pset; warp 0 integrates (the others wait at the barrier), then the whole
+// CTA runs the Chebyshev stage.  Within warp 0; lane l owns types l, l+32, … (KPL per lane).
 //
 // Taylor recurrence for the h-scaled coefficients ĉ_n of p(τ_s + θh) = Σ ĉ_n θ^n:
 //   ĉ_{n+1} = h/(n+1) · [ −(λ+μ) ĉ_n + [n=0] μ(1−σ) + λ Σ_{m≤n} ĉ_m ĉ_{n−m} + δ Γ ĉ_n ]
@@ -172,17 +383,18 @@ __global__ void stadler_cond_kernel(ParamsView pv, PsetPack pk, double present_t
 // KPL  > 1: δΓ is staged transposed in shared memory (lane-contiguous rows).
 // ------------------------------------------------------------------------------------------------
 template <int M, int KP, int KPL>
-__global__ void __launch_bounds__(32) traj_kernel(ParamsView pv, PsetPack pk, TrajCfg cfg, double* __restrict__ tab) {
+__global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetPack pk, TrajCfg cfg, ChebCfg cc,
+                                                            double* __restrict__ tab) {
     extern __shared__ __align__(16) double smem[];
     constexpr int L = M + 2;
     const int p = blockIdx.x;
     const int K = pv.K;
+    prep_pset(pv, pk, p, 0, threadIdx.x, TRAJ_THREADS);
+    if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     const int KS = KPL == 1 ? KP : ((K + 3) & ~3);     // broadcast buffer length (multiple of 4)
     double* cb = smem;                                  // 2 × KS
     double* GT = smem + 2 * KS;                         // KPL > 1 only: GT[j*K + i] = δ Γ[i,j]
-
-    prep_pset(pv, pk, p, 0, lane, 32);
 
     const double mu = pv.mu[p], delta = pv.delta[p], rho = pv.rho[p], sigma = pv.sigma[p];
     const double* G = pv.Gamma + (size_t)p * pv.gamma_stride;
@@ -379,16 +591,11 @@ __global__ void __launch_bounds__(32) traj_kernel(ParamsView pv, PsetPack pk, Tr
         pk.S[p] = s > 0 ? s : 1;
         if (anybad) pk.pstatus[p] |= ST_SOLVER;
     }
-}
-
-// Cell containing τ on a pset's (non-uniform) grid: largest s < S with grid[s] ≤ τ.
-__device__ __forceinline__ int find_cell(const double* __restrict__ grid, int S, double tau) {
-    int lo = 0, hi = S - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (grid[mid] <= tau) lo = mid; else hi = mid - 1;
-    }
-    return lo;
+    }   // warp 0
+    if (cc.D <= 0) return;                              // CTA-uniform
+    __syncthreads();                                    // table, grid, status of this pset are complete and visible
+    const size_t traj_doubles = 2 * (size_t)(KPL == 1 ? KP : ((K + 3) & ~3)) + (KPL == 1 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
+    cheb_stage<M>(pv, pk, cc, p, tab, smem + traj_doubles);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -417,29 +624,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
-}
-
-// F_x(τ) from a table row of L = M+2 coefficients: even/odd split halves the dependent FMA chain.
-template <int M, bool SMEM>
-__device__ __forceinline__ double eval_row(const double* __restrict__ row, double th) {
-    constexpr int L = M + 2;
-    double co[L];
-#pragma unroll
-    for (int n = 0; n < L; n += 2) {
-        double2 v;
-        if constexpr (SMEM) v = *reinterpret_cast<const double2*>(row + n);
-        else v = __ldg(reinterpret_cast<const double2*>(row + n));
-        co[n] = v.x;
-        co[n + 1] = v.y;
-    }
-    const double t2 = th * th;
-    double ev = co[L - 2], od = co[L - 1];
-#pragma unroll
-    for (int n = L - 4; n >= 0; n -= 2) {
-        ev = fma(ev, t2, co[n]);
-        od = fma(od, t2, co[n + 1]);
-    }
-    return fma(od, th, ev);
 }
 
 template <int M, bool SMEM>
