@@ -253,18 +253,21 @@ def run_gpu(args):
         ends[i].record(stream)
     barrier()
     total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    # keep the GPU busy a little longer so the clock sampler sees load even for very short runs
+    result = out.cpu().numpy().copy()           # all-reduced [P] sums of the last timed step
+    # keep the GPU busy a little longer so the clock sampler sees load even for very short runs; local work
+    # only — a time-bounded loop must not contain collectives (ranks would issue different counts)
     t_end = time.perf_counter() + 1.0
     while time.perf_counter() < t_end:
-        step_resident()
-    torch.cuda.synchronize()
+        for _ in range(20):
+            evaluate_resident(forest, dpar, T, out.data_ptr(), out_tree.data_ptr(), 0, stream.cuda_stream,
+                              steps=args.taylor_steps, order=args.order)
+        torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     tm = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms_per_step = float(tm.item()) / args.steps
     value = world * Tn * P / (ms_per_step * 1e-3)
-    result = out.cpu().numpy().copy()
 
     # ---- e2e: the host-buffer C-ABI call (parameters H2D, results D2H inside the timed region)
     for _ in range(3):

@@ -23,21 +23,18 @@
 namespace gcdyn {
 
 // ------------------------------------------------------------------------------------------------
-// moments_kernel: one CTA per tree (run once per forest and present_time).
+// counts_kernel: one CTA per tree (run once per forest and present_time) — the count columns, the K² type-change
+// block and zero padding of the tree's row of Mt.  Integer atomics in shared memory: exact, order-independent.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) moments_kernel(ForestView fv, double T, int Dcap, long long Jtc, long long Jst,
-                                                      double* __restrict__ Mt) {
-    extern __shared__ __align__(16) double sm[];
+__global__ void __launch_bounds__(128) counts_kernel(ForestView fv, int Dcap, long long Jtc, long long Jst,
+                                                     double* __restrict__ Mt) {
+    extern __shared__ __align__(16) int cnt[];
     const int K = fv.K;
     const int C1 = 2 * K + 4;
-    const int NC = C1 + K * K;                              // integer counters: count columns + type-change block
+    const int NC = C1 + K * K;
     const int64_t t = blockIdx.x;
-    int* cnt = reinterpret_cast<int*>(sm);
-    double* acc = sm + ((NC + 1) / 2);                      // [(Dcap+1)*K]
     for (int i = threadIdx.x; i < NC; i += blockDim.x) cnt[i] = 0;
-    for (int i = threadIdx.x; i < (Dcap + 1) * K; i += blockDim.x) acc[i] = 0.0;
     __syncthreads();
-    // node-term counts over live nodes (integer atomics: exact, order-independent)
     for (int64_t i = fv.tree_off[t] + threadIdx.x; i < fv.tree_off[t + 1]; i += blockDim.x) {
         if (!fv.live[i]) continue;
         const int ev = fv.event[i], x = fv.btype_idx[i], y = fv.type_idx[i];
@@ -50,32 +47,93 @@ __global__ void __launch_bounds__(128) moments_kernel(ForestView fv, double T, i
         const int rt = fv.root_type[t];
         if (rt >= 0) cnt[K + 2 + rt] = 1;
     }
-    // Chebyshev moments: thread x owns column x and walks the tree's items in order (deterministic)
-    const int64_t i0 = fv.item_off[t], i1 = fv.item_off[t + 1];
-    for (int x = threadIdx.x; x < K; x += blockDim.x) {
-        for (int64_t i = i0; i < i1; ++i) {
-            const int2 me = fv.it_meta[i];
-            if ((me.x & 0xffffff) != x) continue;
-            const double w = (double)(me.x >> 24);
-            const double u = 2.0 * (T - fv.it_time[i]) / T - 1.0;
-            double tm = 1.0, tc = u;
-            acc[x] += w;
-            for (int d = 1; d <= Dcap; ++d) {
-                acc[d * K + x] = fma(w, tc, acc[d * K + x]);
-                const double tn = fma(2.0 * u, tc, -tm);
-                tm = tc;
-                tc = tn;
-            }
-        }
-    }
     __syncthreads();
     double* row = Mt + (size_t)t * Jst;
+    const long long cheb_end = C1 + (long long)(Dcap + 1) * K;
     for (long long i = threadIdx.x; i < Jst; i += blockDim.x) {
-        double v = 0.0;
-        if (i < C1) v = (double)cnt[i];
-        else if (i < C1 + (long long)(Dcap + 1) * K) v = acc[i - C1];
-        else if (i >= Jtc && i < Jtc + (long long)K * K) v = (double)cnt[C1 + (i - Jtc)];
-        row[i] = v;
+        if (i < C1) row[i] = (double)cnt[i];
+        else if (i < cheb_end) continue;                                   // written by moments_kernel
+        else if (i >= Jtc && i < Jtc + (long long)K * K) row[i] = (double)cnt[C1 + (i - Jtc)];
+        else row[i] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// moments_kernel: one WARP per (tree, type): Mt[t][C1 + d*K + x] = Σ_{items of t with type x} w·T_d(u), d ≤ Dcap.
+// The warp gathers the tree's items of its type 32 at a time (ballot compaction keeps tree order), every lane
+// runs the three-term recurrence for its item, and each degree is summed with a fixed-order shuffle tree —
+// deterministic, and parallel over trees × types × items.  Lane d%32 keeps the accumulator of degree d.
+// ------------------------------------------------------------------------------------------------
+constexpr int MOM_DBLK = 5;   // ceil((Dcap+1)/32) for Dcap = 128 … 159
+
+__global__ void __launch_bounds__(256) moments_kernel(ForestView fv, double T, int Dcap, long long Jst, int C1,
+                                                      double* __restrict__ Mt) {
+    const int K = fv.K;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wid >= fv.n_trees * K) return;
+    const int64_t t = wid / K;
+    const int x = (int)(wid - t * K);
+    double acc[MOM_DBLK];
+#pragma unroll
+    for (int b = 0; b < MOM_DBLK; ++b) acc[b] = 0.0;
+    const int64_t i0 = fv.item_off[t], i1 = fv.item_off[t + 1];
+    double u_mine = 0.0, w_mine = 0.0;    // the item this lane holds in the current batch (w = 0: empty slot)
+    int filled = 0;
+    auto flush = [&]() {
+        double tm = 1.0, tc = u_mine;
+#pragma unroll
+        for (int b = 0; b < MOM_DBLK; ++b) {
+            for (int dd = 0; dd < 32; ++dd) {
+                const int d = b * 32 + dd;
+                if (d > Dcap) break;
+                const double td = d == 0 ? 1.0 : tc;
+                const double ssum = warp_sum(w_mine * td);
+                if (lane == dd) acc[b] += ssum;
+                if (d >= 1) { const double tn = fma(2.0 * u_mine, tc, -tm); tm = tc; tc = tn; }
+            }
+        }
+        w_mine = 0.0; u_mine = 0.0; filled = 0;
+    };
+    for (int64_t base = i0; base < i1; base += 32) {
+        const int64_t i = base + lane;
+        int2 me = make_int2(0, 0);
+        double tm_i = 0.0;
+        bool match = false;
+        if (i < i1) { me = fv.it_meta[i]; tm_i = fv.it_time[i]; match = (me.x & 0xffffff) == x; }
+        unsigned mask = __ballot_sync(FULL, match);
+        while (mask) {
+            // move as many matches as fit into the free slots [filled, 32), in tree order
+            const int room = 32 - filled;
+            const int rank = __popc(mask & ((1u << lane) - 1u));          // my position among the remaining matches
+            const bool take = match && ((mask >> lane) & 1u) && rank < room;
+            const int n_take = min(__popc(mask), room);
+            // destination slot for taker `rank` is filled + rank; gather with shuffles: slot s reads the lane whose rank == s − filled
+            const unsigned takers = __ballot_sync(FULL, take);
+            const int want = lane - filled;                                 // which taker this slot receives
+            int src = -1;
+            if (want >= 0 && want < n_take) {
+                // lane index of the (want)-th set bit of `takers`
+                unsigned m = takers;
+                for (int r = 0; r < want; ++r) m &= m - 1;
+                src = __ffs(m) - 1;
+            }
+            const double u_src = 2.0 * (T - tm_i) / T - 1.0;
+            const double w_src = (double)(me.x >> 24);
+            const double u_got = __shfl_sync(FULL, u_src, src < 0 ? 0 : src);
+            const double w_got = __shfl_sync(FULL, w_src, src < 0 ? 0 : src);
+            if (src >= 0) { u_mine = u_got; w_mine = w_got; }
+            filled += n_take;
+            mask &= ~takers;
+            if (filled == 32) flush();
+        }
+    }
+    if (filled > 0) flush();
+    double* row = Mt + (size_t)t * Jst + C1;
+#pragma unroll
+    for (int b = 0; b < MOM_DBLK; ++b) {
+        const int d = b * 32 + lane;
+        if (d <= Dcap) row[(size_t)d * K + x] = acc[b];
     }
 }
 

@@ -378,15 +378,19 @@ int ensure_moments(gcdyn_ctx* ctx, const gcdyn_forest* f, double T, cudaStream_t
         CU_TRY(ctx, cudaMalloc(&f->d_Mt, std::max<size_t>((size_t)Tn * (size_t)Jst * 8, 8)));
         CU_TRY(ctx, cudaMalloc(&f->d_colsum, (size_t)Jst * 8));
     }
-    const size_t smem = ((size_t)(C1 + K * K + 1) / 2 + (size_t)(Dcap + 1) * K) * 8;
-    if (smem > (size_t)ctx->smem_optin) return fail(ctx, GCDYN_EUNSUPPORTED, "n_types too large for the moment kernel");
+    const size_t smem = ((size_t)C1 + (size_t)K * K) * 4;
     if (smem > 48 * 1024)
-        CU_TRY(ctx, cudaFuncSetAttribute(moments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    moments_kernel<<<(unsigned)Tn, 128, smem, st>>>(f->v, T, Dcap, Jtc, Jst, f->d_Mt);
-    CU_TRY(ctx, cudaGetLastError());
+        CU_TRY(ctx, cudaFuncSetAttribute(counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (Tn > 0) {
+        counts_kernel<<<(unsigned)Tn, 128, smem, st>>>(f->v, Dcap, Jtc, Jst, f->d_Mt);
+        CU_TRY(ctx, cudaGetLastError());
+        const long long warps = (long long)Tn * K;
+        moments_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(f->v, T, Dcap, Jst, C1, f->d_Mt);
+        CU_TRY(ctx, cudaGetLastError());
+    }
     colsum_kernel<<<(unsigned)((Jst + 127) / 128), 128, 0, st>>>(f->d_Mt, Tn, Jst, f->d_colsum);
     CU_TRY(ctx, cudaGetLastError());
-    *launches += 2;
+    *launches += 3;
     f->mom.K = K; f->mom.C1 = C1; f->mom.Dcap = Dcap; f->mom.Jtc = Jtc; f->mom.Jst = Jst;
     f->mom.Mt = f->d_Mt; f->mom.colsum = f->d_colsum;
     f->mom_T = T;
