@@ -4,6 +4,7 @@
 #include "../../include/gcdyn_b200.h"
 #include "kernels.cuh"
 #include "cheb_gemm.cuh"
+#include "simulator.h"
 
 #include <algorithm>
 #include <cmath>
@@ -87,6 +88,10 @@ struct gcdyn_forest {
     // shared-Γ constant Σ count·log Γ_xy per tree, cached for the last Γ seen
     mutable double* d_tree_const = nullptr;
     mutable std::vector<double> tc_gamma;
+};
+
+struct gcdyn_sim {
+    gcdyn_simu::FlatOut out;
 };
 
 struct gcdyn_dparams {
@@ -944,6 +949,101 @@ int gcdyn_last_cheb_degree(gcdyn_ctx* ctx, int32_t* interp_degree, int32_t* effe
     return GCDYN_OK;
     GUARD_END(ctx)
 }
+
+// ---- native simulator (host code; no device needed) ------------------------------------------------------
+int gcdyn_sim_forest(const gcdyn_params* model, double present_time, int32_t init_type_idx, int64_t n_trees,
+                     uint64_t seed, int64_t first_tree_index, int32_t reject_stubs, int32_t min_leaves,
+                     int32_t max_rejections, gcdyn_sim** out) {
+    gcdyn_ctx* none = nullptr;
+    GUARD_BEGIN
+    if (!out) return fail(none, GCDYN_EINVAL, "out is NULL");
+    *out = nullptr;
+    int rc = check_params(none, model);
+    if (rc) return rc;
+    if (model->n_psets != 1) return fail(none, GCDYN_EINVAL, "the simulator takes exactly one parameter set");
+    const int K = model->n_types;
+    if (init_type_idx < 0 || init_type_idx >= K) return fail(none, GCDYN_EINVAL, "init_type_idx out of range");
+    if (n_trees < 0 || !(present_time > 0.0)) return fail(none, GCDYN_EINVAL, "n_trees must be >= 0 and present_time > 0");
+    std::vector<double> lam(K), G((size_t)K * K);
+    for (int i = 0; i < K; ++i) {
+        if (model->response == 0) lam[i] = model->lambda[i];
+        else if (model->response == 1) lam[i] = model->lambda[0];
+        else lam[i] = model->yscale[0] * (1.0 / (1.0 + std::exp(-(model->xscale[0] * (model->type_space[i] - model->xshift[0]))))) + model->yshift[0];
+        for (int j = 0; j < K; ++j) G[(size_t)i * K + j] = model->Gamma[i + (size_t)j * K];   // column-major in, row-major here
+    }
+    for (int i = 0; i < K; ++i) {
+        const double tot = lam[i] + model->mu[0] + model->delta[0] * -G[(size_t)i * K + i];
+        if (!(tot > 0.0) || !(lam[i] >= 0.0) || !(model->mu[0] >= 0.0)) return fail(none, GCDYN_EINVAL, "rates must be non-negative with a positive total");
+    }
+    const gcdyn_simu::Model m{K, lam.data(), model->mu[0], model->delta[0], model->rho[0], model->sigma[0], G.data()};
+    // blocks of trees are simulated in parallel; each tree has its own RNG stream, so the result is independent of threading
+    const int64_t block = 64;
+    const int64_t n_blocks = (n_trees + block - 1) / block;
+    std::vector<gcdyn_simu::FlatOut> parts((size_t)n_blocks);
+    int failed = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        std::vector<gcdyn_simu::Node> nodes;
+        std::vector<double> wbuf((size_t)K);
+        const int64_t lo = b * block, hi = std::min(n_trees, lo + block);
+        for (int64_t t = lo; t < hi; ++t) {
+            if (!gcdyn_simu::simulate_tree(m, present_time, init_type_idx, seed, (uint64_t)(first_tree_index + t), reject_stubs != 0,
+                                          min_leaves, max_rejections, parts[(size_t)b], nodes, wbuf)) {
+#pragma omp atomic write
+                failed = 1;
+                break;
+            }
+        }
+    }
+    if (failed) return fail(none, GCDYN_EINVAL, "max_rejections trees rejected");
+    gcdyn_sim* sim = new gcdyn_sim();
+    gcdyn_simu::FlatOut& o = sim->out;
+    for (auto& part : parts) {
+        const int64_t nb = (int64_t)o.event.size(), cb = (int64_t)o.child_idx.size();
+        for (size_t k = 1; k < part.tree_off.size(); ++k) o.tree_off.push_back(part.tree_off[k] + nb);
+        for (size_t k = 1; k < part.child_off.size(); ++k) o.child_off.push_back(part.child_off[k] + cb);
+        o.event.insert(o.event.end(), part.event.begin(), part.event.end());
+        o.type_idx.insert(o.type_idx.end(), part.type_idx.begin(), part.type_idx.end());
+        o.btype_idx.insert(o.btype_idx.end(), part.btype_idx.begin(), part.btype_idx.end());
+        o.t_start.insert(o.t_start.end(), part.t_start.begin(), part.t_start.end());
+        o.t_end.insert(o.t_end.end(), part.t_end.begin(), part.t_end.end());
+        o.parent.insert(o.parent.end(), part.parent.begin(), part.parent.end());
+        o.child_idx.insert(o.child_idx.end(), part.child_idx.begin(), part.child_idx.end());
+        o.root_type_idx.insert(o.root_type_idx.end(), part.root_type_idx.begin(), part.root_type_idx.end());
+        o.root_time.insert(o.root_time.end(), part.root_time.begin(), part.root_time.end());
+        o.rejections += part.rejections;
+        part = gcdyn_simu::FlatOut();
+    }
+    *out = sim;
+    return GCDYN_OK;
+    GUARD_END(none)
+}
+
+int gcdyn_sim_sizes(const gcdyn_sim* sim, int64_t* n_trees, int64_t* n_nodes, int64_t* n_child_entries, int64_t* n_rejections) {
+    if (!sim) return fail(nullptr, GCDYN_EINVAL, "sim is NULL");
+    if (n_trees) *n_trees = (int64_t)sim->out.tree_off.size() - 1;
+    if (n_nodes) *n_nodes = (int64_t)sim->out.event.size();
+    if (n_child_entries) *n_child_entries = (int64_t)sim->out.child_idx.size();
+    if (n_rejections) *n_rejections = sim->out.rejections;
+    return GCDYN_OK;
+}
+
+int gcdyn_sim_export(const gcdyn_sim* sim, int64_t* tree_off, uint8_t* event, int32_t* type_idx, int32_t* btype_idx,
+                     double* t_start, double* t_end, int32_t* parent, int64_t* child_off, int32_t* child_idx,
+                     int32_t* root_type_idx, double* root_time) {
+    gcdyn_ctx* none = nullptr;
+    GUARD_BEGIN
+    if (!sim) return fail(none, GCDYN_EINVAL, "sim is NULL");
+    const gcdyn_simu::FlatOut& o = sim->out;
+    auto cp = [](auto* dst, const auto& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(v[0])); };
+    cp(tree_off, o.tree_off); cp(event, o.event); cp(type_idx, o.type_idx); cp(btype_idx, o.btype_idx);
+    cp(t_start, o.t_start); cp(t_end, o.t_end); cp(parent, o.parent); cp(child_off, o.child_off);
+    cp(child_idx, o.child_idx); cp(root_type_idx, o.root_type_idx); cp(root_time, o.root_time);
+    return GCDYN_OK;
+    GUARD_END(none)
+}
+
+void gcdyn_sim_destroy(gcdyn_sim* sim) { delete sim; }
 
 int gcdyn_set_profiling(gcdyn_ctx* ctx, int on) {
     GUARD_BEGIN

@@ -16,6 +16,7 @@ from .likelihood import (loglikelihood, naive_loglikelihood, stadler_appx_loglik
                          pack_params, DeviceParams, evaluate, evaluate_resident,
                          GcdynError, library_path)
 from .mcmc import random_walk_metropolis, MetropolisResult
+from .native_sim import simulate_flat
 
 __all__ = [
     # reference exports (gcdyn.jl:15-33)

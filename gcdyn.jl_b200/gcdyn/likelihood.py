@@ -111,6 +111,12 @@ def _lib():
         "gcdyn_last_diag": (C.c_int, [vp, _p_i32, _p_i32, _p_i32, _p_f64, C.c_int32]),
         "gcdyn_probe_fp64_peak": (C.c_int, [vp, _p_f64]),
         "gcdyn_last_cheb_degree": (C.c_int, [vp, _p_i32, _p_i32, _p_i32]),
+        "gcdyn_sim_forest": (C.c_int, [C.POINTER(Params), C.c_double, C.c_int32, C.c_int64, C.c_uint64, C.c_int64,
+                                       C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]),
+        "gcdyn_sim_sizes": (C.c_int, [vp, _p_i64, _p_i64, _p_i64, _p_i64]),
+        "gcdyn_sim_export": (C.c_int, [vp, _p_i64, _p_u8, _p_i32, _p_i32, _p_f64, _p_f64, _p_i32, _p_i64, _p_i32,
+                                       _p_i32, _p_f64]),
+        "gcdyn_sim_destroy": (None, [vp]),
         "gcdyn_set_profiling": (C.c_int, [vp, C.c_int]),
         "gcdyn_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
     }

@@ -168,6 +168,23 @@ int  gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* forest, con
 int  gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_launches,
                      double* err_indicator, int32_t n_psets);
 
+/* Native forward simulator (host code, OpenMP): draws n_trees trees from the law of the reference's
+ * rand_tree(model, present_time, init_type, n; reject_stubs, min_leaves, max_rejections)
+ * (src/multitype_branching_process.jl:318-402, sample_child! :432-461, mutate! :411-420, pruning with the
+ * child re-ordering of delete!, src/treenode.jl:38-48) and emits them already flattened.  `model` holds exactly
+ * one parameter set.  Tree i of the call uses the RNG stream (seed, first_tree_index + i), so forests are
+ * reproducible piecewise.  Two-phase export: ask the sizes, allocate, export, destroy. */
+typedef struct gcdyn_sim gcdyn_sim;
+int  gcdyn_sim_forest(const gcdyn_params* model, double present_time, int32_t init_type_idx, int64_t n_trees,
+                      uint64_t seed, int64_t first_tree_index, int32_t reject_stubs, int32_t min_leaves,
+                      int32_t max_rejections, gcdyn_sim** out);
+int  gcdyn_sim_sizes(const gcdyn_sim* sim, int64_t* n_trees, int64_t* n_nodes, int64_t* n_child_entries,
+                     int64_t* n_rejections);
+int  gcdyn_sim_export(const gcdyn_sim* sim, int64_t* tree_off, uint8_t* event, int32_t* type_idx, int32_t* btype_idx,
+                      double* t_start, double* t_end, int32_t* parent, int64_t* child_off, int32_t* child_idx,
+                      int32_t* root_type_idx, double* root_time);
+void gcdyn_sim_destroy(gcdyn_sim* sim);
+
 /* Chebyshev/GEMM stage of the last ODE evaluation: interpolation degree, effective degree used by the
  * GEMM (max over psets), and how many psets fell back to the item sweep.  All 0 if the stage did not run. */
 int  gcdyn_last_cheb_degree(gcdyn_ctx* ctx, int32_t* interp_degree, int32_t* effective_degree, int32_t* n_fallback);
