@@ -37,7 +37,6 @@ extern "C" {
 #define GCDYN_ENOMEM       (-3)  /* host or device allocation failed                        */
 #define GCDYN_EUNSUPPORTED (-4)  /* e.g. n_types above GCDYN_MAX_TYPES                      */
 #define GCDYN_ENODEVICE    (-5)  /* no usable CUDA device                                   */
-#define GCDYN_ENOTCONVERGED (-6) /* Taylor error indicator above tolerance at the step cap  */
 
 #define GCDYN_MAX_TYPES 128
 
@@ -113,10 +112,11 @@ typedef struct {
     const double* Gamma;           /* K×K COLUMN-major (Julia Matrix{Float64}), 1 or P matrices            */
 } gcdyn_params;
 
-/* Replaces the solver keywords reltol/abstol/maxiters (mbp.jl:114-116).  The kernels use a
- * fixed-order Taylor-series integrator on a uniform grid; all zero = defaults. */
+/* Replaces the solver keywords reltol/abstol/maxiters (mbp.jl:114-116).  The kernels use a fixed-order
+ * Taylor-series integrator whose cell widths adapt to an error indicator; all zero = defaults. */
 typedef struct {
-    int32_t steps;   /* S, Taylor steps on [0, present_time]; 0 = choose from the fastest rate         */
+    int32_t steps;   /* 0 = adaptive cells (default); S > 0 = exactly S uniform cells on [0, present_time],
+                        no adaptivity: a pset whose indicator then exceeds tol is a solver failure (-Inf)  */
     int32_t order;   /* M, Taylor order (8, 12, 16, 20 or 24); 0 = 16                                  */
     double  tol;     /* accepted size of the last Taylor terms (error indicator); 0 = 1e-11, which
                         keeps the relative error of a log-likelihood below ~1e-12        */
@@ -124,7 +124,6 @@ typedef struct {
     int32_t reserved;
 } gcdyn_opts;
 
-#define GCDYN_FLAG_NO_REFINE 1  /* do not re-run with more steps when the indicator exceeds tol */
 #define GCDYN_FLAG_SWEEP_ONLY 4 /* per-tree sums by the item sweep only (skip the Chebyshev-moment GEMM) */
 
 int  gcdyn_version(void);
