@@ -186,12 +186,10 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// blockIdx.z = split of the column range (split-K): each split writes its own partial[z][p][t]; finish_kernel adds them.
 __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A, MomentView mv, int use_tc_block,
                                                    const int* __restrict__ d_common, int P, int64_t T,
-                                                   const double* __restrict__ tree_const,
-                                                   const int* __restrict__ pstatus, const int* __restrict__ need_sweep,
-                                                   const uint8_t* __restrict__ self_loop, double* __restrict__ out_tree,
-                                                   int32_t* __restrict__ status) {
+                                                   double* __restrict__ partial) {
     extern __shared__ __align__(16) double gsm[];          // GT_STAGES × (A tile | B tile)
     auto As = [&](int st) { return gsm + (size_t)st * 2 * GT_TILE * GT_LD; };
     auto Bs = [&](int st) { return gsm + (size_t)st * 2 * GT_TILE * GT_LD + GT_TILE * GT_LD; };
@@ -208,9 +206,12 @@ __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A,
     const int n1 = (int)((J1 + GT_KC - 1) / GT_KC);
     const long long J2 = use_tc_block ? ((long long)mv.K * mv.K + 3) & ~3LL : 0;
     const int n2 = (int)((J2 + GT_KC - 1) / GT_KC);
-    const int nchunks = n1 + n2;
+    const int nall = n1 + n2;
+    const int c_lo = (int)((long long)nall * blockIdx.z / gridDim.z), c_hi = (int)((long long)nall * (blockIdx.z + 1) / gridDim.z);
+    const int nchunks = c_hi - c_lo;
     // this thread's cp.async assignments: 32 rows × 16 segments of 16 B per operand = 512 per tile, 4 per thread
-    auto issue = [&](int chunk, int buf) {
+    auto issue = [&](int rel, int buf) {
+        const int chunk = c_lo + rel;
         long long j0, jend;
         if (chunk < n1) { j0 = (long long)chunk * GT_KC; jend = J1; }
         else { j0 = mv.Jtc + (long long)(chunk - n1) * GT_KC; jend = mv.Jtc + J2; if (jend > Jst) jend = Jst; }
@@ -260,29 +261,87 @@ __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A,
             dmma_m8n8k4(acc[1][1][0], acc[1][1][1], a1, b1);
         }
     }
-    // epilogue: C fragment (row = lane/4, cols = 2*(lane%4) + {0,1})
+    // epilogue: C fragment (row = lane/4, cols = 2*(lane%4) + {0,1}) → this split's partial sums
+    double* dst = partial + (size_t)blockIdx.z * (size_t)P * (size_t)T;
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
         const int p = p0 + wr + 8 * a + fr;
         if (p >= P) continue;
-        const int pst = pstatus[p];
-        if (need_sweep[p] && !(pst & ST_SOLVER)) continue;      // sweep_kernel rewrites this pset's row
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int64_t t = t0 + wc + 8 * b + 2 * fk + e;
-                if (t >= T) continue;
-                double r = acc[a][b][e];
-                if (tree_const) r += tree_const[t];
+                if (t < T) dst[(size_t)p * T + t] = acc[a][b][e];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finish_kernel: one CTA per pset closes the evaluation.  Unflagged psets: add the GEMM's split partials and the
+// per-tree constant, apply the -Inf / status rules.  Flagged psets (series unresolved, non-finite node-term logs):
+// exact item sums for every tree straight from the pset's Taylor table (the fallback).  Then the fixed-order sum
+// over trees → out_pset[p] (mbp.jl:258), in the same order reduce_kernel uses.
+// ------------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(256) finish_kernel(ForestView fv, PsetPack pk, const double* __restrict__ tab,
+                                                     long long tab_stride, int S_cap, int grid_doubles, double Tpres,
+                                                     const double* __restrict__ partial, int splits,
+                                                     const double* __restrict__ tree_const,
+                                                     const int* __restrict__ need_sweep, int P,
+                                                     double* __restrict__ out_tree, int32_t* __restrict__ status,
+                                                     double* __restrict__ out_pset) {
+    __shared__ double part[8];
+    const int p = blockIdx.x;
+    const int K = fv.K;
+    const int64_t T = fv.n_trees;
+    const int pst = pk.pstatus[p];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    double* orow = out_tree + (size_t)p * T;
+    if (need_sweep[p] && !(pst & ST_SOLVER)) {
+        const double* tp = tab + (size_t)p * tab_stride;
+        const double* nt = pk.nt + (size_t)p * pk.ntw;
+        const double lmusig = nt[K + K * K], lrho = nt[K + K * K + 1];
+        const int S = pk.S[p];
+        for (int64_t t = warp; t < T; t += nwarps) {
+            const double acc = tree_items_sum<M, false>(fv, tp, nt, K, S, S_cap, grid_doubles, Tpres, fv.item_off[t],
+                                                        fv.item_off[t + 1], lane);
+            if (lane == 0) {
+                const int rt = fv.root_type[t];
+                double r = acc + count_times_log(fv.n_death[t], lmusig) + count_times_log(fv.n_surv[t], lrho)
+                           - (rt >= 0 ? pk.logcond[(size_t)p * K + rt] : CUDART_NAN);
                 int st = pst;
-                if (self_loop[t]) st |= ST_SELF_LOOP;
-                if (st & (ST_SELF_LOOP | ST_SOLVER)) r = -CUDART_INF;
+                if (fv.self_loop[t]) st |= ST_SELF_LOOP;
+                if (st & ST_SELF_LOOP) r = -CUDART_INF;
                 else if (r != r) st |= ST_DOMAIN;
-                out_tree[(size_t)p * T + t] = r;
+                orow[t] = r;
                 if (status) status[(size_t)p * T + t] = st;
             }
         }
+    } else {
+        for (int64_t t = threadIdx.x; t < T; t += blockDim.x) {
+            double r = 0.0;
+            for (int z = 0; z < splits; ++z) r += partial[((size_t)z * P + p) * (size_t)T + t];
+            if (tree_const) r += tree_const[t];
+            int st = pst;
+            if (fv.self_loop[t]) st |= ST_SELF_LOOP;
+            if (st & (ST_SELF_LOOP | ST_SOLVER)) r = -CUDART_INF;
+            else if (r != r) st |= ST_DOMAIN;
+            orow[t] = r;
+            if (status) status[(size_t)p * T + t] = st;
+        }
+    }
+    __syncthreads();
+    double acc = 0.0;
+    for (int64_t t = threadIdx.x; t < T; t += blockDim.x) acc += orow[t];
+    acc = warp_sum(acc);
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; ++w) s += part[w];
+        out_pset[p] = s;
     }
 }
 

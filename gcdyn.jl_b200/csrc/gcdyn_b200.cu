@@ -60,7 +60,7 @@ struct gcdyn_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     // workspace (grow-only)
-    DevBuf params_blob, pack, table, out_tree, out_pset, status, probe, gemm_a, flags;
+    DevBuf params_blob, pack, table, out_tree, out_pset, status, probe, gemm_a, flags, partial;
     PinBuf pin_in, pin_out;
     // diagnostics of the last evaluation
     int last_steps = 0, last_order = 0, last_launches = 0, last_P = 0;
@@ -403,6 +403,29 @@ int ensure_moments(gcdyn_ctx* ctx, const gcdyn_forest* f, double T, cudaStream_t
     return GCDYN_OK;
 }
 
+template <int M>
+int launch_finish_m(gcdyn_ctx* ctx, const gcdyn_forest* f, const PsetPack& pk, const double* tab, const TrajCfg& cfg, double T,
+                    const double* partial, int splits, const double* tree_const, const int* need_sweep, int P,
+                    double* out_tree, int32_t* status, double* out_pset, cudaStream_t st) {
+    finish_kernel<M><<<P, 256, 0, st>>>(f->v, pk, tab, cfg.tab_stride, cfg.S_cap, cfg.grid_doubles, T, partial, splits,
+                                        tree_const, need_sweep, P, out_tree, status, out_pset);
+    CU_TRY(ctx, cudaGetLastError());
+    return GCDYN_OK;
+}
+
+int launch_finish(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& pk, const double* tab, const TrajCfg& cfg,
+                  double T, const double* partial, int splits, const double* tree_const, const int* need_sweep, int P,
+                  double* out_tree, int32_t* status, double* out_pset, cudaStream_t st) {
+    switch (M) {
+        case 8: return launch_finish_m<8>(ctx, f, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
+        case 12: return launch_finish_m<12>(ctx, f, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
+        case 16: return launch_finish_m<16>(ctx, f, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
+        case 20: return launch_finish_m<20>(ctx, f, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
+        case 24: return launch_finish_m<24>(ctx, f, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
+    }
+    return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
+}
+
 // Enqueue one evaluation on `st`.  All pointers are device pointers; d_out_tree/d_status may be null.
 // S_fixed > 0 pins the number of Taylor cells; otherwise every pset adapts it inside traj_kernel.
 int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, double rate_max, double T, int method,
@@ -490,12 +513,29 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
                 CU_TRY(ctx, cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
                 ctx->gemm_attr_set = true;
             }
+            // split the column range when the tile grid alone cannot fill the machine (deterministic: fixed order in finish)
+            const long long tiles = (long long)grid.x * grid.y;
+            const int splits = tiles >= 4LL * ctx->sm_count ? 1 : (tiles >= 2LL * ctx->sm_count ? 2 : 4);
+            grid.z = (unsigned)splits;
+            CU_TRY(ctx, ctx->partial.ensure((size_t)splits * P * (size_t)Tn * 8));
             gemm_kernel<<<grid, 128, GT_SMEM_BYTES, st>>>(ctx->gemm_a.as<double>(), mv, cc.compact_tc ? 0 : 1, d_common, P, Tn,
-                                              tree_const, pk.pstatus, need_sweep, f->v.self_loop, d_out_tree, d_status);
+                                                          ctx->partial.as<double>());
             CU_TRY(ctx, cudaGetLastError());
             ++launches;
-            only_flagged = need_sweep;
+            if (prof) { cudaEventRecord(ctx->ev[4], st); cudaEventRecord(ctx->ev[5], st); }
+            rc = launch_finish(ctx, M, f, pk, ctx->table.as<double>(), cfg, T, ctx->partial.as<double>(), splits, tree_const,
+                               need_sweep, P, d_out_tree, d_status, d_out_pset, st);
+            if (rc) return rc;
+            ++launches;
+            if (prof) { cudaEventRecord(ctx->ev[6], st); ctx->ev_valid = true; }
             ctx->last_cheb_D = cc.D;
+            ctx->last_steps = cfg.S_cap;
+            ctx->last_order = M;
+            ctx->last_launches = launches;
+            ctx->last_P = P;
+            ctx->last_pack = pk;
+            if (pk_out) *pk_out = pk;
+            return GCDYN_OK;
         } else {
             ctx->last_cheb_D = 0;
         }
@@ -797,7 +837,7 @@ void gcdyn_ctx_destroy(gcdyn_ctx* ctx) {
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     ctx->params_blob.release(); ctx->pack.release(); ctx->table.release(); ctx->out_tree.release();
-    ctx->out_pset.release(); ctx->status.release(); ctx->probe.release(); ctx->gemm_a.release(); ctx->flags.release();
+    ctx->out_pset.release(); ctx->status.release(); ctx->probe.release(); ctx->gemm_a.release(); ctx->flags.release(); ctx->partial.release();
     ctx->pin_in.release(); ctx->pin_out.release();
     cudaSetDevice(prev);
     delete ctx;
