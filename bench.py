@@ -326,23 +326,29 @@ def run_gpu(args):
     C = 2 * K + 4          # count columns (shared Γ: type changes are a per-tree constant, not K² columns)
     J = C + (cheb["effective_degree"] + 1) * K if cheb["interp_degree"] else 0
     Dn = cheb["interp_degree"]
-    flops = {"sweep": n_items * P * (2.0 * (M + 1) + 8.0) * (cheb["n_fallback"] / P if Dn else 1.0),
-             "trajectory": P * S * (M * (2.0 * K * K + 5.0 * K) + M * (M + 1.0) * K + 6.0 * (M + 2) * K),
+    # the Chebyshev stage (node values + DCT) is the tail of the trajectory kernel; the finish kernel only adds
+    # the split-K partials and sums per pset (its item-sum fallback runs for n_fallback psets)
+    gemm_path = bool(Dn)
+    flops = {"trajectory": P * S * (M * (2.0 * K * K + 5.0 * K) + M * (M + 1.0) * K + 6.0 * (M + 2) * K) +
+                           (P * K * ((Dn + 1) * 2.0 * (M + 1) + 2.0 * (Dn + 1) ** 2) if gemm_path else 0.0),
              "gemm": 2.0 * Tn * P * J,
-             "chebyshev": P * K * ((Dn + 1) * 2.0 * (M + 1) + 2.0 * (Dn + 1) ** 2)}
-    dom = max(("sweep", "trajectory", "gemm", "chebyshev"), key=lambda k: acc.get(k, 0.0))
+             "sweep": 0.0 if gemm_path else n_items * P * (2.0 * (M + 1) + 8.0),
+             "finish": (4.0 * Tn * P + n_items * cheb["n_fallback"] * (2.0 * (M + 1) + 8.0)) if gemm_path else 1.0 * Tn * P}
+    ran = ("trajectory", "gemm", "finish") if gemm_path else ("trajectory", "sweep", "finish")
+    dom = max(ran, key=lambda k: acc.get(k, 0.0))
     achieved = flops[dom] / (acc[dom] * 1e-3) / 1e12
     per_kernel = {k: {"ms": acc[k], "algorithmic_gflop": flops[k] / 1e9,
-                      "tflops": flops[k] / (acc[k] * 1e-3) / 1e12 if acc.get(k) else None,
-                      "frac_of_fp64_peak": flops[k] / (acc[k] * 1e-3) / 1e12 / fp64_peak if acc.get(k) else None}
-                  for k in flops}
+                      "tflops": flops[k] / (acc[k] * 1e-3) / 1e12,
+                      "frac_of_fp64_peak": flops[k] / (acc[k] * 1e-3) / 1e12 / fp64_peak}
+                  for k in ran}
     # algorithmic bytes of the GEMM operands (read once) and its output
     gemm_bytes = (Tn * J + P * J + Tn * P) * 8.0
     roofline = {"kernel": f"{dom}_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "peak_source": "measured live: register-resident DFMA loop on all SMs (gcdyn_probe_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 figure",
-                "traffic": None, "kernel_ms": acc, "kernel_share": {k: v / sum(acc.values()) for k, v in acc.items()},
+                "traffic": None, "kernel_ms": {k: acc[k] for k in ran},
+                "kernel_share": {k: acc[k] / sum(acc[r] for r in ran) for k in ran},
                 "algorithmic_flops_per_launch": flops[dom], "per_kernel": per_kernel, "chebyshev": cheb,
                 "hbm": {"achieved_gbs": gemm_bytes / (acc["gemm"] * 1e-3) / 1e9 if acc.get("gemm") else None,
                         "peak_gbs": peaks.get("hbm_gbs"),

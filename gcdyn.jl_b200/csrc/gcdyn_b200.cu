@@ -277,7 +277,9 @@ int carve_pack(gcdyn_ctx* ctx, int P, int K, PsetPack* pk) {
 size_t traj_smem_bytes(int K, int D, int S_cap) {
     const size_t KS = ((size_t)K + 3) & ~(size_t)3;
     size_t n = 2 * KS + (K <= 32 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
-    if (D > 0) n += 2 * (size_t)D + (3 * (size_t)D + 4) * K + 2 * (size_t)S_cap + 8;
+    if (D > 0)   // cheb_stage: cos table, node values / coefficients, folded halves, DCT matrix, node cells, grid
+        n += 2 * (size_t)D + (((size_t)(D + 1) * K + 1) & ~(size_t)1) + ((size_t)D + 2) * K +
+             ((size_t)D / 2 + 1) * ((size_t)D + 4) + 2 * ((size_t)D + 1) + 2 * (size_t)S_cap + 4;
     return n * sizeof(double);
 }
 
@@ -365,7 +367,7 @@ int cheb_degree(double T, double rate_max, int K, int Dcap, int S_cap, int smem_
     for (int d : ladder) if ((double)d >= want) { D = d; break; }
     D = std::min(D, Dcap);
     while (D > 16 && traj_smem_bytes(K, D, S_cap) + 1024 > (size_t)smem_optin) D -= 16;
-    return D & ~1;
+    return D & ~3;   // cheb_stage handles degrees in groups of four
 }
 
 // Build (once per forest and present_time) the per-tree Chebyshev moments and count columns.
@@ -488,7 +490,7 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         rc = launch_traj(ctx, M, pv, pk, cfg, cc, ctx->table.as<double>(), st);
         if (rc) return rc;
         ++launches;
-        if (prof) { cudaEventRecord(ctx->ev[2], st); cudaEventRecord(ctx->ev[3], st); }
+        if (prof) cudaEventRecord(ctx->ev[2], st);
         if (use_gemm) {
             const MomentView& mv = f->mom;
             const double* tree_const = nullptr;
@@ -508,6 +510,7 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
                 }
                 tree_const = f->d_tree_const;
             }
+            if (prof) cudaEventRecord(ctx->ev[3], st);
             dim3 grid((unsigned)((Tn + GT_TILE - 1) / GT_TILE), (unsigned)((P + GT_TILE - 1) / GT_TILE));
             if (!ctx->gemm_attr_set) {
                 CU_TRY(ctx, cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
@@ -539,7 +542,7 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         } else {
             ctx->last_cheb_D = 0;
         }
-        if (prof) cudaEventRecord(ctx->ev[4], st);
+        if (prof) { cudaEventRecord(ctx->ev[3], st); cudaEventRecord(ctx->ev[4], st); }
         const int S_stage = S_fixed > 0 ? S_fixed : std::min(cfg.S_cap, expected_steps(T, rate_max, M));
         const size_t want_smem = ((size_t)cfg.grid_doubles + (size_t)S_stage * K * L) * 8;
         rc = launch_sweep(ctx, M, f, pk, ctx->table.as<double>(), cfg.tab_stride, cfg.S_cap, cfg.grid_doubles, T, P,

@@ -13,6 +13,7 @@
 //   reduce_kernel per pset: fixed-order sum over trees → out_pset[p]   (mbp.jl:258)
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -110,7 +111,8 @@ __device__ __forceinline__ double birth_rate(const ParamsView& pv, int p, int i)
 }
 
 // Rates and node-term logs of one pset, computed cooperatively by `nthr` threads (tid = 0..nthr-1).
-__device__ __forceinline__ void prep_pset(const ParamsView& pv, const PsetPack& pk, int p, int method, int tid, int nthr) {
+__device__ __forceinline__ void prep_pset(const ParamsView& pv, const PsetPack& pk, int p, int method, int tid, int nthr,
+                                          bool init_status = true) {
     const int K = pv.K;
     const double mu = pv.mu[p], delta = pv.delta[p], rho = pv.rho[p], sigma = pv.sigma[p];
     const double* G = pv.Gamma + (size_t)p * pv.gamma_stride;   // column-major: Γ[i,j] = G[i + j*K]
@@ -137,9 +139,11 @@ __device__ __forceinline__ void prep_pset(const ParamsView& pv, const PsetPack& 
     if (tid == 0) {
         nt[K + K * K] = log(mu) + log(sigma);   // mbp.jl:171
         nt[K + K * K + 1] = log(rho);           // mbp.jl:168
-        pk.pstatus[p] = 0;
-        pk.perr[p] = 0.0;
-        pk.S[p] = 0;
+        if (init_status) {
+            pk.pstatus[p] = 0;
+            pk.perr[p] = 0.0;
+            pk.S[p] = 0;
+        }
     }
 }
 
@@ -223,48 +227,82 @@ __device__ __forceinline__ double eval_row(const double* __restrict__ row, doubl
 // at the D+1 Chebyshev–Gauss–Lobatto nodes from the pset's Taylor table, DCT-I → a[d][x]; effective degree;
 // count-column coefficients; fallback flag.  `sm` = this stage's shared-memory scratch.
 // ------------------------------------------------------------------------------------------------
+#ifdef GCDYN_TRAJ_TRACE
+#define TRACE_STAMP(i) do { if (threadIdx.x == 0) g_trace[i] = clock64(); } while (0)
+#define TRACE_ARG , long long* g_trace
+#define TRACE_PASS , g_trace
+#else
+#define TRACE_STAMP(i) do { } while (0)
+#define TRACE_ARG
+#define TRACE_PASS
+#endif
+
 template <int M>
 __device__ __forceinline__ void cheb_stage(const ParamsView& pv, const PsetPack& pk, const ChebCfg& cfg, int p,
-                                           const double* __restrict__ tab, double* __restrict__ sm) {
+                                           const double* __restrict__ tab, double* __restrict__ sm TRACE_ARG) {
     const MomentView& mv = cfg.mv;
     double* __restrict__ A = cfg.A;
     int* __restrict__ need_sweep = cfg.need_sweep;
     int* __restrict__ d_common = cfg.d_common;
     constexpr int L = M + 2;
     const int K = mv.K, C1 = mv.C1, D = cfg.D;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    double* costab = sm;                   // [2D]  cos(π m / D)
-    double* V = costab + 2 * D;            // [(D+1)*K] node values
-    double* Acoef = V + (size_t)(D + 1) * K;   // [(D+1)*K] coefficients
+    const int H = D / 2, CW = D + 4, NV = (D + 1) * K;
+    double* costab = sm;                               // [2D]  cos(π m / D)
+    double* V = costab + 2 * D;                        // [(D+1)*K] node values, later the coefficients a[d][x]
+    double* Acoef = V;
+    double* EO = V + (((size_t)NV + 1) & ~(size_t)1);  // [2][(H+1)*K] folded node values (16-byte aligned)
+    double* cosm = EO + 2 * (size_t)(H + 1) * K;       // [(H+1)][CW]  cos(π k d / D), zero for d > D
+    double* nth = cosm + (size_t)(H + 1) * CW;         // [D+1] θ of node k inside its cell
+    int* ncell = reinterpret_cast<int*>(nth + (D + 1));   // [D+1] cell of node k (2(D+1) ints reserved)
+    double* sgrid = nth + 2 * (D + 1);                 // [S+1] τ_s, then [S] 1/h_s
     __shared__ int s_deff, s_flag;
     const int S = pk.S[p];
     const int pst = pk.pstatus[p];
+    double* sinvh = sgrid + (S + 1);
     if (threadIdx.x == 0) { s_deff = 8; s_flag = (pst & ST_SOLVER) ? 1 : 0; }
     for (int m = threadIdx.x; m < 2 * D; m += blockDim.x) costab[m] = cospi((double)m / (double)D);
-    __syncthreads();
     const double* tp = tab + (size_t)p * cfg.tab_stride;
     const double* rows = tp + cfg.grid_doubles;
     // the pset's grid [τ_s | 1/h_s] goes to shared memory first: the cell search is then a few LDS, not L2 round trips
-    double* sgrid = Acoef + (size_t)(D + 1) * K + 2 * (size_t)(D / 2 + 1) * K;   // [S+1], then [S]
-    double* sinvh = sgrid + (S + 1);
     for (int i = threadIdx.x; i <= S; i += blockDim.x) sgrid[i] = tp[i];
     for (int i = threadIdx.x; i < S; i += blockDim.x) sinvh[i] = tp[cfg.S_cap + 1 + i];
     __syncthreads();
-    if (!(pst & ST_SOLVER)) {
-        for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
-            const int k = idx / K, x = idx - k * K;
-            const double tau = cfg.T * (1.0 + costab[k]) * 0.5;
-            const int s = find_cell(sgrid, S, tau);
-            V[idx] = eval_row<M, false>(rows + ((size_t)s * K + x) * L, (tau - sgrid[s]) * sinvh[s]);
-        }
-    } else {
-        for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) V[idx] = 0.0;
+    TRACE_STAMP(5);
+    // cell and in-cell coordinate of every Chebyshev–Gauss–Lobatto node (shared by the K types), and the DCT matrix
+    for (int k = threadIdx.x; k <= D; k += blockDim.x) {
+        const double tau = cfg.T * (1.0 + costab[k]) * 0.5;
+        const int c = find_cell(sgrid, S, tau);
+        ncell[k] = c;
+        nth[k] = (tau - sgrid[c]) * sinvh[c];
+    }
+    for (int idx = threadIdx.x; idx < (H + 1) * CW; idx += blockDim.x) {
+        const int k = idx / CW, d = idx - k * CW;
+        cosm[idx] = d <= D ? costab[(k * d) % (2 * D)] : 0.0;
     }
     __syncthreads();
+    if (!(pst & ST_SOLVER)) {
+        // four lookups in flight per thread: the table rows come from L2
+        for (int base = threadIdx.x; base < NV; base += 4 * blockDim.x) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = min(base + u * (int)blockDim.x, NV - 1);
+                const int k = idx / K, x = idx - k * K;
+                v[u] = eval_row<M, false>(rows + ((size_t)ncell[k] * K + x) * L, nth[k]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * (int)blockDim.x;
+                if (idx < NV) V[idx] = v[u];
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < NV; idx += blockDim.x) V[idx] = 0.0;
+    }
+    __syncthreads();
+    TRACE_STAMP(6);
     // DCT-I with the symmetry cos(π(D−k)d/D) = (−1)^d cos(πkd/D): fold the node values into an even and an
     // odd half, E_k = w_k (V_k + V_{D−k}), O_k = w_k (V_k − V_{D−k}), k = 0..D/2, w_0 = w_{D/2} = 1/2.
-    const int H = D / 2;
-    double* EO = Acoef + (size_t)(D + 1) * K;        // [2][(H+1)*K]
     for (int idx = threadIdx.x; idx < (H + 1) * K; idx += blockDim.x) {
         const int k = idx / K, x = idx - k * K;
         const double w = (k == 0 || k == H) ? 0.5 : 1.0;
@@ -273,57 +311,50 @@ __device__ __forceinline__ void cheb_stage(const ParamsView& pv, const PsetPack&
         EO[(H + 1) * K + idx] = w * (a - b);
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
-        const int d = idx / K, x = idx - d * K;
-        const double* src = EO + (size_t)(d & 1) * (H + 1) * K + x;
-        double s0 = 0.0, s1 = 0.0;
-        int m = 0;                                   // (k*d) mod 2D, advanced incrementally
-        int k = 0;
-        for (; k + 1 <= H; k += 2) {
-            s0 = fma(src[k * K], costab[m], s0);
-            m += d; m -= (m >= 2 * D) ? 2 * D : 0;
-            s1 = fma(src[(k + 1) * K], costab[m], s1);
-            m += d; m -= (m >= 2 * D) ? 2 * D : 0;
-        }
-        if (k <= H) s0 = fma(src[k * K], costab[m], s0);
-        double a = (2.0 / (double)D) * (s0 + s1);
-        if (d == 0 || d == D) a *= 0.5;
-        Acoef[idx] = a;
-    }
-    __syncthreads();
-    // effective degree per type (a warp per type, lanes over degrees): the smallest d with Σ_{k>d}|a_k| ≤ tol;
-    // the series counts as unresolved if its last three terms are not small
-    for (int x = warp; x < K; x += nwarps) {
-        // lane owns the contiguous degrees [lo, hi); suffix sums of |a| are combined across lanes
-        const int per = (D + 1 + 31) / 32;
-        const int lo = lane * per, hi = min(D + 1, lo + per);
-        double mine = 0.0;
-        for (int d = lo; d < hi; ++d) mine += fabs(Acoef[d * K + x]);
-        double above = 0.0;                        // Σ over lanes > lane
-        {
-            double run = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double v = __shfl_down_sync(FULL, run, o);
-                if (lane + o < 32) run += v;
+    TRACE_STAMP(7);
+    // a thread owns four consecutive degrees 4g..4g+3 of one type: even degrees contract E, odd degrees O
+    {
+        const int NG = D / 4 + 1;
+        const double scale = 2.0 / (double)D;
+        for (int w = threadIdx.x; w < NG * K; w += blockDim.x) {
+            const int g = w / K, x = w - g * K;
+            const double* E = EO + x;
+            const double* O = EO + (size_t)(H + 1) * K + x;
+            const double* cg = cosm + 4 * g;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 5
+            for (int k = 0; k <= H; ++k) {
+                const double e = E[k * K], o = O[k * K];
+                const double2 c01 = *reinterpret_cast<const double2*>(cg + (size_t)k * CW);
+                const double2 c23 = *reinterpret_cast<const double2*>(cg + (size_t)k * CW + 2);
+                a0 = fma(e, c01.x, a0);
+                a1 = fma(o, c01.y, a1);
+                a2 = fma(e, c23.x, a2);
+                a3 = fma(o, c23.y, a3);
             }
-            above = run - mine;
-        }
-        int found = 8;
-        double tail = above;
-        for (int d = hi - 1; d >= lo && d > 8; --d) {
-            tail += fabs(Acoef[d * K + x]);
-            if (!(tail <= cfg.tol)) { found = d; break; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) found = max(found, __shfl_xor_sync(FULL, found, o));
-        if (lane == 0) {
-            const double last3 = fabs(Acoef[D * K + x]) + fabs(Acoef[(D - 1) * K + x]) + fabs(Acoef[(D - 2) * K + x]);
-            if (!(last3 <= cfg.tol)) atomicExch(&s_flag, 1);
-            atomicMax(&s_deff, found);
+            const int d0 = 4 * g;
+            Acoef[d0 * K + x] = (d0 == 0 || d0 == D) ? 0.5 * scale * a0 : scale * a0;
+            if (d0 + 1 <= D) Acoef[(d0 + 1) * K + x] = scale * a1;
+            if (d0 + 2 <= D) Acoef[(d0 + 2) * K + x] = scale * a2;
+            if (d0 + 3 <= D) Acoef[(d0 + 3) * K + x] = (d0 + 3 == D) ? 0.5 * scale * a3 : scale * a3;
         }
     }
     __syncthreads();
+    TRACE_STAMP(8);
+    // effective degree (a thread per type): the largest d whose tail Σ_{k≥d}|a_k| exceeds tol — the sum runs
+    // downwards from D, so it is monotone; the series counts as unresolved if its last three terms are not small
+    for (int x = threadIdx.x; x < K; x += blockDim.x) {
+        double tail = 0.0;
+        int found = 8;
+        for (int d = D; d > 8; --d) {
+            tail += fabs(Acoef[d * K + x]);
+            if (!(tail <= cfg.tol) && d > found) found = d;
+            if (d == D - 2 && !(tail <= cfg.tol)) atomicExch(&s_flag, 1);
+        }
+        atomicMax(&s_deff, found);
+    }
+    __syncthreads();
+    TRACE_STAMP(9);
     const int deff = s_deff;
     double* Arow = A + (size_t)p * mv.Jst;
     for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
@@ -363,6 +394,7 @@ __device__ __forceinline__ void cheb_stage(const ParamsView& pv, const PsetPack&
         }
     }
     __syncthreads();
+    TRACE_STAMP(10);
     if (threadIdx.x == 0) {
         need_sweep[p] = s_flag;
         if (!s_flag) atomicMax(d_common, deff);
@@ -389,7 +421,14 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
     constexpr int L = M + 2;
     const int p = blockIdx.x;
     const int K = pv.K;
-    prep_pset(pv, pk, p, 0, threadIdx.x, TRAJ_THREADS);
+#ifdef GCDYN_TRAJ_TRACE
+    __shared__ long long g_trace[16];
+    __shared__ int g_attempts;
+#endif
+    TRACE_STAMP(0);
+    // warps 1..3 compute the rates and node-term logs while warp 0 integrates (it needs neither)
+    if (threadIdx.x >= 32) prep_pset(pv, pk, p, 0, threadIdx.x - 32, TRAJ_THREADS - 32, false);
+    TRACE_STAMP(1);
     if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     const int KS = KPL == 1 ? KP : ((K + 3) & ~3);     // broadcast buffer length (multiple of 4)
@@ -445,6 +484,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
     const float decade = exp2f(__log2f(0.1f) * (1.0f / (float)M));      // 0.1^(1/M)
     bool bad = false, failed = false;
     int s = 0, rejects = 0;
+    TRACE_STAMP(2);
     for (;;) {
         double hc = h;
         bool last = false;
@@ -517,6 +557,9 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
                 c[n + 1][q] = rhs * hn;
             }
         }
+#ifdef GCDYN_TRAJ_TRACE
+        if (s == 0 && rejects == 0) TRACE_STAMP(11);
+#endif
         // error indicator of this cell: the last two Taylor terms, maximum over the pset's types
         double ind = 0.0;
 #pragma unroll
@@ -540,6 +583,9 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
             continue;
         }
         if (s >= cfg.S_cap) { failed = true; break; }
+#ifdef GCDYN_TRAJ_TRACE
+        if (s == 0 && rejects == 0) TRACE_STAMP(12);
+#endif
         // accept: emit the F polynomial of this cell, advance p and F to the next grid point
 #pragma unroll
         for (int q = 0; q < KPL; ++q) {
@@ -566,6 +612,9 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
         }
         if (lane == 0) { gridp[s] = tau; invhp[s] = 1.0 / hc; }
         if (!(ind_f <= errmax)) errmax = ind_f;
+#ifdef GCDYN_TRAJ_TRACE
+        if (s == 0 && rejects == 0) TRACE_STAMP(13);
+#endif
         ++s;
         if (last) break;
         tau += hc;
@@ -578,6 +627,10 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
         }
     }
     if (lane == 0) gridp[s] = cfg.T;
+    TRACE_STAMP(3);
+#ifdef GCDYN_TRAJ_TRACE
+    if (lane == 0) g_attempts = s + rejects;
+#endif
     // conditioning term and diagnostics
 #pragma unroll
     for (int q = 0; q < KPL; ++q) {
@@ -589,13 +642,25 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
     if (lane == 0) {
         pk.perr[p] = (double)errmax;
         pk.S[p] = s > 0 ? s : 1;
-        if (anybad) pk.pstatus[p] |= ST_SOLVER;
+        pk.pstatus[p] = anybad ? ST_SOLVER : 0;
     }
     }   // warp 0
     if (cc.D <= 0) return;                              // CTA-uniform
     __syncthreads();                                    // table, grid, status of this pset are complete and visible
+    TRACE_STAMP(4);
     const size_t traj_doubles = 2 * (size_t)(KPL == 1 ? KP : ((K + 3) & ~3)) + (KPL == 1 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
-    cheb_stage<M>(pv, pk, cc, p, tab, smem + traj_doubles);
+    cheb_stage<M>(pv, pk, cc, p, tab, smem + traj_doubles TRACE_PASS);
+#ifdef GCDYN_TRAJ_TRACE
+    if (threadIdx.x == 0 && (p == 0 || p == 100 || p == 120 || p == 255)) {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        printf("TRACE sm=%u cell0: orders=%lld ctrl=%lld accept=%lld\n", smid, g_trace[11] - g_trace[2], g_trace[12] - g_trace[11], g_trace[13] - g_trace[12]);
+        printf("TRACE p=%d S=%d attempts=%d prep=%lld setup=%lld integ=%lld fin=%lld | grid=%lld V=%lld fold=%lld dct=%lld deff=%lld write=%lld\n",
+               p, pk.S[p], g_attempts, g_trace[1] - g_trace[0], g_trace[2] - g_trace[1], g_trace[3] - g_trace[2],
+               g_trace[4] - g_trace[3], g_trace[5] - g_trace[4], g_trace[6] - g_trace[5], g_trace[7] - g_trace[6],
+               g_trace[8] - g_trace[7], g_trace[9] - g_trace[8], g_trace[10] - g_trace[9]);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

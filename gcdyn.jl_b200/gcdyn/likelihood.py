@@ -188,10 +188,10 @@ class Context:
         _check(_lib().gcdyn_set_profiling(self._h, 1 if on else 0), self._h)
 
     def last_kernel_ms(self):
-        """(prep, trajectory, sweep, reduce) durations of the last evaluation, CUDA-event timed."""
+        """Durations of the stages of the last evaluation, CUDA-event timed (see gcdyn_last_kernel_ms)."""
         ms = (C.c_float * 6)()
         _check(_lib().gcdyn_last_kernel_ms(self._h, ms), self._h)
-        return dict(zip(("prep", "trajectory", "chebyshev", "gemm", "sweep", "reduce"), (float(x) for x in ms)))
+        return dict(zip(("setup", "trajectory", "tree_const", "gemm", "sweep", "finish"), (float(x) for x in ms)))
 
     def probe_fp64_peak(self):
         v = C.c_double()

@@ -190,7 +190,9 @@ int  gcdyn_last_cheb_degree(gcdyn_ctx* ctx, int32_t* interp_degree, int32_t* eff
 
 /* Per-kernel timing for the roofline report: when on, every evaluation brackets its kernels with CUDA
  * events on the launching stream; gcdyn_last_kernel_ms waits for the last evaluation and returns
- * ms[6] = {prep, trajectory (or Stadler conditioning), chebyshev, gemm, sweep (or alternate), reduce}. */
+ * ms[6] = {setup, trajectory incl. its Chebyshev tail (or Stadler conditioning), tree_const (only when Gamma
+ * changed), gemm, sweep (or alternate), finish (or reduce)}; an interval whose kernel did not run holds only the
+ * event gap (~3 us). */
 int  gcdyn_set_profiling(gcdyn_ctx* ctx, int on);
 int  gcdyn_last_kernel_ms(gcdyn_ctx* ctx, float* ms);
 
