@@ -274,19 +274,21 @@ int carve_pack(gcdyn_ctx* ctx, int P, int K, PsetPack* pk) {
 
 // Dynamic shared memory of traj_kernel: [ĉ broadcast buffer | δΓ (K > 32 only)] for the integrating warp, then the
 // Chebyshev stage's scratch [cos table | node values | coefficients | folded halves | grid].  Mirrors the kernel.
-size_t traj_smem_bytes(int K, int D, int S_cap) {
+size_t traj_smem_bytes(int K, int D, int S_cap, int M) {
     const size_t KS = ((size_t)K + 3) & ~(size_t)3;
     size_t n = 2 * KS + (K <= 32 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
-    if (D > 0)   // cheb_stage: cos table, node values / coefficients, folded halves, DCT matrix, node cells, grid
+    // ring of published cells + their grid/flags (ChebSmem)
+    n += 2 * (size_t)S_cap + 4 + ((size_t)S_cap + 8) / 2 + (size_t)CHEB_RING_SLOTS * K * (M + 2);
+    if (D > 0)   // Chebyshev stage: cos table, node values / coefficients, folded halves, DCT matrix, two row buffers
         n += 2 * (size_t)D + (((size_t)(D + 1) * K + 1) & ~(size_t)1) + ((size_t)D + 2) * K +
-             ((size_t)D / 2 + 1) * ((size_t)D + 4) + 2 * ((size_t)D + 1) + 2 * (size_t)S_cap + 4;
+             ((size_t)D / 2 + 1) * ((size_t)D + 4) + 2 * (size_t)K * (M + 2);
     return n * sizeof(double);
 }
 
 template <int M, int KP, int KPL>
 int launch_traj_inst(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, const ChebCfg& cc,
                      double* tab, cudaStream_t st) {
-    const size_t smem = traj_smem_bytes(pv.K, cc.D, cfg.S_cap);
+    const size_t smem = traj_smem_bytes(pv.K, cc.D, cfg.S_cap, M);
     if (smem > 48 * 1024)
         CU_TRY(ctx, cudaFuncSetAttribute(traj_kernel<M, KP, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     traj_kernel<M, KP, KPL><<<pv.P, TRAJ_THREADS, smem, st>>>(pv, pk, cfg, cc, tab);
@@ -359,14 +361,14 @@ int launch_sweep(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& p
 
 // Chebyshev interpolation degree for this batch: generous (the kernel trims to the effective degree),
 // even, ≤ the moment cap and small enough for cheb_kernel's shared memory.
-int cheb_degree(double T, double rate_max, int K, int Dcap, int S_cap, int smem_optin) {
+int cheb_degree(double T, double rate_max, int K, int Dcap, int S_cap, int M, int smem_optin) {
     double want = T * rate_max + 12.0;
     if (!(want == want)) want = 32.0;
     const int ladder[] = {32, 48, 64, 96, 128};
     int D = 128;
     for (int d : ladder) if ((double)d >= want) { D = d; break; }
     D = std::min(D, Dcap);
-    while (D > 16 && traj_smem_bytes(K, D, S_cap) + 1024 > (size_t)smem_optin) D -= 16;
+    while (D > 16 && traj_smem_bytes(K, D, S_cap, M) + 1024 > (size_t)smem_optin) D -= 16;
     return D & ~3;   // cheb_stage handles degrees in groups of four
 }
 
@@ -480,7 +482,7 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             cc.tab_stride = cfg.tab_stride;
             cc.S_cap = cfg.S_cap;
             cc.grid_doubles = cfg.grid_doubles;
-            cc.D = cheb_degree(T, rate_max, K, f->mom.Dcap, cfg.S_cap, ctx->smem_optin);
+            cc.D = cheb_degree(T, rate_max, K, f->mom.Dcap, cfg.S_cap, M, ctx->smem_optin);
             cc.compact_tc = pv.gamma_stride == 0 ? 1 : 0;
             cc.mv = f->mom;
             cc.A = ctx->gemm_a.as<double>();
@@ -1141,3 +1143,9 @@ int gcdyn_probe_fp64_peak(gcdyn_ctx* ctx, double* tflops) {
 }
 
 }  // extern "C"
+
+#ifdef GCDYN_TRAJ_TRACE
+extern "C" int gcdyn_trace_dump(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, gcdyn::g_trace_out, sizeof(long long) * 1024 * 24);
+}
+#endif

@@ -199,7 +199,8 @@ __device__ __forceinline__ int find_cell(const double* __restrict__ grid, int S,
 }
 
 // F_x(τ) from a table row of L = M+2 coefficients: even/odd split halves the dependent FMA chain.
-template <int M, bool SMEM>
+// COHERENT: the row was written earlier by this same kernel (ld.global.cg instead of the read-only path).
+template <int M, bool SMEM, bool COHERENT = false>
 __device__ __forceinline__ double eval_row(const double* __restrict__ row, double th) {
     constexpr int L = M + 2;
     double co[L];
@@ -207,6 +208,7 @@ __device__ __forceinline__ double eval_row(const double* __restrict__ row, doubl
     for (int n = 0; n < L; n += 2) {
         double2 v;
         if constexpr (SMEM) v = *reinterpret_cast<const double2*>(row + n);
+        else if constexpr (COHERENT) v = __ldcg(reinterpret_cast<const double2*>(row + n));
         else v = __ldg(reinterpret_cast<const double2*>(row + n));
         co[n] = v.x;
         co[n + 1] = v.y;
@@ -222,13 +224,46 @@ __device__ __forceinline__ double eval_row(const double* __restrict__ row, doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// cheb_stage: the Chebyshev stage of one pset, executed by the whole CTA of traj_kernel once warp 0 has
-// integrated the trajectory (psets that finish early do this while others still integrate).  Values of F_x
-// at the D+1 Chebyshev–Gauss–Lobatto nodes from the pset's Taylor table, DCT-I → a[d][x]; effective degree;
-// count-column coefficients; fallback flag.  `sm` = this stage's shared-memory scratch.
+// Bulk-copy (TMA) helpers: one elected thread arms an mbarrier with the byte count and issues
+// cp.async.bulk global→shared; everybody waits on the barrier's phase parity.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chebyshev stage of one pset inside traj_kernel.  While warp 0 integrates, warps 1..3 (`cheb_consume`) build
+// the cosine tables and evaluate F_x at the D+1 Chebyshev–Gauss–Lobatto nodes cell by cell, as soon as warp 0
+// publishes a cell (release/acquire on a shared-memory counter; table rows are read back through L2).  After the
+// CTA barrier `cheb_finish` runs on all threads: DCT-I → a[d][x]; effective degree; count-column coefficients;
+// fallback flag.
 // ------------------------------------------------------------------------------------------------
 #ifdef GCDYN_TRAJ_TRACE
-#define TRACE_STAMP(i) do { if (threadIdx.x == 0) g_trace[i] = clock64(); } while (0)
+__device__ long long g_trace_out[1024 * 24];
+#define TRACE_STAMP(i) do { if ((threadIdx.x & 31) == 0) g_trace[i] = clock64(); } while (0)
 #define TRACE_ARG , long long* g_trace
 #define TRACE_PASS , g_trace
 #else
@@ -237,69 +272,162 @@ __device__ __forceinline__ double eval_row(const double* __restrict__ row, doubl
 #define TRACE_PASS
 #endif
 
+constexpr int CHEB_RING_SLOTS = 3;   // cells in flight between the integrating warp and the consumer warps
+constexpr int CELL_LAST = 1, CELL_FAIL = 2;   // flags of a published cell
+
+struct ChebSmem {                      // carve-up of the stage's shared-memory scratch
+    double* costab;                    // [2D]  cos(π m / D)
+    double* V;                         // [(D+1)*K] node values, later the coefficients a[d][x]
+    double* EO;                        // [2][(H+1)*K] folded node values
+    double* cosm;                      // [H+1][D+4]  cos(π k d / D), zero for d > D
+    double* sgrid;                     // [S_cap+1] τ_s as published by warp 0
+    double* shc;                       // [S_cap]   h_s
+    int* sflag;                        // [S_cap+1] CELL_LAST / CELL_FAIL of a published cell
+    double* ring;                      // [CHEB_RING_SLOTS][K*L] Taylor coefficients ĉ_0..ĉ_M of the cells in flight
+    double* rowbuf;                    // [2][K*L] table rows of the cell being evaluated at the Chebyshev nodes
+    __device__ ChebSmem(double* sm, int K, int D, int S_cap, int L) {
+        const int H = D / 2;
+        costab = sm;
+        V = costab + 2 * D;
+        if (D > 0) {
+            EO = V + ((((size_t)(D + 1) * K) + 1) & ~(size_t)1);
+            cosm = EO + 2 * (size_t)(H + 1) * K;
+            sgrid = cosm + (size_t)(H + 1) * (D + 4);
+        } else {                                        // no Chebyshev stage: only the ring and its grid/flags exist
+            EO = cosm = sgrid = sm;
+        }
+        shc = sgrid + (S_cap + 1);
+        sflag = reinterpret_cast<int*>(sgrid + 2 * S_cap + 1);
+        ring = sgrid + 2 * (S_cap + 1) + (((size_t)S_cap + 4) / 2 & ~(size_t)1);   // even offset: 16-byte aligned rows
+        rowbuf = ring + (size_t)CHEB_RING_SLOTS * K * L;
+    }
+};
+
+// The three warps that do not integrate (ct = 0..nct-1).  For every cell the integrating warp publishes (ĉ_0..ĉ_M per
+// type, τ_s, h_s) they build the table rows of F — row[0] = F(τ_s), row[1] = h(2λĉ_0 − Λ), row[n+1] = 2hλ ĉ_n/(n+1) —
+// keep the running F(τ_s) per type, write rows and grid to the table in global memory and, when the Chebyshev stage
+// is on, evaluate F_x at the Chebyshev–Gauss–Lobatto nodes inside the cell.  Node k sits at τ_k = T(1 + cos(πk/D))/2,
+// so cells (increasing τ) meet the nodes in decreasing k; a node belongs to the largest cell with τ_s ≤ τ_k
+// (find_cell's rule), the last cell takes the rest.
 template <int M>
-__device__ __forceinline__ void cheb_stage(const ParamsView& pv, const PsetPack& pk, const ChebCfg& cfg, int p,
-                                           const double* __restrict__ tab, double* __restrict__ sm TRACE_ARG) {
+__device__ __forceinline__ void cell_consume(const ParamsView& pv, const TrajCfg& tc, const ChebCfg& cfg, bool cheb, int p,
+                                             double* __restrict__ tab, const ChebSmem& cs, uint64_t* full, uint64_t* empty,
+                                             int ct, int nct) {
+    constexpr int L = M + 2;
+    constexpr int TPT = 2;                              // types per consumer thread: K ≤ 128 (KPL ≤ 4), nct = 96
+    const int K = pv.K, D = cfg.D, H = D / 2, CW = D + 4;
+    const double mu = pv.mu[p], delta = pv.delta[p];
+    const double* G = pv.Gamma + (size_t)p * pv.gamma_stride;
+    double lamx[TPT], Lamx[TPT], Fc[TPT];
+#pragma unroll
+    for (int j = 0; j < TPT; ++j) {
+        const int x = ct + j * nct;
+        lamx[j] = x < K ? birth_rate(pv, p, x) : 0.0;
+        const double gam = x < K ? delta * -G[x + (size_t)x * K] : 0.0;
+        Lamx[j] = lamx[j] + mu + gam;
+        Fc[j] = 0.0;
+    }
+    if (cheb) {
+        for (int m = ct; m < 2 * D; m += nct) cs.costab[m] = cospi((double)m / (double)D);
+        asm volatile("bar.sync 1, %0;" ::"r"(nct) : "memory");
+        for (int idx = ct; idx < (H + 1) * CW; idx += nct) {
+            const int k = idx / CW, d = idx - k * CW;
+            cs.cosm[idx] = d <= D ? cs.costab[(k * d) % (2 * D)] : 0.0;
+        }
+    }
+    double* tabp = tab + (size_t)p * tc.tab_stride;
+    double* gridp = tabp;
+    double* invhp = tabp + (tc.S_cap + 1);
+    double* rowsp = tabp + tc.grid_doubles;
+    int kn = D;
+    for (int sc = 0;; ++sc) {
+        const int slot_i = sc % CHEB_RING_SLOTS;
+        mbar_wait(full + slot_i, (uint32_t)(sc / CHEB_RING_SLOTS) & 1u);
+        const int flag = cs.sflag[sc];
+        if (flag & CELL_FAIL) {
+            if (ct == 0) gridp[sc] = tc.T;
+            break;
+        }
+        const double t0 = cs.sgrid[sc], t1 = cs.sgrid[sc + 1], hc = cs.shc[sc];
+        const double ih = 1.0 / hc;
+        const double* slot = cs.ring + (size_t)slot_i * K * L;
+        double* rb = cs.rowbuf + (size_t)(sc & 1) * K * L;
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) {
+            const int x = ct + j * nct;
+            if (x < K) {
+                double c[L], row[L];
+#pragma unroll
+                for (int n = 0; n < L; n += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(slot + (size_t)x * L + n);
+                    c[n] = v.x;
+                    c[n + 1] = v.y;
+                }
+                row[0] = Fc[j];
+                row[1] = hc * (2.0 * lamx[j] * c[0] - Lamx[j]);
+                const double h2l = 2.0 * hc * lamx[j];
+                double fs[4] = {0.0, 0.0, 0.0, 0.0};         // smallest terms first, four partial sums
+#pragma unroll
+                for (int n = M; n >= 1; --n) {
+                    row[n + 1] = (h2l * (1.0 / (double)(n + 1))) * c[n];
+                    fs[n & 3] += row[n + 1];
+                }
+                Fc[j] += ((fs[0] + fs[1]) + (fs[2] + fs[3])) + row[1];
+                double2* dst = reinterpret_cast<double2*>(rowsp + ((size_t)sc * K + x) * L);
+#pragma unroll
+                for (int n = 0; n < L; n += 2) dst[n >> 1] = make_double2(row[n], row[n + 1]);
+                if (cheb) {
+                    double2* d2 = reinterpret_cast<double2*>(rb + (size_t)x * L);
+#pragma unroll
+                    for (int n = 0; n < L; n += 2) d2[n >> 1] = make_double2(row[n], row[n + 1]);
+                }
+            }
+        }
+        mbar_arrive(empty + slot_i);                    // this thread has read what it needs from the slot
+        if (ct == 0) {
+            gridp[sc] = t0;
+            invhp[sc] = ih;
+            if (flag & CELL_LAST) gridp[sc + 1] = tc.T;
+        }
+        if (cheb) {
+            // rows of this cell are complete in rb; rb alternates, and the barrier of the next cell keeps the cell
+            // after next from overwriting rows that are still being read
+            asm volatile("bar.sync 1, %0;" ::"r"(nct) : "memory");
+            int klo = kn;                               // nodes klo+1..kn lie in this cell
+            if (flag & CELL_LAST) klo = -1;
+            else while (klo >= 0 && cfg.T * (1.0 + cs.costab[klo]) * 0.5 < t1) --klo;
+            const int nitems = (kn - klo) * K;
+            for (int it = ct; it < nitems; it += nct) {
+                const int k = kn - it / K, x = it % K;
+                const double tau = cfg.T * (1.0 + cs.costab[k]) * 0.5;
+                cs.V[k * K + x] = eval_row<M, true>(rb + (size_t)x * L, (tau - t0) * ih);
+            }
+            kn = klo;
+        }
+        if (flag & CELL_LAST) break;
+    }
+}
+
+template <int M>
+__device__ __forceinline__ void cheb_finish(const ParamsView& pv, const PsetPack& pk, const ChebCfg& cfg, int p,
+                                            const ChebSmem& cs TRACE_ARG) {
     const MomentView& mv = cfg.mv;
     double* __restrict__ A = cfg.A;
     int* __restrict__ need_sweep = cfg.need_sweep;
     int* __restrict__ d_common = cfg.d_common;
-    constexpr int L = M + 2;
     const int K = mv.K, C1 = mv.C1, D = cfg.D;
     const int H = D / 2, CW = D + 4, NV = (D + 1) * K;
-    double* costab = sm;                               // [2D]  cos(π m / D)
-    double* V = costab + 2 * D;                        // [(D+1)*K] node values, later the coefficients a[d][x]
+    double* V = cs.V;
     double* Acoef = V;
-    double* EO = V + (((size_t)NV + 1) & ~(size_t)1);  // [2][(H+1)*K] folded node values (16-byte aligned)
-    double* cosm = EO + 2 * (size_t)(H + 1) * K;       // [(H+1)][CW]  cos(π k d / D), zero for d > D
-    double* nth = cosm + (size_t)(H + 1) * CW;         // [D+1] θ of node k inside its cell
-    int* ncell = reinterpret_cast<int*>(nth + (D + 1));   // [D+1] cell of node k (2(D+1) ints reserved)
-    double* sgrid = nth + 2 * (D + 1);                 // [S+1] τ_s, then [S] 1/h_s
+    double* EO = cs.EO;
+    const double* cosm = cs.cosm;
     __shared__ int s_deff, s_flag;
-    const int S = pk.S[p];
     const int pst = pk.pstatus[p];
-    double* sinvh = sgrid + (S + 1);
     if (threadIdx.x == 0) { s_deff = 8; s_flag = (pst & ST_SOLVER) ? 1 : 0; }
-    for (int m = threadIdx.x; m < 2 * D; m += blockDim.x) costab[m] = cospi((double)m / (double)D);
-    const double* tp = tab + (size_t)p * cfg.tab_stride;
-    const double* rows = tp + cfg.grid_doubles;
-    // the pset's grid [τ_s | 1/h_s] goes to shared memory first: the cell search is then a few LDS, not L2 round trips
-    for (int i = threadIdx.x; i <= S; i += blockDim.x) sgrid[i] = tp[i];
-    for (int i = threadIdx.x; i < S; i += blockDim.x) sinvh[i] = tp[cfg.S_cap + 1 + i];
-    __syncthreads();
-    TRACE_STAMP(5);
-    // cell and in-cell coordinate of every Chebyshev–Gauss–Lobatto node (shared by the K types), and the DCT matrix
-    for (int k = threadIdx.x; k <= D; k += blockDim.x) {
-        const double tau = cfg.T * (1.0 + costab[k]) * 0.5;
-        const int c = find_cell(sgrid, S, tau);
-        ncell[k] = c;
-        nth[k] = (tau - sgrid[c]) * sinvh[c];
-    }
-    for (int idx = threadIdx.x; idx < (H + 1) * CW; idx += blockDim.x) {
-        const int k = idx / CW, d = idx - k * CW;
-        cosm[idx] = d <= D ? costab[(k * d) % (2 * D)] : 0.0;
-    }
-    __syncthreads();
-    if (!(pst & ST_SOLVER)) {
-        // four lookups in flight per thread: the table rows come from L2
-        for (int base = threadIdx.x; base < NV; base += 4 * blockDim.x) {
-            double v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = min(base + u * (int)blockDim.x, NV - 1);
-                const int k = idx / K, x = idx - k * K;
-                v[u] = eval_row<M, false>(rows + ((size_t)ncell[k] * K + x) * L, nth[k]);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = base + u * (int)blockDim.x;
-                if (idx < NV) V[idx] = v[u];
-            }
-        }
-    } else {
+    if (pst & ST_SOLVER) {                               // CTA-uniform: a failed trajectory has no usable nodes
         for (int idx = threadIdx.x; idx < NV; idx += blockDim.x) V[idx] = 0.0;
+        __syncthreads();
     }
-    __syncthreads();
     TRACE_STAMP(6);
     // DCT-I with the symmetry cos(π(D−k)d/D) = (−1)^d cos(πkd/D): fold the node values into an even and an
     // odd half, E_k = w_k (V_k + V_{D−k}), O_k = w_k (V_k − V_{D−k}), k = 0..D/2, w_0 = w_{D/2} = 1/2.
@@ -341,17 +469,38 @@ __device__ __forceinline__ void cheb_stage(const ParamsView& pv, const PsetPack&
     }
     __syncthreads();
     TRACE_STAMP(8);
-    // effective degree (a thread per type): the largest d whose tail Σ_{k≥d}|a_k| exceeds tol — the sum runs
-    // downwards from D, so it is monotone; the series counts as unresolved if its last three terms are not small
-    for (int x = threadIdx.x; x < K; x += blockDim.x) {
-        double tail = 0.0;
-        int found = 8;
-        for (int d = D; d > 8; --d) {
-            tail += fabs(Acoef[d * K + x]);
-            if (!(tail <= cfg.tol) && d > found) found = d;
-            if (d == D - 2 && !(tail <= cfg.tol)) atomicExch(&s_flag, 1);
+    // effective degree: the largest d whose tail Σ_{k≥d}|a_k| exceeds tol (the sum runs downwards from D, so it is
+    // monotone).  nparts threads share a type: chunk sums first, then each rescans its chunk on top of the chunks
+    // above it.  The series counts as unresolved if its last three terms are not small.
+    {
+        const int nparts = max(1, min((int)blockDim.x / K, 8));
+        const int span = D - 8;                               // degrees 9..D
+        const int per = (span + nparts - 1) / nparts;
+        double* part = EO;                                    // [K][nparts], EO is dead after the DCT
+        for (int w = threadIdx.x; w < K * nparts; w += blockDim.x) {
+            const int x = w / nparts, q = w - x * nparts;
+            const int hi = D - q * per, lo = max(hi - per, 8);   // this chunk: degrees lo+1..hi
+            double sum = 0.0;
+            for (int d = hi; d > lo; --d) sum += fabs(Acoef[d * K + x]);
+            part[w] = sum;
         }
-        atomicMax(&s_deff, found);
+        __syncthreads();
+        for (int w = threadIdx.x; w < K * nparts; w += blockDim.x) {
+            const int x = w / nparts, q = w - x * nparts;
+            const int hi = D - q * per, lo = max(hi - per, 8);
+            double tail = 0.0;
+            for (int r = 0; r < q; ++r) tail += part[x * nparts + r];
+            int found = 8;
+            for (int d = hi; d > lo; --d) {
+                tail += fabs(Acoef[d * K + x]);
+                if (!(tail <= cfg.tol) && d > found) found = d;
+            }
+            if (found > 8) atomicMax(&s_deff, found);
+            if (q == 0) {
+                const double last3 = fabs(Acoef[D * K + x]) + fabs(Acoef[(D - 1) * K + x]) + fabs(Acoef[(D - 2) * K + x]);
+                if (!(last3 <= cfg.tol)) atomicExch(&s_flag, 1);
+            }
+        }
     }
     __syncthreads();
     TRACE_STAMP(9);
@@ -426,11 +575,44 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
     __shared__ int g_attempts;
 #endif
     TRACE_STAMP(0);
-    // warps 1..3 compute the rates and node-term logs while warp 0 integrates (it needs neither)
-    if (threadIdx.x >= 32) prep_pset(pv, pk, p, 0, threadIdx.x - 32, TRAJ_THREADS - 32, false);
+#ifdef GCDYN_TRAJ_TRACE
+    if (threadIdx.x == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_trace[14] = gt; }
+#endif
+    __shared__ __align__(8) uint64_t s_full[CHEB_RING_SLOTS], s_empty[CHEB_RING_SLOTS];   // ring of cells → Chebyshev warps
+    const bool cheb = cc.D > 0;                         // CTA-uniform
+    const size_t traj_doubles = 2 * (size_t)(KPL == 1 ? KP : ((K + 3) & ~3)) + (KPL == 1 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
+    const ChebSmem cs(smem + traj_doubles, K, cheb ? cc.D : 0, cfg.S_cap, L);
+    // The integrating warp is chosen from the hardware warp slots so that CTAs sharing an SM integrate on different
+    // sub-partitions (two integrations on one FP64 pipe: +32 % per Taylor stage, tools/traj_micro.cu).  Slot groups
+    // of four are the usual allocation for a 4-warp CTA; any other allocation only loses the benefit.
+    __shared__ int s_wid[TRAJ_THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        unsigned wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        if (lane == 0) s_wid[warp] = (int)wid;
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < CHEB_RING_SLOTS; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, TRAJ_THREADS - 32); }
+    }
+    __syncthreads();
+    int pw = 0;
+    {
+        int lo = s_wid[0];
+#pragma unroll
+        for (int w = 1; w < TRAJ_THREADS / 32; ++w) lo = min(lo, s_wid[w]);
+        const int want = (lo >> 2) & 3;
+#pragma unroll
+        for (int w = TRAJ_THREADS / 32 - 1; w >= 0; --w) if ((s_wid[w] & 3) == want) pw = w;
+    }
+    if (warp != pw) {
+        const int ct = (warp < pw ? warp : warp - 1) * 32 + lane;
+        prep_pset(pv, pk, p, 0, ct, TRAJ_THREADS - 32, false);
+        cell_consume<M>(pv, cfg, cc, cheb, p, tab, cs, s_full, s_empty, ct, TRAJ_THREADS - 32);
+    }
     TRACE_STAMP(1);
-    if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
+    if (warp == pw) {
     const int KS = KPL == 1 ? KP : ((K + 3) & ~3);     // broadcast buffer length (multiple of 4)
     double* cb = smem;                                  // 2 × KS
     double* GT = smem + 2 * KS;                         // KPL > 1 only: GT[j*K + i] = δ Γ[i,j]
@@ -466,25 +648,29 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
     __syncwarp();
 
     const bool adaptive = cfg.S_fixed <= 0;
-    // per-pset block of the table: [τ_s, s = 0..S_cap | 1/h_s, s < S_cap | pad][rows (cell, type) of L doubles]
-    double* tabp = tab + (size_t)p * cfg.tab_stride;
-    double* gridp = tabp;
-    double* invhp = tabp + (cfg.S_cap + 1);
-    double* rowsp = tabp + cfg.grid_doubles;
-    double pcur[KPL], Fcur[KPL];
+    // (the table block of this pset — [τ_s | 1/h_s | pad][rows (cell, type) of L doubles] — is written by the consumers)
+    double pcur[KPL];
 #pragma unroll
-    for (int q = 0; q < KPL; ++q) { pcur[q] = own[q] ? 1.0 - rho : 0.0; Fcur[q] = 0.0; }   // p(0) = 1 − ρ, mbp.jl:130,141,226
+    for (int q = 0; q < KPL; ++q) pcur[q] = own[q] ? 1.0 - rho : 0.0;   // p(0) = 1 − ρ, mbp.jl:130,141,226
     // first cell width: optimistic guess from the fastest rate; the controller below corrects it
     double h = adaptive ? hrate_target_start(M) / rate : cfg.T / (double)cfg.S_fixed;
     if (!(h > 0.0) || !(h <= 0.25 * cfg.T)) h = adaptive ? 0.25 * cfg.T : cfg.T / (double)cfg.S_fixed;
     double tau = 0.0;
-    float errmax = 0.0f;
-    // tolerance seen by the controller, a hair inside the double value so float rounding can only be stricter
-    const float tol_f = (float)cfg.tol * (1.0f - 1e-6f);
+    // Step control works on the HIGH WORD of the indicator (sign, exponent, 20 mantissa bits): non-negative doubles
+    // order like their bit patterns and NaN sorts above +Inf, so one integer REDUX gives the warp maximum, the accept
+    // test is an integer compare (at most 1e-6 stricter than ind ≤ tol) and log2(ind) ≈ (hi − 0x3ff00000)/2^20
+    // (exponent plus linear mantissa, error < 0.09) is all the accuracy (tol/ind)^(1/M) needs.  Every lane sees the
+    // same value, so accept/reject decisions are warp-uniform and deterministic.
+    const unsigned tol_hi = (unsigned)__double2hiint(cfg.tol);
+    const float tol_l2 = (float)((int)tol_hi - 0x3ff00000) * (1.0f / 1048576.0f);
     const float decade = exp2f(__log2f(0.1f) * (1.0f / (float)M));      // 0.1^(1/M)
+    unsigned errmax_hi = 0u;
     bool bad = false, failed = false;
     int s = 0, rejects = 0;
     TRACE_STAMP(2);
+#ifdef GCDYN_TRAJ_TRACE
+    long long tr_a = 0, tr_b = 0, tr_c = 0, tr_t = clock64();
+#endif
     for (;;) {
         double hc = h;
         bool last = false;
@@ -559,6 +745,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
         }
 #ifdef GCDYN_TRAJ_TRACE
         if (s == 0 && rejects == 0) TRACE_STAMP(11);
+        if (s > 0) { const long long t = clock64(); tr_a += t - tr_t; tr_t = t; }
 #endif
         // error indicator of this cell: the last two Taylor terms, maximum over the pset's types
         double ind = 0.0;
@@ -567,13 +754,10 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
             const double v = fabs(c[M][q]) + fabs(c[M - 1][q]);
             if (own[q] && !(v <= ind)) ind = v;
         }
-        // Warp maximum through the float image of the indicator (one REDUX on its bit pattern; non-negative
-        // floats order like their bits and NaN sorts above +Inf).  Single precision is ample for step control,
-        // and every lane sees the same value, so accept/reject decisions are warp-uniform and deterministic.
-        const float ind_f = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fabsf((float)ind))));
-        // (tol/ind)^(1/M) in single precision: the controller needs two digits, not sixteen
-        const float ratio = exp2f(__log2f(tol_f / ind_f) * (1.0f / (float)M));
-        if (adaptive && !(ind_f <= tol_f)) {
+        const unsigned ind_hi = __reduce_max_sync(FULL, (unsigned)__double2hiint(ind));
+        const float ind_l2 = (float)((int)ind_hi - 0x3ff00000) * (1.0f / 1048576.0f);
+        const float ratio = exp2f((tol_l2 - ind_l2) * (1.0f / (float)M));     // ≈ (tol/ind)^(1/M)
+        if (adaptive && !(ind_hi < tol_hi)) {
             // reject: the indicator scales like h^M — shrink the cell accordingly and redo it
             float f = 0.9f * ratio;
             if (!(f >= 0.2f)) f = 0.2f;
@@ -585,35 +769,42 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
         if (s >= cfg.S_cap) { failed = true; break; }
 #ifdef GCDYN_TRAJ_TRACE
         if (s == 0 && rejects == 0) TRACE_STAMP(12);
+        if (s > 0) { const long long t = clock64(); tr_b += t - tr_t; tr_t = t; }
 #endif
-        // accept: emit the F polynomial of this cell, advance p and F to the next grid point
+        // accept: publish ĉ_0..ĉ_M, τ_s and h_s to the consumer warps (they build and store the table rows of F, which
+        // the integration itself never needs) and advance p to the next grid point
+        {
+            const int slot_i = s % CHEB_RING_SLOTS;
+            if (s >= CHEB_RING_SLOTS) mbar_wait(s_empty + slot_i, (uint32_t)(s / CHEB_RING_SLOTS - 1) & 1u);   // consumers left it
+            double* slot = cs.ring + (size_t)slot_i * K * L;
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) {
+                if (own[q]) {
+                    double2* dst = reinterpret_cast<double2*>(slot + (size_t)(lane + 32 * q) * L);
+#pragma unroll
+                    for (int n = 0; n < M; n += 2) dst[n >> 1] = make_double2(c[n][q], c[n + 1][q]);
+                    dst[M >> 1] = make_double2(c[M][q], 0.0);
+                }
+            }
+            if (lane == 0) {
+                cs.sgrid[s] = tau; cs.sgrid[s + 1] = last ? cfg.T : tau + hc; cs.shc[s] = hc;
+                cs.sflag[s] = last ? CELL_LAST : 0;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_full + slot_i);
+        }
 #pragma unroll
         for (int q = 0; q < KPL; ++q) {
-            const int i = lane + 32 * q;
-            double row[L];
-            row[0] = Fcur[q];
-            row[1] = hc * (2.0 * lam[q] * c[0][q] - Lam[q]);
-            const double h2l = 2.0 * hc * lam[q];
-            double psum = 0.0, fsum = 0.0;
+            double ps[4] = {0.0, 0.0, 0.0, 0.0};             // Σ_{n≥1} ĉ_n, smallest terms first, four partial sums
 #pragma unroll
-            for (int n = M; n >= 1; --n) {
-                row[n + 1] = (h2l * (1.0 / (double)(n + 1))) * c[n][q];
-                fsum += row[n + 1];
-                psum += c[n][q];
-            }
-            if (own[q]) {
-                double2* dst = reinterpret_cast<double2*>(rowsp + ((size_t)s * K + i) * L);
-#pragma unroll
-                for (int n = 0; n < L; n += 2) dst[n >> 1] = make_double2(row[n], row[n + 1]);
-            }
-            Fcur[q] += fsum + row[1];
-            pcur[q] = psum + c[0][q];
+            for (int n = M; n >= 1; --n) ps[n & 3] += c[n][q];
+            pcur[q] = ((ps[0] + ps[1]) + (ps[2] + ps[3])) + c[0][q];
             if (own[q] && !(pcur[q] >= -1e-9 && pcur[q] <= 1.0 + 1e-9)) bad = true;   // isoutofdomain, mbp.jl:146,204,231
         }
-        if (lane == 0) { gridp[s] = tau; invhp[s] = 1.0 / hc; }
-        if (!(ind_f <= errmax)) errmax = ind_f;
+        if (ind_hi > errmax_hi) errmax_hi = ind_hi;
 #ifdef GCDYN_TRAJ_TRACE
         if (s == 0 && rejects == 0) TRACE_STAMP(13);
+        { const long long t = clock64(); if (s > 0) tr_c += t - tr_t; tr_t = t; }
 #endif
         ++s;
         if (last) break;
@@ -626,10 +817,14 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
             h = hc * (double)f;
         }
     }
-    if (lane == 0) gridp[s] = cfg.T;
+    if (failed) {                                       // tell the consumers to stop (the regular exit flagged its last cell)
+        const int slot_i = s % CHEB_RING_SLOTS;
+        if (s >= CHEB_RING_SLOTS) mbar_wait(s_empty + slot_i, (uint32_t)(s / CHEB_RING_SLOTS - 1) & 1u);
+        if (lane == 0) { cs.sflag[s] = CELL_FAIL; mbar_arrive(s_full + slot_i); }
+    }
     TRACE_STAMP(3);
 #ifdef GCDYN_TRAJ_TRACE
-    if (lane == 0) g_attempts = s + rejects;
+    if (lane == 0) { g_attempts = s + rejects; g_trace[1] = tr_a; g_trace[5] = tr_b; g_trace[11] = tr_c; }
 #endif
     // conditioning term and diagnostics
 #pragma unroll
@@ -637,58 +832,29 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
         const int i = lane + 32 * q;
         if (own[q]) pk.logcond[(size_t)p * K + i] = log1p(-pcur[q]);   // log(1 − p_i(T)), mbp.jl:244-245
     }
-    const bool unresolved = failed || !(errmax <= tol_f);
+    const bool unresolved = failed || !(errmax_hi < tol_hi);
     const bool anybad = __any_sync(FULL, bad) || unresolved;
     if (lane == 0) {
-        pk.perr[p] = (double)errmax;
+        pk.perr[p] = __hiloint2double((int)min(errmax_hi + 1u, 0x7ff00000u), 0);   // upper bound of the largest accepted indicator
         pk.S[p] = s > 0 ? s : 1;
         pk.pstatus[p] = anybad ? ST_SOLVER : 0;
     }
     }   // warp 0
-    if (cc.D <= 0) return;                              // CTA-uniform
-    __syncthreads();                                    // table, grid, status of this pset are complete and visible
+    if (!cheb) return;
+    __syncthreads();                                    // node values, status of this pset are complete and visible
     TRACE_STAMP(4);
-    const size_t traj_doubles = 2 * (size_t)(KPL == 1 ? KP : ((K + 3) & ~3)) + (KPL == 1 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
-    cheb_stage<M>(pv, pk, cc, p, tab, smem + traj_doubles TRACE_PASS);
+    cheb_finish<M>(pv, pk, cc, p, cs TRACE_PASS);
 #ifdef GCDYN_TRAJ_TRACE
-    if (threadIdx.x == 0 && (p == 0 || p == 100 || p == 120 || p == 255)) {
+    __syncthreads();
+    if (threadIdx.x == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_trace[15] = gt; }
+    if (threadIdx.x == 0 && p < 1024) {
         unsigned smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
-        printf("TRACE sm=%u cell0: orders=%lld ctrl=%lld accept=%lld\n", smid, g_trace[11] - g_trace[2], g_trace[12] - g_trace[11], g_trace[13] - g_trace[12]);
-        printf("TRACE p=%d S=%d attempts=%d prep=%lld setup=%lld integ=%lld fin=%lld | grid=%lld V=%lld fold=%lld dct=%lld deff=%lld write=%lld\n",
-               p, pk.S[p], g_attempts, g_trace[1] - g_trace[0], g_trace[2] - g_trace[1], g_trace[3] - g_trace[2],
-               g_trace[4] - g_trace[3], g_trace[5] - g_trace[4], g_trace[6] - g_trace[5], g_trace[7] - g_trace[6],
-               g_trace[8] - g_trace[7], g_trace[9] - g_trace[8], g_trace[10] - g_trace[9]);
+        long long* o = g_trace_out + (size_t)p * 24;
+        for (int i = 0; i < 16; ++i) o[i] = g_trace[i];
+        o[16] = smid; o[17] = pw; o[18] = pk.S[p]; o[19] = g_attempts; o[20] = s_wid[0]; o[21] = s_wid[1]; o[22] = s_wid[2]; o[23] = s_wid[3];
     }
 #endif
-}
-
-// ------------------------------------------------------------------------------------------------
-// Bulk-copy (TMA) helpers: one elected thread arms an mbarrier with the byte count and issues
-// cp.async.bulk global→shared; everybody waits on the barrier's phase parity.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra.uni WAIT_DONE;\n\t"
-        "bra.uni WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 
 template <int M, bool SMEM>

@@ -6,7 +6,7 @@
 template <int M, int KP, int V>
 __global__ void cell_loop(double* out, long long* cyc, int cells, double hc, double lamv, double av, double bv, double gv) {
     __shared__ __align__(16) double cb[2 * KP];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const bool own = lane < KP;
     double g[KP];
 #pragma unroll
@@ -15,6 +15,7 @@ __global__ void cell_loop(double* out, long long* cyc, int cells, double hc, dou
     for (int e = lane; e < 2 * KP; e += 32) cb[e] = 0.0;
     __syncwarp();
     double pcur = own ? 0.5 : 0.0;
+    if (blockDim.x == 160 && (threadIdx.x >> 5) != 0 && (threadIdx.x >> 5) != 4) return;   // warps 0 and 4 only: same sub-partition
     const long long t0 = clock64();
     for (int s = 0; s < cells; ++s) {
         double c[M + 1];
@@ -140,6 +141,7 @@ int main() {
         run<6>("V6 V5 + off-path combine + tree psum", out, cyc, 1, 32);
         run<0>("V0 two warps same CTA", out, cyc, 1, 64);
         run<0>("V0 256 CTAs", out, cyc, 256, 32);
+        run<0>("V0 warps 0 and 4 (one sub-partition)", out, cyc, 1, 160);
     }
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
