@@ -291,7 +291,7 @@ def run_gpu(args):
     n_par_doubles = sum(int(np.size(a)) for a in (params.lam, params.mu, params.delta, params.rho, params.sigma, params.Gamma)
                         if a is not None)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_par_doubles,
-           "d2h_bytes_per_step": P * (8 + 8 + 4), "ms_per_step": 1e3 * float(te.item()) / args.steps,
+           "d2h_bytes_per_step": P * 8, "ms_per_step": 1e3 * float(te.item()) / args.steps,
            "api": "gcdyn_loglik_batch (host buffers; forest handle created once per dataset, as a sampler would)"}
     if world > 1:
         assert np.allclose(o, result, rtol=1e-12, atol=0)

@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A,
     const int64_t t0 = (int64_t)blockIdx.x * GT_TILE;
     const long long Jst = mv.Jst;
     const double* Mt = mv.Mt;
+    pdl_wait();                                            // A, d_common come from the trajectory kernel
+    pdl_launch_dependents();
     // segment 1: count columns + Chebyshev columns up to the batch's effective degree; segment 2: K² block
     long long J1 = mv.C1 + (long long)(*d_common + 1) * mv.K;
     J1 = (J1 + 3) & ~3LL;
@@ -296,6 +298,12 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, PsetPack pk,
     const int p = blockIdx.x;
     const int K = fv.K;
     const int64_t T = fv.n_trees;
+    pdl_wait();                                            // partial sums come from the contraction
+    if (blockIdx.x == 0 && threadIdx.x == 0) {             // leave d_common zeroed for the next evaluation
+        int* dc = const_cast<int*>(need_sweep) + P;
+        dc[1] = dc[0];
+        dc[0] = 0;
+    }
     const int pst = pk.pstatus[p];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     double* orow = out_tree + (size_t)p * T;

@@ -62,6 +62,7 @@ struct gcdyn_ctx {
     // workspace (grow-only)
     DevBuf params_blob, pack, table, out_tree, out_pset, status, probe, gemm_a, flags, partial;
     PinBuf pin_in, pin_out;
+    const int* dcommon_clean = nullptr;   // the d_common slot finish_kernel has left zeroed (see enqueue_eval)
     // diagnostics of the last evaluation
     int last_steps = 0, last_order = 0, last_launches = 0, last_P = 0;
     PsetPack last_pack{};
@@ -407,13 +408,29 @@ int ensure_moments(gcdyn_ctx* ctx, const gcdyn_forest* f, double T, cudaStream_t
     return GCDYN_OK;
 }
 
+// Launch configuration with programmatic stream serialization: the kernel may become resident while its predecessor
+// in the stream is still running; it calls pdl_wait() before touching the predecessor's output.
+thread_local cudaLaunchAttribute g_pdl_attr[1];
+cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    g_pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    g_pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = grid;
+    lc.blockDim = block;
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    lc.attrs = g_pdl_attr;
+    lc.numAttrs = 1;
+    return lc;
+}
+
 template <int M>
 int launch_finish_m(gcdyn_ctx* ctx, const gcdyn_forest* f, const PsetPack& pk, const double* tab, const TrajCfg& cfg, double T,
                     const double* partial, int splits, const double* tree_const, const int* need_sweep, int P,
                     double* out_tree, int32_t* status, double* out_pset, cudaStream_t st) {
-    finish_kernel<M><<<P, 256, 0, st>>>(f->v, pk, tab, cfg.tab_stride, cfg.S_cap, cfg.grid_doubles, T, partial, splits,
-                                        tree_const, need_sweep, P, out_tree, status, out_pset);
-    CU_TRY(ctx, cudaGetLastError());
+    cudaLaunchConfig_t lc = pdl_config(dim3((unsigned)P), dim3(256), 0, st);
+    CU_TRY(ctx, cudaLaunchKernelEx(&lc, finish_kernel<M>, f->v, pk, tab, cfg.tab_stride, cfg.S_cap, cfg.grid_doubles, T, partial,
+                                   splits, tree_const, need_sweep, P, out_tree, status, out_pset));
     return GCDYN_OK;
 }
 
@@ -473,10 +490,13 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             rc = ensure_moments(ctx, f, T, st, &launches);
             if (rc) return rc;
             CU_TRY(ctx, ctx->gemm_a.ensure((size_t)P * (size_t)f->mom.Jst * 8));
-            CU_TRY(ctx, ctx->flags.ensure((size_t)(P + 1) * 4));
+            // flags: [need_sweep P][d_common][d_common of the last finished evaluation]; finish_kernel leaves d_common
+            // zeroed for the next call, so the memset is only needed when the slot moved or a call failed midway
+            CU_TRY(ctx, ctx->flags.ensure((size_t)(P + 2) * 4));
             need_sweep = ctx->flags.as<int>();
             d_common = need_sweep + P;
-            CU_TRY(ctx, cudaMemsetAsync(d_common, 0, 4, st));
+            if (ctx->dcommon_clean != d_common) CU_TRY(ctx, cudaMemsetAsync(d_common, 0, 4, st));
+            ctx->dcommon_clean = nullptr;
             cc.T = T;
             cc.tol = 1e-11;
             cc.tab_stride = cfg.tab_stride;
@@ -523,14 +543,17 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             const int splits = tiles >= 4LL * ctx->sm_count ? 1 : (tiles >= 2LL * ctx->sm_count ? 2 : 4);
             grid.z = (unsigned)splits;
             CU_TRY(ctx, ctx->partial.ensure((size_t)splits * P * (size_t)Tn * 8));
-            gemm_kernel<<<grid, 128, GT_SMEM_BYTES, st>>>(ctx->gemm_a.as<double>(), mv, cc.compact_tc ? 0 : 1, d_common, P, Tn,
-                                                          ctx->partial.as<double>());
-            CU_TRY(ctx, cudaGetLastError());
+            {
+                cudaLaunchConfig_t lc = pdl_config(grid, dim3(128), GT_SMEM_BYTES, st);
+                CU_TRY(ctx, cudaLaunchKernelEx(&lc, gemm_kernel, (const double*)ctx->gemm_a.as<double>(), mv, cc.compact_tc ? 0 : 1,
+                                               (const int*)d_common, P, (int64_t)Tn, ctx->partial.as<double>()));
+            }
             ++launches;
             if (prof) { cudaEventRecord(ctx->ev[4], st); cudaEventRecord(ctx->ev[5], st); }
             rc = launch_finish(ctx, M, f, pk, ctx->table.as<double>(), cfg, T, ctx->partial.as<double>(), splits, tree_const,
                                need_sweep, P, d_out_tree, d_status, d_out_pset, st);
             if (rc) return rc;
+            ctx->dcommon_clean = d_common;
             ++launches;
             if (prof) { cudaEventRecord(ctx->ev[6], st); ctx->ev_valid = true; }
             ctx->last_cheb_D = cc.D;
@@ -756,19 +779,18 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
     const ParamsView pv = view_of(pr, L, ctx->params_blob.as<double>());
 
     const bool want_rows = out_tree_pset || status;
-    CU_TRY(ctx, ctx->out_pset.ensure((size_t)P * 8));
     if (status) CU_TRY(ctx, ctx->status.ensure((size_t)P * Tn * 4));
-    // pinned result staging
+    // the per-pset sums are written by the last kernel straight into pinned host memory (device-accessible under
+    // unified addressing): no device→host copy node for the 8·P bytes a sampler waits on
     CU_TRY(ctx, ctx->pin_out.ensure((size_t)P * 8 + 64));
     double* h_out = reinterpret_cast<double*>(ctx->pin_out.p);
 
     // one pass: every pset adapts its own step count inside traj_kernel (or uses opts->steps as given);
     // a pset that cannot be resolved within the table capacity comes back as a solver failure (-Inf)
     rc = enqueue_eval(ctx, f, pv, rate_max_of(pr), T, method, M, o.steps, tol, o.flags,
-                      pr->gamma_pset_stride == 0 ? pr->Gamma : nullptr, ctx->out_pset.as<double>(), nullptr,
+                      pr->gamma_pset_stride == 0 ? pr->Gamma : nullptr, h_out, nullptr,
                       status ? ctx->status.as<int32_t>() : nullptr, st, nullptr);
     if (rc) return rc;
-    CU_TRY(ctx, cudaMemcpyAsync(h_out, ctx->out_pset.p, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
     if (want_rows) {
         if (out_tree_pset)
             CU_TRY(ctx, cudaMemcpyAsync(out_tree_pset, ctx->out_tree.p, (size_t)P * Tn * 8, cudaMemcpyDeviceToHost, st));
@@ -981,11 +1003,11 @@ int gcdyn_last_cheb_degree(gcdyn_ctx* ctx, int32_t* interp_degree, int32_t* effe
     if (!ctx) return fail(ctx, GCDYN_EINVAL, "ctx is NULL");
     if (interp_degree) *interp_degree = ctx->last_cheb_D;
     if ((effective_degree || n_fallback) && ctx->last_cheb_D > 0 && ctx->flags.p && ctx->last_P > 0) {
-        std::vector<int> h(ctx->last_P + 1);
+        std::vector<int> h(ctx->last_P + 2);
         CU_TRY(ctx, cudaSetDevice(ctx->device));
         CU_TRY(ctx, cudaDeviceSynchronize());
-        CU_TRY(ctx, cudaMemcpy(h.data(), ctx->flags.p, (size_t)(ctx->last_P + 1) * 4, cudaMemcpyDeviceToHost));
-        if (effective_degree) *effective_degree = h[ctx->last_P];
+        CU_TRY(ctx, cudaMemcpy(h.data(), ctx->flags.p, (size_t)(ctx->last_P + 2) * 4, cudaMemcpyDeviceToHost));
+        if (effective_degree) *effective_degree = h[ctx->last_P + 1];
         if (n_fallback) { int n = 0; for (int p = 0; p < ctx->last_P; ++p) n += h[p] != 0; *n_fallback = n; }
     } else {
         if (effective_degree) *effective_degree = 0;

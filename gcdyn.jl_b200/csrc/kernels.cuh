@@ -229,6 +229,12 @@ __device__ __forceinline__ double eval_row(const double* __restrict__ row, doubl
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Programmatic dependent launch: a kernel launched with the stream-serialization attribute may become resident while
+// its predecessor still runs; pdl_wait() blocks until the predecessor has completed and its writes are visible,
+// pdl_launch_dependents() lets the successor start becoming resident.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -597,6 +603,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
         for (int i = 0; i < CHEB_RING_SLOTS; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, TRAJ_THREADS - 32); }
     }
     __syncthreads();
+    pdl_launch_dependents();                            // the contraction's CTAs may become resident behind this grid
     int pw = 0;
     {
         int lo = s_wid[0];
