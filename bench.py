@@ -100,7 +100,16 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------- CPU arm
 
-def cpu_reference_rate(flat, par, T, n_trees, n_psets, nthreads=0):
+def host_threads():
+    """Host threads the CPU arm may use: the process's affinity set (torchrun pins OMP_NUM_THREADS to 1, which
+    would otherwise silently turn the reference arm into a single-thread run)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_reference_rate(flat, par, T, n_trees, n_psets, nthreads=None):
     """Time oracle/refcpu.c (reference algorithm as written, reltol = abstol = 1e-3 like the reference's
     defaults) on the first `n_trees` trees × first `n_psets` parameter sets.  Returns (pairs/s, seconds)."""
     import refcpu
@@ -108,14 +117,13 @@ def cpu_reference_rate(flat, par, T, n_trees, n_psets, nthreads=0):
     sub = subset_flat(flat, np.arange(n_trees))
     sp = {k: (v[:n_psets] if k != "Gamma" else v[:n_psets]) for k, v in par.items()}
     t0 = time.perf_counter()
-    refcpu.loglik(sub, sp, T, rtol=1e-3, atol=1e-3, nthreads=nthreads)
+    refcpu.loglik(sub, sp, T, rtol=1e-3, atol=1e-3, nthreads=nthreads or host_threads())
     dt = time.perf_counter() - t0
     return n_trees * n_psets / dt, dt
 
 
 def cpu_baseline(flat, par, T, budget_s=12.0):
-    import refcpu
-    cores = refcpu.max_threads()
+    cores = host_threads()
     n_trees = min(flat.n_trees, 64)
     n_psets = min(par["lam"].shape[0], 4)
     rate, dt = cpu_reference_rate(flat, par, T, n_trees, n_psets)
@@ -143,8 +151,7 @@ def run_reference(args):
     c = workloads.CONFIGS[WORKLOAD]
     flat = workloads.flat_forest(WORKLOAD, 0, args.trees)
     par = workloads.par_dict(workloads.jittered_models(WORKLOAD, args.psets))
-    import refcpu
-    cores = refcpu.max_threads()
+    cores = host_threads()
     # bounded sample per step: sized from a probe so that (warmup + steps) stay within a few minutes
     n_trees, n_psets = min(flat.n_trees, 64), min(args.psets, 4)
     rate, dt = cpu_reference_rate(flat, par, c["T"], n_trees, n_psets)
