@@ -229,10 +229,29 @@ def run_gpu(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
 
+    # multi-GPU: the [P] partial sums are combined by one peer-memory kernel per rank (gcdyn_comm_*, NVLink P2P
+    # stores + sequence flags); NCCL stays as the fallback when the windows cannot be mapped (no P2P between the GPUs)
+    peer, allreduce_kind = None, "none"
+    if world > 1:
+        from gcdyn.sharding import PeerAllReduce
+        ok = 1
+        try:
+            peer = PeerAllReduce(ctx, P)
+        except Exception as e:          # noqa: BLE001 - any failure on any rank -> everybody uses NCCL
+            print(f"[bench] rank {rank}: peer all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            peer = None
+        allreduce_kind = "peer-memory kernel (gcdyn_comm_allreduce)" if peer else "nccl"
+
     def step_resident():
         evaluate_resident(forest, dpar, T, out.data_ptr(), out_tree.data_ptr(), 0, stream.cuda_stream,
                           steps=args.taylor_steps, order=args.order)
-        if world > 1:
+        if peer is not None:
+            peer.allreduce(out.data_ptr(), P, stream.cuda_stream)
+        elif world > 1:
             dist.all_reduce(out)
 
     def barrier():
@@ -288,7 +307,10 @@ def run_gpu(args):
         o, _, _ = evaluate(forest, params, T, steps=args.taylor_steps, order=args.order, want_status=False)
         if world > 1:
             t = torch.from_numpy(o).cuda()
-            dist.all_reduce(t)
+            if peer is not None:
+                peer.allreduce(t.data_ptr(), P, stream.cuda_stream)
+            else:
+                dist.all_reduce(t)
             o = t.cpu().numpy()
         e2e_s += time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -378,8 +400,10 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(WORKLOAD, Tn, P, world, {
                 "nodes_per_gpu": info["n_nodes"], "lookup_items_per_gpu": n_items, "taylor_steps": S,
-                "taylor_order": M, "max_err_indicator": float(np.max(diag["err_indicator"]))}),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+                "taylor_order": M, "max_err_indicator": float(np.max(diag["err_indicator"])),
+                "allreduce": allreduce_kind}),
+            "clocks": clocks, "e2e": e2e,
+            "gpu_launches": (launches_per_step + (1 if peer is not None else 0)) * args.steps,
             "roofline": roofline, "parity": parity}
     if cpu:
         line["cpu_baseline"] = cpu

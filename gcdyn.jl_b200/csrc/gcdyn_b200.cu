@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "cheb_gemm.cuh"
 #include "simulator.h"
+#include "peer_allreduce.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1165,6 +1166,99 @@ int gcdyn_probe_fp64_peak(gcdyn_ctx* ctx, double* tflops) {
 }
 
 }  // extern "C"
+
+// ---- peer all-reduce (multi-GPU) ---------------------------------------------------------------------------
+struct gcdyn_comm {
+    gcdyn_ctx* ctx = nullptr;
+    int rank = 0, world = 1, cap = 0;
+    void* window = nullptr;               // this rank's allocation: data then flags
+    void* peer[gcdyn::PEER_MAX_WORLD] = {};   // peers' windows as mapped here (peer[rank] == window)
+    bool connected = false;
+    unsigned long long seq = 0;
+};
+
+namespace {
+size_t comm_data_bytes(int world, int cap) { return (size_t)2 * world * cap * sizeof(double); }
+}
+
+extern "C" int gcdyn_comm_create(gcdyn_ctx* ctx, int32_t rank, int32_t world, int32_t max_psets, void* handle_out,
+                                 gcdyn_comm** out) {
+    GUARD_BEGIN
+    if (!ctx || !out || !handle_out) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    *out = nullptr;
+    if (world < 1 || world > gcdyn::PEER_MAX_WORLD || rank < 0 || rank >= world || max_psets < 1)
+        return fail(ctx, GCDYN_EINVAL, "bad rank/world/max_psets (world <= 16)");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    gcdyn_comm* c = new gcdyn_comm();
+    c->ctx = ctx; c->rank = rank; c->world = world; c->cap = (max_psets + 1) & ~1;
+    const size_t bytes = comm_data_bytes(world, c->cap) + (size_t)world * sizeof(unsigned long long);
+    cudaError_t e = cudaMalloc(&c->window, bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->window, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h{};
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->window);
+    if (e != cudaSuccess) {
+        if (c->window) cudaFree(c->window);
+        delete c;
+        return fail(ctx, GCDYN_ECUDA, cudaGetErrorString(e));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handle_out, &h, 64);
+    c->peer[rank] = c->window;
+    *out = c;
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+extern "C" int gcdyn_comm_connect(gcdyn_comm* c, const void* handles) {
+    gcdyn_ctx* ctx = c ? c->ctx : nullptr;
+    GUARD_BEGIN
+    if (!c || !handles) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank || c->peer[r]) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char*>(handles) + (size_t)r * 64, 64);
+        CU_TRY(ctx, cudaIpcOpenMemHandle(&c->peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->connected = true;
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+extern "C" int gcdyn_comm_allreduce(gcdyn_comm* c, double* d_inout, int32_t n_psets, void* stream) {
+    gcdyn_ctx* ctx = c ? c->ctx : nullptr;
+    GUARD_BEGIN
+    if (!c || !d_inout) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    if (!c->connected && c->world > 1) return fail(ctx, GCDYN_EINVAL, "gcdyn_comm_connect has not been called");
+    if (n_psets < 1 || n_psets > c->cap) return fail(ctx, GCDYN_EINVAL, "n_psets exceeds the window capacity");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    gcdyn::PeerView pv{};
+    pv.rank = c->rank; pv.world = c->world; pv.cap = c->cap;
+    for (int r = 0; r < c->world; ++r) {
+        pv.win[r].data = static_cast<double*>(c->peer[r]);
+        pv.win[r].flag = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->peer[r]) + comm_data_bytes(c->world, c->cap));
+    }
+    ++c->seq;
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    cudaLaunchConfig_t lc = pdl_config(dim3(1), dim3(1024), 0, st);
+    CU_TRY(ctx, cudaLaunchKernelEx(&lc, gcdyn::peer_allreduce_kernel, pv, d_inout, (int)n_psets, c->seq));
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+extern "C" void gcdyn_comm_destroy(gcdyn_comm* c) {
+    if (!c) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(c->ctx->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; ++r)
+        if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    if (c->window) cudaFree(c->window);
+    cudaSetDevice(prev);
+    delete c;
+}
 
 #ifdef GCDYN_TRAJ_TRACE
 extern "C" int gcdyn_trace_dump(long long* out) {

@@ -1,0 +1,66 @@
+// Peer all-reduce of the per-pset sums over NVLink peer memory (the multi-GPU form of the plain
+// `sum` over trees at src/multitype_branching_process.jl:258 when the trees are sharded over GPUs).
+//
+// Every rank owns a window in its own HBM, mapped into every peer through CUDA IPC:
+//     data[2 parities][world slots][cap doubles]   flag[world] (u64 sequence numbers)
+// One kernel per evaluation and rank: (1) store this rank's [P] sums into slot `rank` of EVERY peer's window
+// (P2P stores over NVLink/NVSwitch), fence, then publish the call's sequence number in every peer's flag[rank];
+// (2) wait until all `world` flags of the local window carry that sequence number; (3) sum the slots in rank
+// order.  Every rank adds the same numbers in the same order, so all ranks hold bit-identical results.
+// The parity alternates per call: a rank can be at most one call ahead of its slowest peer (it needs that
+// peer's flag for the current call before it can start the next), so the slots of call n+2 never overwrite
+// slots of call n that are still being read.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gcdyn {
+
+struct PeerWindow {
+    double* data;                  // [2][world][cap]
+    unsigned long long* flag;      // [world]
+};
+
+constexpr int PEER_MAX_WORLD = 16;
+
+struct PeerView {
+    PeerWindow win[PEER_MAX_WORLD];    // win[r] = rank r's window as mapped in this process (win[rank] is local)
+    int rank, world, cap;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One CTA.  `inout` = this rank's [P] partial sums on entry, the all-reduced sums on exit.
+__global__ void __launch_bounds__(1024) peer_allreduce_kernel(PeerView pv, double* __restrict__ inout, int P,
+                                                              unsigned long long seq) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // launched behind finish_kernel with programmatic serialization
+    const int par = (int)(seq & 1ULL);
+    const size_t slot = ((size_t)par * pv.world + pv.rank) * pv.cap;
+    for (int i = threadIdx.x; i < P * pv.world; i += blockDim.x) {
+        const int r = i / P, p = i - r * P;
+        pv.win[r].data[slot + p] = inout[p];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < pv.world) st_release_sys(pv.win[threadIdx.x].flag + pv.rank, seq);
+    if (threadIdx.x < pv.world) {
+        const unsigned long long* f = pv.win[pv.rank].flag + threadIdx.x;
+        while (ld_acquire_sys(f) < seq) __nanosleep(100);
+    }
+    __syncthreads();
+    const double* local = pv.win[pv.rank].data + (size_t)par * pv.world * pv.cap;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < pv.world; ++r) s += __ldcg(local + (size_t)r * pv.cap + p);
+        inout[p] = s;
+    }
+}
+
+}  // namespace gcdyn

@@ -118,6 +118,10 @@ def _lib():
         "gcdyn_sim_destroy": (None, [vp]),
         "gcdyn_set_profiling": (C.c_int, [vp, C.c_int]),
         "gcdyn_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "gcdyn_comm_create": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, vp, C.POINTER(vp)]),
+        "gcdyn_comm_connect": (C.c_int, [vp, vp]),
+        "gcdyn_comm_allreduce": (C.c_int, [vp, vp, C.c_int32, vp]),
+        "gcdyn_comm_destroy": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)       # AttributeError here = header and library out of sync

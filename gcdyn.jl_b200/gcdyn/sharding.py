@@ -77,3 +77,46 @@ def allreduce_sum(tensor_or_array, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(tensor_or_array, op=dist.ReduceOp.SUM, group=group)
     return tensor_or_array
+
+
+class PeerAllReduce:
+    """`gcdyn_comm_*`: all-reduce of the `[P]` per-pset sums with one kernel per rank over NVLink peer memory
+    (P2P stores into every peer's window + sequence flags) instead of a library collective.  One process per
+    GPU; the 64-byte CUDA IPC handles are exchanged once through `torch.distributed` (any backend).  Every
+    rank ends with bit-identical sums.  Collective: every rank calls `allreduce` the same number of times."""
+
+    def __init__(self, ctx, max_psets, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        from .likelihood import _lib, _check
+        self._lib, self._check, self.ctx = _lib(), _check, ctx
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        handle = C.create_string_buffer(64)
+        h = C.c_void_p()
+        _check(self._lib.gcdyn_comm_create(ctx._h, self.rank, self.world, int(max_psets), handle, C.byref(h)), ctx._h)
+        self._h = h
+        if self.world > 1:
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, handle.raw, group=group)
+            blob = C.create_string_buffer(b"".join(gathered), 64 * self.world)
+            _check(self._lib.gcdyn_comm_connect(self._h, blob), ctx._h)
+            dist.barrier(group)        # every window is mapped everywhere before the first store
+
+    def allreduce(self, d_inout, n_psets, stream=0):
+        """Enqueue on `stream` (raw cudaStream_t, 0 = the context's stream): `d_inout` (raw device address of
+        `[n_psets]` doubles) is summed over the ranks in place."""
+        import ctypes as C
+        self._check(self._lib.gcdyn_comm_allreduce(self._h, C.c_void_p(d_inout), int(n_psets), C.c_void_p(stream or None)),
+                    self.ctx._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gcdyn_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

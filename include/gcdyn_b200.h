@@ -200,6 +200,24 @@ int  gcdyn_last_kernel_ms(gcdyn_ctx* ctx, float* ms);
  * register-resident DFMA loop on every SM and returns achieved TFLOP/s. */
 int  gcdyn_probe_fp64_peak(gcdyn_ctx* ctx, double* tflops);
 
+/* ---- multi-GPU: peer all-reduce of the [P] per-pset sums ---------------------------------
+ * With the trees sharded over GPUs (one process per GPU), the plain sum over trees of
+ * src/multitype_branching_process.jl:258 becomes a sum over ranks of [P] doubles.  These entry points do
+ * it with ONE kernel per rank over NVLink peer memory (P2P stores into every peer's window + sequence
+ * flags) instead of a library collective; every rank ends with bit-identical sums.
+ *   gcdyn_comm_create   allocates this rank's window (max_psets doubles per slot) and returns its 64-byte
+ *                       CUDA IPC handle in `handle_out`;
+ *   gcdyn_comm_connect  takes the `world` handles (64 bytes each, rank order; exchanged by the host, e.g.
+ *                       torch.distributed / MPI all-gather) and maps the peers' windows;
+ *   gcdyn_comm_allreduce enqueues the kernel on `stream`: `d_inout[P]` (device) is summed over ranks in
+ *                       place.  Collective: every rank must call it the same number of times. */
+typedef struct gcdyn_comm gcdyn_comm;
+int  gcdyn_comm_create(gcdyn_ctx* ctx, int32_t rank, int32_t world, int32_t max_psets, void* handle_out,
+                       gcdyn_comm** out);
+int  gcdyn_comm_connect(gcdyn_comm* comm, const void* handles);
+int  gcdyn_comm_allreduce(gcdyn_comm* comm, double* d_inout, int32_t n_psets, void* stream);
+void gcdyn_comm_destroy(gcdyn_comm* comm);
+
 #ifdef __cplusplus
 }
 #endif
