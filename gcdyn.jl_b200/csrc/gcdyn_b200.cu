@@ -212,7 +212,7 @@ double rate_max_of(const gcdyn_params* pr) {
             // off-diagonal mass also bounds the spectrum of δΓ; use |λ| + |μ| + 2|γ_i|
             const double g = std::fabs(pr->delta[p] * G[i + (size_t)i * K]);
             const double r = std::fabs(lam) + std::fabs(pr->mu[p]) + 2.0 * g;
-            if (r > best || r != r) best = r;
+            if (std::isfinite(r) && r > best) best = r;   // a pset with non-finite rates fails on its own; it must not size the others' tables
         }
     }
     return best;

@@ -318,3 +318,25 @@ def test_shards_sum_to_the_whole(ctx):
         parts = [gcdyn.Forest(s, None, T, ctx=ctx) for s in shard_flat(flat, R)]
         total = sum(evaluate(p, params, T)[0] for p in parts)
         assert rel(total, out_w) <= 1e-13
+
+
+@pytest.mark.gpu
+def test_failed_trajectory_in_a_gemm_batch_does_not_stall_the_other_warps(ctx):
+    """A pset whose step controller gives up (NaN rate: every cell is rejected) must release the three consumer
+    warps of its CTA (CELL_FAIL through the ring) and come back as a solver failure; its neighbours in the same
+    GEMM batch are untouched."""
+    flat, params, T, exp, _ = load_golden("g2_config2")
+    forest = gcdyn.Forest(flat, None, T, ctx=ctx)
+    tiled = _tile(params, 9)
+    good, _, st0 = evaluate(forest, tiled, T, per_tree=True)
+    assert not st0.any()
+    bad = _tile(params, 9)
+    bad.mu = bad.mu.copy()
+    bad.mu[4] = np.nan
+    out, tp, st = evaluate(forest, bad, T, per_tree=True)
+    assert np.all(st[4] & 2) and np.all(np.isneginf(tp[4])) and np.isneginf(out[4])
+    keep = np.arange(9) != 4
+    assert np.array_equal(out[keep], good[keep]) and not st[keep].any()
+    # the same through the item sweep (no Chebyshev stage: the consumers only build the table)
+    out_s, _, st_s = evaluate(forest, bad, T, per_tree=True, flags=4)
+    assert np.all(st_s[4] & 2) and np.isneginf(out_s[4]) and rel(out_s[keep], good[keep]) <= 1e-10
