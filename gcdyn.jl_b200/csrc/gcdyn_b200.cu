@@ -6,6 +6,7 @@
 #include "cheb_gemm.cuh"
 #include "simulator.h"
 #include "peer_allreduce.cuh"
+#include "metropolis.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -452,7 +453,9 @@ int launch_finish(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& 
 // S_fixed > 0 pins the number of Taylor cells; otherwise every pset adapts it inside traj_kernel.
 int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, double rate_max, double T, int method,
                  int M, int S_fixed, double tol, int flags, const double* host_gamma_shared, double* d_out_pset,
-                 double* d_out_tree, int32_t* d_status, cudaStream_t st, PsetPack* pk_out) {
+                 double* d_out_tree, int32_t* d_status, cudaStream_t st, PsetPack* pk_out, double rate_typical = 0.0) {
+    // rate_max bounds every pset's rates (table capacity); rate_typical (> 0: the sampler's current rates) only picks
+    // the Chebyshev interpolation degree — a pset it is too small for is flagged and summed exactly
     const int P = pv.P, K = pv.K;
     if (P > 65535) return fail(ctx, GCDYN_EUNSUPPORTED, "more than 65535 parameter sets per call");
     PsetPack pk{};
@@ -503,7 +506,8 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             cc.tab_stride = cfg.tab_stride;
             cc.S_cap = cfg.S_cap;
             cc.grid_doubles = cfg.grid_doubles;
-            cc.D = cheb_degree(T, rate_max, K, f->mom.Dcap, cfg.S_cap, M, ctx->smem_optin);
+            cc.D = cheb_degree(T, rate_typical > 0.0 ? std::min(rate_typical, rate_max) : rate_max, K, f->mom.Dcap, cfg.S_cap, M,
+                               ctx->smem_optin);
             cc.compact_tc = pv.gamma_stride == 0 ? 1 : 0;
             cc.mv = f->mom;
             cc.A = ctx->gemm_a.as<double>();
@@ -1258,6 +1262,173 @@ extern "C" void gcdyn_comm_destroy(gcdyn_comm* c) {
     if (c->window) cudaFree(c->window);
     cudaSetDevice(prev);
     delete c;
+}
+
+// ---- device-resident Metropolis ----------------------------------------------------------------------------
+struct gcdyn_mh {
+    gcdyn_ctx* ctx = nullptr;
+    const gcdyn_forest* forest = nullptr;
+    gcdyn_comm* comm = nullptr;
+    int C = 0, K = 0;
+    double T = 0.0, rate_bound = 0.0, rate_typical = 0.0;
+    void* blob = nullptr;              // parameters in the likelihood's layout (SIGMOID response) + sampler state
+    ParamsView pv{};
+    gcdyn::MhView v{};
+    std::vector<double> host_gamma;
+    int64_t iteration = 0;
+    bool have_ll = false;
+    void* hist = nullptr;              // device history buffer (grow-only)
+    size_t hist_cap = 0;
+};
+
+extern "C" int gcdyn_mh_create(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_mh_desc* d, double present_time,
+                               gcdyn_comm* comm, gcdyn_mh** out) {
+    GUARD_BEGIN
+    if (!ctx || !f || !d || !out) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    *out = nullptr;
+    if (d->n_chains < 1 || d->n_chains > 65535) return fail(ctx, GCDYN_EINVAL, "n_chains out of range");
+    if (d->n_types != f->v.K) return fail(ctx, GCDYN_EINVAL, "desc and forest disagree on n_types");
+    if (!d->type_space || !d->Gamma || !d->theta0 || !d->lower || !d->upper) return fail(ctx, GCDYN_EINVAL, "NULL array in desc");
+    if (!(d->rho >= 0.0 && d->rho <= 1.0) || !(d->sigma >= 0.0 && d->sigma <= 1.0)) return fail(ctx, GCDYN_EINVAL, "rho, sigma must be between 0 and 1");
+    if (!(present_time > 0.0) || !(d->step > 0.0)) return fail(ctx, GCDYN_EINVAL, "present_time and step must be positive");
+    for (int j = 2; j < gcdyn::MH_DIM; ++j)
+        if (!std::isfinite(d->upper[j])) return fail(ctx, GCDYN_EINVAL, "upper[2..5] must be finite: they bound the rates");
+    if (comm && comm->cap < d->n_chains) return fail(ctx, GCDYN_EINVAL, "comm window smaller than n_chains");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const int C = d->n_chains, K = d->n_types;
+    gcdyn_mh* m = new gcdyn_mh();
+    m->ctx = ctx; m->forest = f; m->comm = comm; m->C = C; m->K = K; m->T = present_time;
+    m->host_gamma.assign(d->Gamma, d->Gamma + (size_t)K * K);
+    // rates are bounded on the prior box: lambda <= yscale + yshift, |gamma_i| <= delta * max|Gamma_ii|
+    double gmax = 0.0;
+    for (int i = 0; i < K; ++i) gmax = std::max(gmax, std::fabs(d->Gamma[i + (size_t)i * K]));
+    const auto up = [&](int j) { return std::exp(std::min(d->upper[j], 50.0)); };
+    m->rate_bound = up(2) + up(3) + up(4) + 2.0 * up(5) * gmax;
+    // the interpolation degree follows the rates at the starting points (with a margin), not the worst corner of the box
+    for (int c = 0; c < C; ++c) {
+        const double* t = d->theta0 + (size_t)c * gcdyn::MH_DIM;
+        const double r = std::exp(t[2]) + std::exp(t[3]) + std::exp(t[4]) + 2.0 * std::exp(t[5]) * gmax;
+        if (std::isfinite(r)) m->rate_typical = std::max(m->rate_typical, 1.5 * r);
+    }
+    // blob: xscale xshift yscale yshift mu delta rho sigma [C each] | type_space [K] | Gamma [K*K] | theta prop [6C each]
+    //       | ll ll_prop [C each] | accepted [C i64] | inside [C i32]
+    const size_t nd = (size_t)8 * C + K + (size_t)K * K + (size_t)2 * gcdyn::MH_DIM * C + 2 * (size_t)C + C + (C + 1) / 2 + 8;
+    cudaError_t e = cudaMalloc(&m->blob, nd * 8);
+    if (e != cudaSuccess) { delete m; return fail(ctx, GCDYN_ECUDA, cudaGetErrorString(e)); }
+    std::vector<double> h(nd, 0.0);
+    double* base = static_cast<double*>(m->blob);
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += n; return r; };
+    const size_t o_xs = take(C), o_xsh = take(C), o_ys = take(C), o_ysh = take(C), o_mu = take(C), o_de = take(C);
+    const size_t o_rho = take(C), o_sig = take(C), o_ts = take(K), o_G = take((size_t)K * K);
+    const size_t o_th = take((size_t)gcdyn::MH_DIM * C), o_pr = take((size_t)gcdyn::MH_DIM * C);
+    const size_t o_ll = take(C), o_llp = take(C), o_acc = take(C), o_in = take((C + 1) / 2);
+    for (int c = 0; c < C; ++c) { h[o_rho + c] = d->rho; h[o_sig + c] = d->sigma; }
+    std::memcpy(&h[o_ts], d->type_space, (size_t)K * 8);
+    std::memcpy(&h[o_G], d->Gamma, (size_t)K * K * 8);
+    std::memcpy(&h[o_th], d->theta0, (size_t)gcdyn::MH_DIM * C * 8);
+    e = cudaMemcpy(m->blob, h.data(), nd * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(m->blob); delete m; return fail(ctx, GCDYN_ECUDA, cudaGetErrorString(e)); }
+    ParamsView& pv = m->pv;
+    pv.P = C; pv.K = K; pv.response = GCDYN_LAMBDA_SIGMOID; pv.gamma_stride = 0; pv.lambda = nullptr;
+    pv.xscale = base + o_xs; pv.xshift = base + o_xsh; pv.yscale = base + o_ys; pv.yshift = base + o_ysh;
+    pv.type_space = base + o_ts; pv.mu = base + o_mu; pv.delta = base + o_de; pv.rho = base + o_rho; pv.sigma = base + o_sig;
+    pv.Gamma = base + o_G;
+    gcdyn::MhView& v = m->v;
+    v.C = C; v.K = K;
+    v.theta = base + o_th; v.prop = base + o_pr; v.ll = base + o_ll; v.ll_prop = base + o_llp;
+    v.accepted = reinterpret_cast<long long*>(base + o_acc); v.inside = reinterpret_cast<int*>(base + o_in);
+    v.xscale = base + o_xs; v.xshift = base + o_xsh; v.yscale = base + o_ys; v.yshift = base + o_ysh;
+    v.mu = base + o_mu; v.delta = base + o_de;
+    for (int j = 0; j < gcdyn::MH_DIM; ++j) { v.lower[j] = d->lower[j]; v.upper[j] = d->upper[j]; }
+    v.step = d->step; v.seed = d->seed;
+    *out = m;
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+namespace {
+// one batched likelihood of the C parameter sets currently in the blob → dst[C] (all-reduced when sharded)
+int mh_loglik(gcdyn_mh* m, double* dst, cudaStream_t st) {
+    gcdyn_ctx* ctx = m->ctx;
+    int rc = enqueue_eval(ctx, m->forest, m->pv, m->rate_bound, m->T, GCDYN_METHOD_ODE, 16, 0, 1e-11, 0, m->host_gamma.data(),
+                          dst, nullptr, nullptr, st, nullptr, m->rate_typical);
+    if (rc) return rc;
+    if (m->comm) return gcdyn_comm_allreduce(m->comm, dst, m->C, st);
+    return GCDYN_OK;
+}
+}  // namespace
+
+extern "C" int gcdyn_mh_run(gcdyn_mh* m, int64_t iterations, double* theta_hist, double* loglik_hist) {
+    gcdyn_ctx* ctx = m ? m->ctx : nullptr;
+    GUARD_BEGIN
+    if (!m || iterations < 0) return fail(ctx, GCDYN_EINVAL, "bad argument");
+    if ((theta_hist == nullptr) != (loglik_hist == nullptr)) return fail(ctx, GCDYN_EINVAL, "give both history buffers or neither");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int C = m->C, threads = 128, blocks = (C + threads - 1) / threads;
+    double *d_ht = nullptr, *d_hl = nullptr;
+    if (theta_hist && iterations > 0) {
+        const size_t need = (size_t)iterations * C * (gcdyn::MH_DIM + 1) * 8;
+        if (need > m->hist_cap) {
+            if (m->hist) cudaFree(m->hist);
+            m->hist = nullptr; m->hist_cap = 0;
+            CU_TRY(ctx, cudaMalloc(&m->hist, need));
+            m->hist_cap = need;
+        }
+        d_ht = static_cast<double*>(m->hist);
+        d_hl = d_ht + (size_t)iterations * C * gcdyn::MH_DIM;
+    }
+    if (!m->have_ll) {
+        gcdyn::mh_state_params_kernel<<<blocks, threads, 0, st>>>(m->v);
+        CU_TRY(ctx, cudaGetLastError());
+        int rc = mh_loglik(m, m->v.ll, st);
+        if (rc) return rc;
+        m->have_ll = true;
+    }
+    for (int64_t i = 0; i < iterations; ++i) {
+        const uint64_t it = (uint64_t)(m->iteration + 1);
+        gcdyn::mh_propose_kernel<<<blocks, threads, 0, st>>>(m->v, it);
+        CU_TRY(ctx, cudaGetLastError());
+        int rc = mh_loglik(m, m->v.ll_prop, st);
+        if (rc) return rc;
+        gcdyn::mh_accept_kernel<<<blocks, threads, 0, st>>>(m->v, it, d_ht, d_hl, (long long)i);
+        CU_TRY(ctx, cudaGetLastError());
+        ++m->iteration;
+    }
+    if (d_ht) {
+        CU_TRY(ctx, cudaMemcpyAsync(theta_hist, d_ht, (size_t)iterations * C * gcdyn::MH_DIM * 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaMemcpyAsync(loglik_hist, d_hl, (size_t)iterations * C * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+extern "C" int gcdyn_mh_state(gcdyn_mh* m, double* theta, double* loglik, int64_t* accepted, int64_t* iteration) {
+    gcdyn_ctx* ctx = m ? m->ctx : nullptr;
+    GUARD_BEGIN
+    if (!m) return fail(ctx, GCDYN_EINVAL, "mh is NULL");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (theta) CU_TRY(ctx, cudaMemcpy(theta, m->v.theta, (size_t)m->C * gcdyn::MH_DIM * 8, cudaMemcpyDeviceToHost));
+    if (loglik) CU_TRY(ctx, cudaMemcpy(loglik, m->v.ll, (size_t)m->C * 8, cudaMemcpyDeviceToHost));
+    if (accepted) CU_TRY(ctx, cudaMemcpy(accepted, m->v.accepted, (size_t)m->C * 8, cudaMemcpyDeviceToHost));
+    if (iteration) *iteration = m->iteration;
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+extern "C" void gcdyn_mh_destroy(gcdyn_mh* m) {
+    if (!m) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    if (m->blob) cudaFree(m->blob);
+    if (m->hist) cudaFree(m->hist);
+    cudaSetDevice(prev);
+    delete m;
 }
 
 #ifdef GCDYN_TRAJ_TRACE

@@ -62,6 +62,13 @@ class Params(C.Structure):
                 ("Gamma", _p_f64)]
 
 
+class MhDesc(C.Structure):
+    """`gcdyn_mh_desc` (include/gcdyn_b200.h)."""
+    _fields_ = [("n_chains", C.c_int32), ("n_types", C.c_int32), ("type_space", _p_f64), ("Gamma", _p_f64),
+                ("rho", C.c_double), ("sigma", C.c_double), ("theta0", _p_f64), ("lower", _p_f64), ("upper", _p_f64),
+                ("step", C.c_double), ("seed", C.c_uint64)]
+
+
 class Opts(C.Structure):
     _fields_ = [("steps", C.c_int32), ("order", C.c_int32), ("tol", C.c_double), ("flags", C.c_int32),
                 ("reserved", C.c_int32)]
@@ -122,6 +129,10 @@ def _lib():
         "gcdyn_comm_connect": (C.c_int, [vp, vp]),
         "gcdyn_comm_allreduce": (C.c_int, [vp, vp, C.c_int32, vp]),
         "gcdyn_comm_destroy": (None, [vp]),
+        "gcdyn_mh_create": (C.c_int, [vp, vp, C.POINTER(MhDesc), C.c_double, vp, C.POINTER(vp)]),
+        "gcdyn_mh_run": (C.c_int, [vp, C.c_int64, _p_f64, _p_f64]),
+        "gcdyn_mh_state": (C.c_int, [vp, _p_f64, _p_f64, _p_i64, _p_i64]),
+        "gcdyn_mh_destroy": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)       # AttributeError here = header and library out of sync

@@ -18,7 +18,7 @@ import numpy as np
 from .types import SigmoidalBranchingProcess
 from .likelihood import DeviceParams, Forest, evaluate, pack_params
 
-__all__ = ["MetropolisResult", "random_walk_metropolis", "theta_of", "model_of"]
+__all__ = ["MetropolisResult", "random_walk_metropolis", "device_metropolis", "CounterRNG", "theta_of", "model_of"]
 
 NAMES = ("log_xscale", "xshift", "log_yscale", "log_yshift", "log_mu", "log_delta")
 
@@ -46,18 +46,94 @@ class MetropolisResult:
         return self.accepted / max(1, self.chain.shape[0] - 1)
 
 
+class CounterRNG:
+    """The counter-based stream of `csrc/metropolis.cuh`: uniform(seed, iteration, chain, slot) is a splitmix64
+    hash, normals are Box–Muller on slots (2j, 2j+1), the accept draw is slot 12.  Pure NumPy, so the host-driven
+    sampler below can replay exactly what the device-resident one draws."""
+
+    M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+    def __init__(self, seed):
+        self.seed = np.uint64(int(seed) & 0xFFFFFFFFFFFFFFFF)
+
+    @staticmethod
+    def _mix(z):
+        with np.errstate(over="ignore"):
+            z = (z + np.uint64(0x9E3779B97F4A7C15))
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            return z ^ (z >> np.uint64(31))
+
+    def uniform(self, it, chain, slot):
+        chain = np.asarray(chain, dtype=np.uint64)
+        slot = np.asarray(slot, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            h = self._mix(self._mix(self._mix(self.seed) ^ np.uint64(it)) ^ (chain * np.uint64(16) + slot))
+        return ((h >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+    def normals(self, it, n_chains, dim):
+        c = np.arange(n_chains)[:, None]
+        j = np.arange(dim)[None, :]
+        u1, u2 = self.uniform(it, c, 2 * j), self.uniform(it, c, 2 * j + 1)
+        return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+
+    def log_uniform(self, it, n_chains, dim):
+        return np.log(self.uniform(it, np.arange(n_chains), np.full(n_chains, 2 * dim)))
+
+
+def device_metropolis(forest: Forest, template: SigmoidalBranchingProcess, present_time, theta0, iterations, *,
+                      step=0.05, lower, upper, seed=0, comm=None, history=True) -> MetropolisResult:
+    """`gcdyn_mh_*`: the same sampler as `random_walk_metropolis(..., rng="counter")`, but proposals, likelihood,
+    all-reduce (`comm`: a `gcdyn.sharding.PeerAllReduce` when the forest is a shard) and accept/reject all run on
+    the device; the host only enqueues.  `upper[2:]` must be finite."""
+    import ctypes as C
+    from .likelihood import MhDesc, _lib, _check, _ptr, _p_f64, _p_i64
+    lib = _lib()
+    theta0 = np.ascontiguousarray(theta0, dtype=np.float64)
+    n, D = theta0.shape
+    assert D == 6
+    ts = np.ascontiguousarray(template.type_space, dtype=np.float64)
+    gam = np.ascontiguousarray(np.asarray(template.Γ, dtype=np.float64).ravel(order="F"))
+    lo = np.ascontiguousarray(lower, dtype=np.float64)
+    up = np.ascontiguousarray(upper, dtype=np.float64)
+    desc = MhDesc(n, len(ts), _ptr(ts, _p_f64), _ptr(gam, _p_f64), float(template.ρ), float(template.σ),
+                  _ptr(theta0, _p_f64), _ptr(lo, _p_f64), _ptr(up, _p_f64), float(step), int(seed) & 0xFFFFFFFFFFFFFFFF)
+    h = C.c_void_p()
+    ctxh = forest.ctx._h
+    _check(lib.gcdyn_mh_create(ctxh, forest._h, C.byref(desc), float(present_time),
+                               comm._h if comm is not None else None, C.byref(h)), ctxh)
+    try:
+        th = np.empty((n, 6)); ll = np.empty(n); acc = np.zeros(n, dtype=np.int64); it = C.c_int64()
+        _check(lib.gcdyn_mh_run(h, 0, None, None), ctxh)          # initial log-likelihood
+        _check(lib.gcdyn_mh_state(h, _ptr(th, _p_f64), _ptr(ll, _p_f64), _ptr(acc, _p_i64), C.byref(it)), ctxh)
+        if history:
+            chain = np.empty((iterations + 1, n, 6)); lls = np.empty((iterations + 1, n))
+            chain[0], lls[0] = th, ll
+            _check(lib.gcdyn_mh_run(h, int(iterations), _ptr(chain[1:], _p_f64), _ptr(lls[1:], _p_f64)), ctxh)
+        else:
+            _check(lib.gcdyn_mh_run(h, int(iterations), None, None), ctxh)
+        _check(lib.gcdyn_mh_state(h, _ptr(th, _p_f64), _ptr(ll, _p_f64), _ptr(acc, _p_i64), C.byref(it)), ctxh)
+        if not history:
+            chain, lls = th[None].copy(), ll[None].copy()
+    finally:
+        lib.gcdyn_mh_destroy(h)
+    return MetropolisResult(chain=chain, loglik=lls, accepted=acc)
+
+
 def random_walk_metropolis(forest: Forest, template: SigmoidalBranchingProcess, present_time, theta0,
                            iterations, *, step=0.05, lower=None, upper=None, seed=0, loglik_fn=None,
-                           allreduce=None) -> MetropolisResult:
+                           allreduce=None, rng="numpy") -> MetropolisResult:
     """Run C = len(theta0) chains for `iterations` steps.
 
     `loglik_fn(models) -> [C]` defaults to the GPU batched likelihood on `forest`; tests pass the oracle here
     to check that both produce the same chain from the same seed.  `allreduce(array) -> array` sums the
-    per-rank partial log-likelihoods when the forest is a shard (see `gcdyn.sharding.allreduce_sum`)."""
+    per-rank partial log-likelihoods when the forest is a shard (see `gcdyn.sharding.allreduce_sum`).
+    `rng="counter"` draws from `CounterRNG`, the stream of the device-resident sampler (`device_metropolis`)."""
     theta = np.array(theta0, dtype=np.float64)
     C, D = theta.shape
     lower = np.full(D, -np.inf) if lower is None else np.asarray(lower, dtype=np.float64)
     upper = np.full(D, np.inf) if upper is None else np.asarray(upper, dtype=np.float64)
+    counter = CounterRNG(seed) if rng == "counter" else None
     rng = np.random.default_rng(seed)
 
     gamma_col = np.ascontiguousarray(template.Γ.ravel(order="F"))
@@ -88,12 +164,12 @@ def random_walk_metropolis(forest: Forest, template: SigmoidalBranchingProcess, 
     chain[0], lls[0] = theta, ll
     accepted = np.zeros(C, dtype=np.int64)
     for it in range(1, iterations + 1):
-        prop = theta + step * rng.standard_normal((C, D))
+        prop = theta + step * (counter.normals(it, C, D) if counter else rng.standard_normal((C, D)))
         inside = np.all((prop >= lower) & (prop <= upper), axis=1)
         # proposals outside the prior box are rejected without looking at their likelihood, but they are
         # still evaluated (clipped) so that every iteration is one batch of exactly C parameter sets
         ll_prop = loglik(np.clip(prop, np.maximum(lower, -50.0), np.minimum(upper, 50.0)))
-        logu = np.log(rng.random(C))
+        logu = counter.log_uniform(it, C, D) if counter else np.log(rng.random(C))
         with np.errstate(invalid="ignore"):
             accept = inside & (logu < ll_prop - ll)
         theta = np.where(accept[:, None], prop, theta)

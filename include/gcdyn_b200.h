@@ -218,6 +218,36 @@ int  gcdyn_comm_connect(gcdyn_comm* comm, const void* handles);
 int  gcdyn_comm_allreduce(gcdyn_comm* comm, double* d_inout, int32_t n_psets, void* stream);
 void gcdyn_comm_destroy(gcdyn_comm* comm);
 
+/* ---- device-resident random-walk Metropolis (BASELINE config 4) --------------------------
+ * The reference ships no sampler (README.md:3); this is the consumer of the batched likelihood.  C chains over
+ * theta = (log xscale, xshift, log yscale, log yshift, log mu, log delta) of a SigmoidalBranchingProcess
+ * (src/types.jl:65-110) advance in lock-step: per iteration one proposal kernel, ONE batched likelihood of C
+ * parameter sets on `forest`, the peer all-reduce when `comm` is given (trees sharded over ranks), and one
+ * accept/reject kernel - no host round trip inside an iteration.  Flat prior on the box [lower, upper];
+ * upper[2..5] must be finite (they bound the rates that size the integrator's tables).  Random numbers are
+ * a hash of (seed, iteration, chain, slot): every rank draws identical proposals. */
+typedef struct {
+    int32_t n_chains;
+    int32_t n_types;
+    const double* type_space;      /* [K]                                   */
+    const double* Gamma;           /* K x K column-major, shared            */
+    double rho, sigma;
+    const double* theta0;          /* [n_chains*6]                          */
+    const double* lower;           /* [6]                                   */
+    const double* upper;           /* [6]                                   */
+    double step;                   /* proposal standard deviation           */
+    uint64_t seed;
+} gcdyn_mh_desc;
+typedef struct gcdyn_mh gcdyn_mh;
+int  gcdyn_mh_create(gcdyn_ctx* ctx, const gcdyn_forest* forest, const gcdyn_mh_desc* desc, double present_time,
+                     gcdyn_comm* comm, gcdyn_mh** out);
+/* Runs `iterations` Metropolis steps and waits for them.  theta_hist [iterations*n_chains*6] and
+ * loglik_hist [iterations*n_chains] (host, may be NULL) receive the state after every step. */
+int  gcdyn_mh_run(gcdyn_mh* mh, int64_t iterations, double* theta_hist, double* loglik_hist);
+/* Current state: theta [n_chains*6], loglik [n_chains], accepted [n_chains] (host; any may be NULL). */
+int  gcdyn_mh_state(gcdyn_mh* mh, double* theta, double* loglik, int64_t* accepted, int64_t* iteration);
+void gcdyn_mh_destroy(gcdyn_mh* mh);
+
 #ifdef __cplusplus
 }
 #endif

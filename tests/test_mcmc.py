@@ -45,3 +45,44 @@ def test_gpu_chain_equals_oracle_chain(ctx):
     assert np.array_equal(gpu.accepted, ora.accepted)
     assert np.array_equal(gpu.chain, ora.chain)
     assert np.max(np.abs(gpu.loglik - ora.loglik) / np.abs(ora.loglik)) <= 1e-10
+
+
+def test_counter_rng_is_a_sane_standard_normal_stream():
+    from gcdyn.mcmc import CounterRNG
+    r = CounterRNG(11)
+    z = np.concatenate([r.normals(it, 32, 6).ravel() for it in range(1, 400)])
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
+    u = np.concatenate([np.exp(r.log_uniform(it, 32, 6)) for it in range(1, 400)])
+    assert 0.0 < u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.02
+    assert np.array_equal(r.normals(7, 5, 6), CounterRNG(11).normals(7, 5, 6))          # stateless
+    assert not np.array_equal(r.normals(7, 5, 6), CounterRNG(12).normals(7, 5, 6))
+    # proposals of a chain do not depend on how many chains run beside it (multi-GPU ranks draw the same numbers)
+    assert np.array_equal(r.normals(7, 5, 6), r.normals(7, 9, 6)[:5])
+
+
+@pytest.mark.gpu
+def test_device_resident_chain_equals_host_driven_and_oracle_chains(ctx):
+    """`gcdyn_mh_*` (proposal, likelihood, accept/reject all on the device) against the host-driven sampler replaying
+    the same counter-based stream — once with the GPU likelihood (16 chains: GEMM path), once with the oracle."""
+    import oracle
+    from gcdyn.mcmc import device_metropolis
+    rng = np.random.default_rng(33)
+    tpl = _template()
+    T = 3.0
+    trees = gcdyn.rand_tree(tpl, T, tpl.type_space[2], 8, rng=rng)
+    forest = gcdyn.Forest(trees, tpl.type_space, T, ctx=ctx)
+    th = theta_of(tpl)
+    lower, upper = th - 0.6, th + 0.6
+    lower[1], upper[1] = th[1] - 0.05, th[1] + 0.05          # a tight side of the box: some proposals fall outside
+    for C, iters, use_oracle in ((16, 40, False), (4, 10, True)):
+        th0 = np.clip(th + 0.03 * rng.standard_normal((C, 6)), lower, upper)
+        kw = dict(step=0.04, seed=21, lower=lower, upper=upper)
+        dev = device_metropolis(forest, tpl, T, th0, iters, **kw)
+        fn = (lambda ms: [oracle.loglikelihood_shared(m, trees, T) for m in ms]) if use_oracle else None
+        host = random_walk_metropolis(None if use_oracle else forest, tpl, T, th0, iters, rng="counter", loglik_fn=fn, **kw)
+        assert dev.chain.shape == host.chain.shape == (iters + 1, C, 6)
+        assert np.array_equal(dev.accepted, host.accepted)
+        assert 0 < dev.accepted.sum() < C * iters
+        assert np.max(np.abs(dev.chain - host.chain)) <= 1e-12
+        assert np.max(np.abs(dev.loglik - host.loglik) / np.abs(host.loglik)) <= 1e-10
+        assert np.all(dev.chain[..., 1] >= lower[1]) and np.all(dev.chain[..., 1] <= upper[1])
