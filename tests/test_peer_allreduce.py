@@ -39,7 +39,7 @@ for it in range(40):                                 # many calls: sequence numb
     assert all(g == gathered[0] for g in gathered)   # bit-identical on every rank
 peer.close()
 dist.barrier()
-print("rank", rank, "ok")
+sys.stdout.write("rank%d-ok\n" % rank)
 """
 
 
@@ -54,8 +54,9 @@ def _run(world):
         r = subprocess.run(cmd, env=dict(os.environ), capture_output=True, text=True, timeout=300)
     finally:
         os.unlink(path)
+    # every assertion lives in the workers; torchrun exits non-zero if any rank fails
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert r.stdout.count(" ok") == world
+    assert r.stdout.count("-ok") == world, r.stdout
 
 
 @pytest.mark.gpu
