@@ -10,7 +10,7 @@ from .treenode import (attach, detach, delete, map_types, map_types_inplace,
                        PostOrderTraversal, PreOrderTraversal, LeafTraversal)
 from .multitype_branching_process import (expit, sigmoid, type_space_index, λ, μ, γ,
                                           lambda_, mu, gamma, rand_tree, mutate, sample_child)
-from .flatten import FlatForest, flatten
+from .flatten import FlatForest, flatten, map_types_flat
 from .likelihood import (loglikelihood, naive_loglikelihood, stadler_appx_loglikelihood,
                          stadler_appx_unconditioned_loglikelihood, Forest, Context,
                          pack_params, DeviceParams, evaluate, evaluate_resident,
@@ -28,7 +28,7 @@ __all__ = [
     "naive_loglikelihood", "stadler_appx_loglikelihood", "stadler_appx_unconditioned_loglikelihood",
     "expit", "sigmoid", "type_space_index", "mutate", "sample_child", "EVENTS",
     # additions of this build
-    "Forest", "Context", "FlatForest", "flatten", "pack_params", "DeviceParams", "evaluate",
+    "Forest", "Context", "FlatForest", "flatten", "map_types_flat", "pack_params", "DeviceParams", "evaluate",
     "evaluate_resident", "lambda_", "mu", "gamma",
     "ArgumentError", "DimensionMismatch", "BoundsError", "DomainError", "GcdynError", "library_path",
 ]

@@ -19,7 +19,7 @@ import numpy as np
 from .types import ArgumentError, BoundsError, EVENT_CODE, TreeNode
 from .treenode import LeafTraversal, PostOrderTraversal
 
-__all__ = ["FlatForest", "flatten", "METHODS"]
+__all__ = ["FlatForest", "flatten", "map_types_flat", "METHODS"]
 
 METHODS = ("ode", "naive", "stadler", "stadler_unconditioned")
 
@@ -206,3 +206,108 @@ def flatten(trees, type_space, present_time=None, method="ode", *, discrete_lamb
         child_off=child_off, child_idx=np.asarray(child_idx, dtype=np.int32),
         live=np.asarray(live, dtype=np.uint8), root_type_idx=np.asarray(root_type_idx, dtype=np.int32),
         root_time=root_time_a, self_loop=np.asarray(self_loop, dtype=np.uint8), event_counts=counts)
+
+
+def map_types_flat(flat: FlatForest, index_map, n_types_new, *, prune_self_loops=True) -> FlatForest:
+    """`map_types(mapping, tree; prune_self_loops)` (treenode.jl:60-85) on flattened arrays.
+
+    `index_map[k]` is the position, in the NEW type space, of the image of old type `k` under the mapping
+    (e.g. the bin of a discretised affinity); a type outside the old space (index -1) stays -1.  The result equals
+    `flatten(map_types(mapping, tree), new_type_space)` array for array — including the reference's child order:
+    `delete!` (treenode.jl:38-48) re-attaches the children of a pruned self-loop type change at the END of its
+    parent's children, and the nodes are examined in the pre-order of the ORIGINAL tree (`PreOrderTraversal`
+    snapshots the node list before iterating, treenode.jl:177-194).  No pointer trees are rebuilt.  The per-node
+    validation of `flatten` is not repeated (the forest was valid for the old type space; a mapping cannot
+    invalidate events or times)."""
+    imap = np.asarray(index_map, dtype=np.int64)
+    if imap.shape != (flat.n_types,):
+        raise ArgumentError("index_map must have one entry per old type")
+
+    def remap(a):
+        a = np.asarray(a, dtype=np.int64)
+        return np.where(a >= 0, imap[np.clip(a, 0, None)], -1).astype(np.int32)
+
+    tnew_all, bnew_all, rnew = remap(flat.type_idx), remap(flat.btype_idx), remap(flat.root_type_idx)
+    o_tree_off = [0]
+    o_event, o_type, o_btype, o_ts, o_te, o_parent, o_live, o_ccnt, o_cidx, o_loop = [], [], [], [], [], [], [], [], [], []
+    for t in range(flat.n_trees):
+        a, b = int(flat.tree_off[t]), int(flat.tree_off[t + 1])
+        n = b - a
+        ev, tn, bn = flat.event[a:b], tnew_all[a:b], bnew_all[a:b]
+        te = flat.t_end[a:b]
+        coff = flat.child_off[a:b + 1]
+        children = [list(flat.child_idx[coff[i]:coff[i + 1]]) for i in range(n)]
+        up = [int(x) for x in flat.parent[a:b]]
+        root_children = [n - 1]                       # the top node closes the post-order
+        if prune_self_loops:
+            order, stack = [], [n - 1]
+            while stack:                               # pre-order of the original tree
+                v = stack.pop()
+                order.append(v)
+                stack.extend(reversed(children[v]))
+            for v in order:
+                if ev[v] == _EV_TC and tn[v] == bn[v]:
+                    w = up[v]
+                    lst = root_children if w < 0 else children[w]
+                    lst.remove(v)
+                    for c in children[v]:
+                        up[c] = w
+                        lst.append(c)
+                    children[v] = []
+                    up[v] = -2                          # gone
+        if not root_children:
+            raise BoundsError("attempt to access 0-element Vector{TreeNode} at index [1]")
+        # post-order of the new first subtree
+        post, stack = [], [(root_children[0], 0)]
+        while stack:
+            v, k = stack.pop()
+            if k < len(children[v]):
+                stack.append((v, k + 1))
+                stack.append((children[v][k], 0))
+            else:
+                post.append(v)
+        newpos = {v: i for i, v in enumerate(post)}
+        dead = set()
+        looped = 0
+        for v in post:
+            w = up[v]
+            o_event.append(int(ev[v]))
+            o_type.append(int(tn[v]))
+            o_btype.append(int(rnew[t]) if w < 0 else int(tn[w]))
+            o_ts.append(float(flat.root_time[t]) if w < 0 else float(te[w]))
+            o_te.append(float(te[v]))
+            o_parent.append(-1 if w < 0 else newpos[w])
+            o_ccnt.append(len(children[v]))
+            o_cidx.extend(newpos[c] for c in children[v])
+            if ev[v] == _EV_BIRTH:
+                dead.update(children[v][2:])
+            elif ev[v] == _EV_TC:
+                dead.update(children[v][1:])
+                if tn[v] == (rnew[t] if w < 0 else tn[w]):
+                    looped = 1
+        flags = [1] * len(post)
+        if dead:
+            for i in range(len(post) - 1, -1, -1):    # parents first
+                v = post[i]
+                w = up[v]
+                if v in dead or (w >= 0 and flags[newpos[w]] == 0):
+                    flags[i] = 0
+        o_live.extend(flags)
+        o_loop.append(looped)
+        o_tree_off.append(len(o_event))
+    ev_a = np.asarray(o_event, dtype=np.uint8)
+    tree_off_a = np.asarray(o_tree_off, dtype=np.int64)
+    child_off = np.zeros(len(o_event) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(o_ccnt, dtype=np.int64), out=child_off[1:])
+    counts = np.zeros((flat.n_trees, 7), dtype=np.int64)
+    if len(ev_a):
+        tree_id = np.repeat(np.arange(flat.n_trees), np.diff(tree_off_a))
+        np.add.at(counts, (tree_id, ev_a), 1)
+    return FlatForest(
+        n_types=int(n_types_new), tree_off=tree_off_a, event=ev_a,
+        type_idx=np.asarray(o_type, dtype=np.int32), btype_idx=np.asarray(o_btype, dtype=np.int32),
+        t_start=np.asarray(o_ts, dtype=np.float64), t_end=np.asarray(o_te, dtype=np.float64),
+        parent=np.asarray(o_parent, dtype=np.int32), child_off=child_off,
+        child_idx=np.asarray(o_cidx, dtype=np.int32), live=np.asarray(o_live, dtype=np.uint8),
+        root_type_idx=rnew, root_time=np.asarray(flat.root_time, dtype=np.float64).copy(),
+        self_loop=np.asarray(o_loop, dtype=np.uint8), event_counts=counts)
