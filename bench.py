@@ -297,20 +297,17 @@ def run_gpu(args):
 
     # ---- e2e: the host-buffer C-ABI call (parameters H2D, results D2H inside the timed region)
     for _ in range(3):
-        evaluate(forest, params, T, steps=args.taylor_steps, order=args.order, want_status=False)
+        evaluate(forest, params, T, steps=args.taylor_steps, order=args.order, want_status=False, comm=peer)
     barrier()
     e2e_s = 0.0
     for i in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        o, _, _ = evaluate(forest, params, T, steps=args.taylor_steps, order=args.order, want_status=False)
-        if world > 1:
+        o, _, _ = evaluate(forest, params, T, steps=args.taylor_steps, order=args.order, want_status=False, comm=peer)
+        if world > 1 and peer is None:
             t = torch.from_numpy(o).cuda()
-            if peer is not None:
-                peer.allreduce(t.data_ptr(), P, stream.cuda_stream)
-            else:
-                dist.all_reduce(t)
+            dist.all_reduce(t)
             o = t.cpu().numpy()
         e2e_s += time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -321,7 +318,8 @@ def run_gpu(args):
                         if a is not None)
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_par_doubles,
            "d2h_bytes_per_step": P * 8, "ms_per_step": 1e3 * float(te.item()) / args.steps,
-           "api": "gcdyn_loglik_batch (host buffers; forest handle created once per dataset, as a sampler would)"}
+           "api": ("gcdyn_loglik_batch_sharded" if peer is not None else "gcdyn_loglik_batch") +
+                  " (host buffers; forest handle created once per dataset, as a sampler would)"}
     if world > 1:
         assert np.allclose(o, result, rtol=1e-12, atol=0)
 

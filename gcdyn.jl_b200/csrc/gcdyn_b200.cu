@@ -755,8 +755,10 @@ int forest_create_impl(gcdyn_ctx* ctx, const gcdyn_forest_desc* d, gcdyn_forest*
     return GCDYN_OK;
 }
 
+int comm_enqueue(gcdyn_comm* c, const double* d_in, double* out, int n_psets, cudaStream_t st);   // peer all-reduce (below)
+
 int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, double T, int method,
-               const gcdyn_opts* opts, double* out_pset, double* out_tree_pset, int32_t* status) {
+               const gcdyn_opts* opts, double* out_pset, double* out_tree_pset, int32_t* status, gcdyn_comm* comm = nullptr) {
     if (!ctx || !f || !out_pset) return fail(ctx, GCDYN_EINVAL, "NULL argument");
     int rc = check_params(ctx, pr);
     if (rc) return rc;
@@ -785,6 +787,7 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
 
     const bool want_rows = out_tree_pset || status;
     if (status) CU_TRY(ctx, ctx->status.ensure((size_t)P * Tn * 4));
+    if (comm) CU_TRY(ctx, ctx->out_pset.ensure((size_t)P * 8));
     // the per-pset sums are written by the last kernel straight into pinned host memory (device-accessible under
     // unified addressing): no device→host copy node for the 8·P bytes a sampler waits on
     CU_TRY(ctx, ctx->pin_out.ensure((size_t)P * 8 + 64));
@@ -793,9 +796,13 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
     // one pass: every pset adapts its own step count inside traj_kernel (or uses opts->steps as given);
     // a pset that cannot be resolved within the table capacity comes back as a solver failure (-Inf)
     rc = enqueue_eval(ctx, f, pv, rate_max_of(pr), T, method, M, o.steps, tol, o.flags,
-                      pr->gamma_pset_stride == 0 ? pr->Gamma : nullptr, h_out, nullptr,
+                      pr->gamma_pset_stride == 0 ? pr->Gamma : nullptr, comm ? ctx->out_pset.as<double>() : h_out, nullptr,
                       status ? ctx->status.as<int32_t>() : nullptr, st, nullptr);
     if (rc) return rc;
+    if (comm) {                       // trees sharded over ranks: sum the partial [P] over the peers, result → pinned host
+        rc = comm_enqueue(comm, ctx->out_pset.as<double>(), h_out, P, st);
+        if (rc) return rc;
+    }
     if (want_rows) {
         if (out_tree_pset)
             CU_TRY(ctx, cudaMemcpyAsync(out_tree_pset, ctx->out_tree.p, (size_t)P * Tn * 8, cudaMemcpyDeviceToHost, st));
@@ -1230,13 +1237,11 @@ extern "C" int gcdyn_comm_connect(gcdyn_comm* c, const void* handles) {
     GUARD_END(ctx)
 }
 
-extern "C" int gcdyn_comm_allreduce(gcdyn_comm* c, double* d_inout, int32_t n_psets, void* stream) {
-    gcdyn_ctx* ctx = c ? c->ctx : nullptr;
-    GUARD_BEGIN
-    if (!c || !d_inout) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+namespace {
+int comm_enqueue(gcdyn_comm* c, const double* d_in, double* out, int n_psets, cudaStream_t st) {
+    gcdyn_ctx* ctx = c->ctx;
     if (!c->connected && c->world > 1) return fail(ctx, GCDYN_EINVAL, "gcdyn_comm_connect has not been called");
     if (n_psets < 1 || n_psets > c->cap) return fail(ctx, GCDYN_EINVAL, "n_psets exceeds the window capacity");
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
     gcdyn::PeerView pv{};
     pv.rank = c->rank; pv.world = c->world; pv.cap = c->cap;
     for (int r = 0; r < c->world; ++r) {
@@ -1244,10 +1249,29 @@ extern "C" int gcdyn_comm_allreduce(gcdyn_comm* c, double* d_inout, int32_t n_ps
         pv.win[r].flag = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->peer[r]) + comm_data_bytes(c->world, c->cap));
     }
     ++c->seq;
-    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     cudaLaunchConfig_t lc = pdl_config(dim3(1), dim3(1024), 0, st);
-    CU_TRY(ctx, cudaLaunchKernelEx(&lc, gcdyn::peer_allreduce_kernel, pv, d_inout, (int)n_psets, c->seq));
+    CU_TRY(ctx, cudaLaunchKernelEx(&lc, gcdyn::peer_allreduce_kernel, pv, d_in, out, n_psets, c->seq));
     return GCDYN_OK;
+}
+}  // namespace
+
+extern "C" int gcdyn_comm_allreduce(gcdyn_comm* c, double* d_inout, int32_t n_psets, void* stream) {
+    gcdyn_ctx* ctx = c ? c->ctx : nullptr;
+    GUARD_BEGIN
+    if (!c || !d_inout) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    return comm_enqueue(c, d_inout, d_inout, n_psets, st);
+    GUARD_END(ctx)
+}
+
+extern "C" int gcdyn_loglik_batch_sharded(gcdyn_ctx* ctx, const gcdyn_forest* forest, const gcdyn_params* params,
+                                          double present_time, int method, const gcdyn_opts* opts, gcdyn_comm* comm,
+                                          double* out_pset, double* out_tree_pset, int32_t* status) {
+    GUARD_BEGIN
+    if (!comm) return fail(ctx, GCDYN_EINVAL, "comm is NULL");
+    if (comm->ctx != ctx) return fail(ctx, GCDYN_EINVAL, "comm belongs to another context");
+    return batch_impl(ctx, forest, params, present_time, method, opts, out_pset, out_tree_pset, status, comm);
     GUARD_END(ctx)
 }
 
@@ -1354,7 +1378,7 @@ int mh_loglik(gcdyn_mh* m, double* dst, cudaStream_t st) {
     int rc = enqueue_eval(ctx, m->forest, m->pv, m->rate_bound, m->T, GCDYN_METHOD_ODE, 16, 0, 1e-11, 0, m->host_gamma.data(),
                           dst, nullptr, nullptr, st, nullptr, m->rate_typical);
     if (rc) return rc;
-    if (m->comm) return gcdyn_comm_allreduce(m->comm, dst, m->C, st);
+    if (m->comm) return comm_enqueue(m->comm, dst, dst, m->C, st);
     return GCDYN_OK;
 }
 }  // namespace

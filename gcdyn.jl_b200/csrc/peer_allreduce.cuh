@@ -37,15 +37,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-// One CTA.  `inout` = this rank's [P] partial sums on entry, the all-reduced sums on exit.
-__global__ void __launch_bounds__(1024) peer_allreduce_kernel(PeerView pv, double* __restrict__ inout, int P,
+// One CTA.  `in` = this rank's [P] partial sums, `out` = the all-reduced sums (may alias `in`; may be pinned host memory).
+__global__ void __launch_bounds__(1024) peer_allreduce_kernel(PeerView pv, const double* in, double* out, int P,
                                                               unsigned long long seq) {
     asm volatile("griddepcontrol.wait;" ::: "memory");      // launched behind finish_kernel with programmatic serialization
     const int par = (int)(seq & 1ULL);
     const size_t slot = ((size_t)par * pv.world + pv.rank) * pv.cap;
     for (int i = threadIdx.x; i < P * pv.world; i += blockDim.x) {
         const int r = i / P, p = i - r * P;
-        pv.win[r].data[slot + p] = inout[p];
+        pv.win[r].data[slot + p] = in[p];
     }
     __threadfence_system();
     __syncthreads();
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(1024) peer_allreduce_kernel(PeerView pv, doubl
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
         double s = 0.0;
         for (int r = 0; r < pv.world; ++r) s += __ldcg(local + (size_t)r * pv.cap + p);
-        inout[p] = s;
+        out[p] = s;
     }
 }
 

@@ -129,6 +129,8 @@ def _lib():
         "gcdyn_comm_connect": (C.c_int, [vp, vp]),
         "gcdyn_comm_allreduce": (C.c_int, [vp, vp, C.c_int32, vp]),
         "gcdyn_comm_destroy": (None, [vp]),
+        "gcdyn_loglik_batch_sharded": (C.c_int, [vp, vp, C.POINTER(Params), C.c_double, C.c_int, C.POINTER(Opts), vp,
+                                                 _p_f64, _p_f64, _p_i32]),
         "gcdyn_mh_create": (C.c_int, [vp, vp, C.POINTER(MhDesc), C.c_double, vp, C.POINTER(vp)]),
         "gcdyn_mh_run": (C.c_int, [vp, C.c_int64, _p_f64, _p_f64]),
         "gcdyn_mh_state": (C.c_int, [vp, _p_f64, _p_f64, _p_i64, _p_i64]),
@@ -372,8 +374,10 @@ def _opts(reltol=None, abstol=None, steps=0, order=0, flags=0):
 
 
 def evaluate(forest: Forest, params: PackedParams, present_time, method="ode", *, per_tree=False,
-             want_status=True, reltol=None, abstol=None, steps=0, order=0, flags=0):
-    """One `gcdyn_loglik_batch` call.  Returns (out_pset[P], out_tree_pset[P,T] | None, status[P,T] | None)."""
+             want_status=True, reltol=None, abstol=None, steps=0, order=0, flags=0, comm=None):
+    """One `gcdyn_loglik_batch` call.  Returns (out_pset[P], out_tree_pset[P,T] | None, status[P,T] | None).
+    `comm` (a `gcdyn.sharding.PeerAllReduce`): the forest is this rank's shard and `out_pset` is summed over the
+    ranks inside the call (`gcdyn_loglik_batch_sharded`)."""
     lib = _lib()
     P, T = params.n_psets, forest.flat.n_trees
     if params.n_types != forest.flat.n_types:
@@ -383,10 +387,13 @@ def evaluate(forest: Forest, params: PackedParams, present_time, method="ode", *
     st = np.zeros((P, T), dtype=np.int32) if (want_status or per_tree) else None
     ps = params.struct()
     op = _opts(reltol, abstol, steps, order, flags)
-    _check(lib.gcdyn_loglik_batch(forest.ctx._h, forest._h, C.byref(ps),
-                                  float(present_time if present_time is not None else 0.0),
-                                  METHOD_CODE[method], C.byref(op),
-                                  _ptr(out, _p_f64), _ptr(tp, _p_f64), _ptr(st, _p_i32)), forest.ctx._h)
+    T = float(present_time if present_time is not None else 0.0)
+    if comm is not None:
+        _check(lib.gcdyn_loglik_batch_sharded(forest.ctx._h, forest._h, C.byref(ps), T, METHOD_CODE[method], C.byref(op),
+                                              comm._h, _ptr(out, _p_f64), _ptr(tp, _p_f64), _ptr(st, _p_i32)), forest.ctx._h)
+    else:
+        _check(lib.gcdyn_loglik_batch(forest.ctx._h, forest._h, C.byref(ps), T, METHOD_CODE[method], C.byref(op),
+                                      _ptr(out, _p_f64), _ptr(tp, _p_f64), _ptr(st, _p_i32)), forest.ctx._h)
     return out, tp, st
 
 

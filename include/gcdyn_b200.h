@@ -216,6 +216,12 @@ int  gcdyn_comm_create(gcdyn_ctx* ctx, int32_t rank, int32_t world, int32_t max_
                        gcdyn_comm** out);
 int  gcdyn_comm_connect(gcdyn_comm* comm, const void* handles);
 int  gcdyn_comm_allreduce(gcdyn_comm* comm, double* d_inout, int32_t n_psets, void* stream);
+/* gcdyn_loglik_batch for a forest that is this rank's SHARD of the trees: `out_pset` receives the sums over all
+ * ranks' trees (partial sums -> peer all-reduce -> pinned host memory, one synchronisation); `out_tree_pset` and
+ * `status` stay per-shard.  Collective. */
+int  gcdyn_loglik_batch_sharded(gcdyn_ctx* ctx, const gcdyn_forest* forest, const gcdyn_params* params,
+                                double present_time, int method, const gcdyn_opts* opts, gcdyn_comm* comm,
+                                double* out_pset, double* out_tree_pset, int32_t* status);
 void gcdyn_comm_destroy(gcdyn_comm* comm);
 
 /* ---- device-resident random-walk Metropolis (BASELINE config 4) --------------------------

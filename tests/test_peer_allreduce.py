@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 WORKER = r"""
 import os, sys
-sys.path[:0] = [os.path.join(%(root)r, "gcdyn.jl_b200")]
+sys.path[:0] = [os.path.join("@ROOT@", "gcdyn.jl_b200")]
 import numpy as np, torch, torch.distributed as dist
 import gcdyn
 from gcdyn.sharding import PeerAllReduce
@@ -37,6 +37,20 @@ for it in range(40):                                 # many calls: sequence numb
     gathered = [None] * world
     dist.all_gather_object(gathered, got.tobytes())
     assert all(g == gathered[0] for g in gathered)   # bit-identical on every rank
+# the host-buffer entry point for a sharded forest: partial sums -> peer all-reduce -> pinned host memory
+from gcdyn.likelihood import evaluate, pack_params
+ts = np.linspace(-1.0, 1.0, 5)
+models = [gcdyn.SigmoidalBranchingProcess(1.2, 0.0, 2.0 + 0.1 * i, 0.5, 1.0, 1.0, 0.6, 0.2, ts) for i in range(9)]
+trees = gcdyn.rand_tree(models[0], 2.5, ts[2], 8, rng=np.random.default_rng(3))      # same forest on every rank
+whole = gcdyn.Forest(trees, ts, 2.5, ctx=ctx)
+shard = gcdyn.Forest(trees[rank::world], ts, 2.5, ctx=ctx)
+full, _, _ = evaluate(whole, pack_params(models), 2.5)
+for _ in range(3):
+    got, _, st = evaluate(shard, pack_params(models), 2.5, comm=peer)
+    assert not st.any() and np.max(np.abs(got - full) / np.abs(full)) <= 1e-12, (rank, got, full)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, got.tobytes())
+    assert all(g == gathered[0] for g in gathered)
 peer.close()
 dist.barrier()
 sys.stdout.write("rank%d-ok\n" % rank)
@@ -46,7 +60,7 @@ sys.stdout.write("rank%d-ok\n" % rank)
 def _run(world):
     import tempfile
     with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
-        f.write(WORKER % {"root": ROOT})
+        f.write(WORKER.replace("@ROOT@", ROOT))
         path = f.name
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + world), path]
