@@ -15,7 +15,7 @@ from .likelihood import (loglikelihood, naive_loglikelihood, stadler_appx_loglik
                          stadler_appx_unconditioned_loglikelihood, Forest, Context,
                          pack_params, DeviceParams, evaluate, evaluate_resident,
                          GcdynError, library_path)
-from .mcmc import random_walk_metropolis, MetropolisResult
+from .mcmc import random_walk_metropolis, device_metropolis, loglikelihood_gradient, MetropolisResult
 from .native_sim import simulate_flat
 
 __all__ = [

@@ -86,3 +86,25 @@ def test_device_resident_chain_equals_host_driven_and_oracle_chains(ctx):
         assert np.max(np.abs(dev.chain - host.chain)) <= 1e-12
         assert np.max(np.abs(dev.loglik - host.loglik) / np.abs(host.loglik)) <= 1e-10
         assert np.all(dev.chain[..., 1] >= lower[1]) and np.all(dev.chain[..., 1] <= upper[1])
+
+
+@pytest.mark.gpu
+def test_batched_finite_difference_gradient_matches_high_precision_oracle_gradient(ctx):
+    """13 parameter sets in one batch → log-likelihood + gradient; checked against Richardson-extrapolated central
+    differences of the oracle (scipy DOP853 at 1e-13), parameter by parameter."""
+    import oracle
+    from gcdyn.mcmc import loglikelihood_gradient
+    rng = np.random.default_rng(41)
+    tpl = _template()
+    T = 3.0
+    trees = gcdyn.rand_tree(tpl, T, tpl.type_space[2], 6, rng=rng)
+    forest = gcdyn.Forest(trees, tpl.type_space, T, ctx=ctx)
+    th = theta_of(tpl)
+    ll, grad = loglikelihood_gradient(forest, tpl, T, th)
+    f = lambda t: oracle.loglikelihood_shared(model_of(t, tpl), trees, T)
+    assert abs(ll - f(th)) <= 1e-10 * abs(ll)
+    for k in range(6):
+        e = np.zeros(6); e[k] = 1.0
+        d = lambda h: (f(th + h * e) - f(th - h * e)) / (2 * h)
+        want = (4.0 * d(1e-3) - d(2e-3)) / 3.0                    # O(h^4)
+        assert abs(grad[k] - want) <= 2e-6 * max(1.0, abs(want)), (k, grad[k], want)
