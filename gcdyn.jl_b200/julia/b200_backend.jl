@@ -263,3 +263,86 @@ stadler_appx_loglikelihood(model::AbstractBranchingProcess, tree::TreeNode, pres
     b200_evaluate([model], B200Forest(flatten([tree], model, present_time; method = :stadler)), present_time, GCDYN_METHOD_STADLER)[1][1]
 stadler_appx_unconditioned_loglikelihood(model::AbstractBranchingProcess, tree::TreeNode, present_time) =
     b200_evaluate([model], B200Forest(flatten([tree], model, present_time; method = :stadler)), present_time, GCDYN_METHOD_STADLER_UNCOND)[1][1]
+
+# ---- multi-GPU: one process per GPU, trees sharded; the [P] sums are combined by the library's peer-memory kernel ----
+
+"`gcdyn_comm_*`: `allgather_handles(handle::Vector{UInt8}) -> Vector{UInt8}` (world × 64 bytes, rank order) is supplied
+by the caller, e.g. `h -> MPI.Allgather(h, comm)`."
+mutable struct B200Comm
+    handle::Ptr{Cvoid}
+    function B200Comm(ctx::B200Context, rank::Integer, world::Integer, max_psets::Integer, allgather_handles)
+        mine = Vector{UInt8}(undef, 64)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:gcdyn_comm_create, LIBGCDYN), Cint, (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{UInt8}, Ref{Ptr{Cvoid}}),
+                   ctx.handle, rank, world, max_psets, mine, out)
+        rc == 0 || error(unsafe_string(ccall((:gcdyn_last_error, LIBGCDYN), Cstring, (Ptr{Cvoid},), ctx.handle)))
+        if world > 1
+            all = allgather_handles(mine)
+            rc = ccall((:gcdyn_comm_connect, LIBGCDYN), Cint, (Ptr{Cvoid}, Ptr{UInt8}), out[], all)
+            rc == 0 || error(unsafe_string(ccall((:gcdyn_last_error, LIBGCDYN), Cstring, (Ptr{Cvoid},), ctx.handle)))
+        end
+        c = new(out[])
+        finalizer(x -> ccall((:gcdyn_comm_destroy, LIBGCDYN), Cvoid, (Ptr{Cvoid},), x.handle), c)
+        return c
+    end
+end
+
+"Sharded batched entry: `forest` holds this rank's trees, the result is the sum over all ranks (collective)."
+function StatsAPI.loglikelihood(models::Vector{<:AbstractBranchingProcess}, forest::B200Forest, present_time, comm::B200Comm)
+    pp = pack_params(models)
+    out = Vector{Float64}(undef, pp.P)
+    GC.@preserve pp out begin
+        par = GcdynParams(pp.P, pp.K, 0, pp.stride, pointer(pp.lambda), C_NULL, C_NULL, C_NULL, C_NULL, C_NULL,
+                          pointer(pp.mu), pointer(pp.delta), pointer(pp.rho), pointer(pp.sigma), pointer(pp.Gamma))
+        rc = ccall((:gcdyn_loglik_batch_sharded, LIBGCDYN), Cint,
+                   (Ptr{Cvoid}, Ptr{Cvoid}, Ref{GcdynParams}, Cdouble, Cint, Ref{GcdynOpts}, Ptr{Cvoid},
+                    Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+                   forest.ctx.handle, forest.handle, par, Float64(present_time), GCDYN_METHOD_ODE, GcdynOpts(0, 0, 0.0, 0, 0),
+                   comm.handle, out, C_NULL, C_NULL)
+    end
+    rc == 0 || error(unsafe_string(ccall((:gcdyn_last_error, LIBGCDYN), Cstring, (Ptr{Cvoid},), forest.ctx.handle)))
+    return out
+end
+
+# ---- device-resident random-walk Metropolis (gcdyn_mh_*) -----------------------------------------------------------
+
+struct GcdynMhDesc
+    n_chains::Int32
+    n_types::Int32
+    type_space::Ptr{Float64}
+    Gamma::Ptr{Float64}
+    rho::Float64
+    sigma::Float64
+    theta0::Ptr{Float64}
+    lower::Ptr{Float64}
+    upper::Ptr{Float64}
+    step::Float64
+    seed::UInt64
+end
+
+"C chains over θ = (log xscale, xshift, log yscale, log yshift, log μ, log δ) of a `SigmoidalBranchingProcess`;
+returns (chain[6, C, iterations], loglik[C, iterations], accepted[C])."
+function b200_metropolis(template::SigmoidalBranchingProcess, forest::B200Forest, present_time, theta0::Matrix{Float64},
+                         iterations::Integer; step = 0.05, lower, upper, seed = 0, comm = nothing)
+    C = size(theta0, 2)                                   # column per chain: Julia [6, C] = C [C][6]
+    ts = collect(Float64, template.type_space); G = vec(collect(Float64, template.Γ))
+    lo = collect(Float64, lower); up = collect(Float64, upper)
+    mh = Ref{Ptr{Cvoid}}(C_NULL)
+    chain = Array{Float64}(undef, 6, C, iterations); ll = Matrix{Float64}(undef, C, iterations); acc = Vector{Int64}(undef, C)
+    GC.@preserve ts G lo up theta0 begin
+        d = GcdynMhDesc(C, length(ts), pointer(ts), pointer(G), template.ρ, template.σ, pointer(theta0), pointer(lo), pointer(up),
+                        step, UInt64(seed))
+        rc = ccall((:gcdyn_mh_create, LIBGCDYN), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{GcdynMhDesc}, Cdouble, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                   forest.ctx.handle, forest.handle, d, Float64(present_time), comm === nothing ? C_NULL : comm.handle, mh)
+        rc == 0 || error(unsafe_string(ccall((:gcdyn_last_error, LIBGCDYN), Cstring, (Ptr{Cvoid},), forest.ctx.handle)))
+    end
+    try
+        rc = ccall((:gcdyn_mh_run, LIBGCDYN), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}), mh[], iterations, chain, ll)
+        rc == 0 || error(unsafe_string(ccall((:gcdyn_last_error, LIBGCDYN), Cstring, (Ptr{Cvoid},), forest.ctx.handle)))
+        ccall((:gcdyn_mh_state, LIBGCDYN), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
+              mh[], C_NULL, C_NULL, acc, C_NULL)
+    finally
+        ccall((:gcdyn_mh_destroy, LIBGCDYN), Cvoid, (Ptr{Cvoid},), mh[])
+    end
+    return chain, ll, acc
+end
