@@ -307,17 +307,19 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, PsetPack pk,
     const int pst = pk.pstatus[p];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     double* orow = out_tree + (size_t)p * T;
+    double acc = 0.0;
+    bool have_acc = false;
     if (need_sweep[p] && !(pst & ST_SOLVER)) {
         const double* tp = tab + (size_t)p * tab_stride;
         const double* nt = pk.nt + (size_t)p * pk.ntw;
         const double lmusig = nt[K + K * K], lrho = nt[K + K * K + 1];
         const int S = pk.S[p];
         for (int64_t t = warp; t < T; t += nwarps) {
-            const double acc = tree_items_sum<M, false>(fv, tp, nt, K, S, S_cap, grid_doubles, Tpres, fv.item_off[t],
-                                                        fv.item_off[t + 1], lane);
+            const double isum = tree_items_sum<M, false>(fv, tp, nt, K, S, S_cap, grid_doubles, Tpres, fv.item_off[t],
+                                                         fv.item_off[t + 1], lane);
             if (lane == 0) {
                 const int rt = fv.root_type[t];
-                double r = acc + count_times_log(fv.n_death[t], lmusig) + count_times_log(fv.n_surv[t], lrho)
+                double r = isum + count_times_log(fv.n_death[t], lmusig) + count_times_log(fv.n_surv[t], lrho)
                            - (rt >= 0 ? pk.logcond[(size_t)p * K + rt] : CUDART_NAN);
                 int st = pst;
                 if (fv.self_loop[t]) st |= ST_SELF_LOOP;
@@ -328,21 +330,40 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, PsetPack pk,
             }
         }
     } else {
-        for (int64_t t = threadIdx.x; t < T; t += blockDim.x) {
-            double r = 0.0;
-            for (int z = 0; z < splits; ++z) r += partial[((size_t)z * P + p) * (size_t)T + t];
-            if (tree_const) r += tree_const[t];
-            int st = pst;
-            if (fv.self_loop[t]) st |= ST_SELF_LOOP;
-            if (st & (ST_SELF_LOOP | ST_SOLVER)) r = -CUDART_INF;
-            else if (r != r) st |= ST_DOMAIN;
-            orow[t] = r;
-            if (status) status[(size_t)p * T + t] = st;
+        // four trees per thread in flight (the partials come from L2); the per-pset sum accumulates the values just
+        // computed, in the same thread/tree assignment — and therefore the same order — as the re-read below
+        for (int64_t t0 = threadIdx.x; t0 < T; t0 += 4 * (int64_t)blockDim.x) {
+            double r[4];
+            int st[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t t = t0 + (int64_t)u * blockDim.x;
+                r[u] = 0.0;
+                st[u] = pst;
+                if (t < T) {
+                    for (int z = 0; z < splits; ++z) r[u] += __ldcg(partial + ((size_t)z * P + p) * (size_t)T + t);
+                    if (tree_const) r[u] += __ldg(tree_const + t);
+                    if (fv.self_loop[t]) st[u] |= ST_SELF_LOOP;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t t = t0 + (int64_t)u * blockDim.x;
+                if (t < T) {
+                    if (st[u] & (ST_SELF_LOOP | ST_SOLVER)) r[u] = -CUDART_INF;
+                    else if (r[u] != r[u]) st[u] |= ST_DOMAIN;
+                    orow[t] = r[u];
+                    if (status) status[(size_t)p * T + t] = st[u];
+                    acc += r[u];
+                }
+            }
         }
+        have_acc = true;
     }
-    __syncthreads();
-    double acc = 0.0;
-    for (int64_t t = threadIdx.x; t < T; t += blockDim.x) acc += orow[t];
+    if (!have_acc) {                                       // CTA-uniform: the fallback wrote orow warp by warp
+        __syncthreads();
+        for (int64_t t = threadIdx.x; t < T; t += blockDim.x) acc += orow[t];
+    }
     acc = warp_sum(acc);
     if (lane == 0) part[warp] = acc;
     __syncthreads();

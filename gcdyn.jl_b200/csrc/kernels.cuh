@@ -475,38 +475,19 @@ __device__ __forceinline__ void cheb_finish(const ParamsView& pv, const PsetPack
     }
     __syncthreads();
     TRACE_STAMP(8);
-    // effective degree: the largest d whose tail Σ_{k≥d}|a_k| exceeds tol (the sum runs downwards from D, so it is
-    // monotone).  nparts threads share a type: chunk sums first, then each rescans its chunk on top of the chunks
-    // above it.  The series counts as unresolved if its last three terms are not small.
-    {
-        const int nparts = max(1, min((int)blockDim.x / K, 8));
-        const int span = D - 8;                               // degrees 9..D
-        const int per = (span + nparts - 1) / nparts;
-        double* part = EO;                                    // [K][nparts], EO is dead after the DCT
-        for (int w = threadIdx.x; w < K * nparts; w += blockDim.x) {
-            const int x = w / nparts, q = w - x * nparts;
-            const int hi = D - q * per, lo = max(hi - per, 8);   // this chunk: degrees lo+1..hi
-            double sum = 0.0;
-            for (int d = hi; d > lo; --d) sum += fabs(Acoef[d * K + x]);
-            part[w] = sum;
+    // effective degree (a thread per type): the largest d whose tail Σ_{k≥d}|a_k| exceeds tol.  The sum runs downwards
+    // from D and stops at the first excess — for a resolved series that is after the D − d_eff smallest coefficients.
+    // The series counts as unresolved if its last three terms are not small.
+    for (int x = threadIdx.x; x < K; x += blockDim.x) {
+        const double last3 = fabs(Acoef[D * K + x]) + fabs(Acoef[(D - 1) * K + x]) + fabs(Acoef[(D - 2) * K + x]);
+        if (!(last3 <= cfg.tol)) atomicExch(&s_flag, 1);
+        double tail = 0.0;
+        int found = 8;
+        for (int d = D; d > 8; --d) {
+            tail += fabs(Acoef[d * K + x]);
+            if (!(tail <= cfg.tol)) { found = d; break; }
         }
-        __syncthreads();
-        for (int w = threadIdx.x; w < K * nparts; w += blockDim.x) {
-            const int x = w / nparts, q = w - x * nparts;
-            const int hi = D - q * per, lo = max(hi - per, 8);
-            double tail = 0.0;
-            for (int r = 0; r < q; ++r) tail += part[x * nparts + r];
-            int found = 8;
-            for (int d = hi; d > lo; --d) {
-                tail += fabs(Acoef[d * K + x]);
-                if (!(tail <= cfg.tol) && d > found) found = d;
-            }
-            if (found > 8) atomicMax(&s_deff, found);
-            if (q == 0) {
-                const double last3 = fabs(Acoef[D * K + x]) + fabs(Acoef[(D - 1) * K + x]) + fabs(Acoef[(D - 2) * K + x]);
-                if (!(last3 <= cfg.tol)) atomicExch(&s_flag, 1);
-            }
-        }
+        if (found > 8) atomicMax(&s_deff, found);
     }
     __syncthreads();
     TRACE_STAMP(9);
