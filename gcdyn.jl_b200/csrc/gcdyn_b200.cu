@@ -280,12 +280,16 @@ int carve_pack(gcdyn_ctx* ctx, int P, int K, PsetPack* pk) {
 size_t traj_smem_bytes(int K, int D, int S_cap, int M) {
     const size_t KS = ((size_t)K + 3) & ~(size_t)3;
     size_t n = 2 * KS + (K <= 32 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
-    // ring of published cells + their grid/flags (ChebSmem)
-    n += 2 * (size_t)S_cap + 4 + ((size_t)S_cap + 8) / 2 + (size_t)CHEB_RING_SLOTS * K * (M + 2);
-    if (D > 0)   // Chebyshev stage: cos table, node values / coefficients, folded halves, DCT matrix, two row buffers
-        n += 2 * (size_t)D + (((size_t)(D + 1) * K + 1) & ~(size_t)1) + ((size_t)D + 2) * K +
-             ((size_t)D / 2 + 1) * ((size_t)D + 4) + 2 * (size_t)K * (M + 2);
-    return n * sizeof(double);
+    // grid/flags of the published cells (ChebSmem)
+    n += 2 * (size_t)S_cap + 4 + ((size_t)S_cap + 8) / 2;
+    // ring of published cells + two row buffers while integrating; the folded DCT halves afterwards (same memory)
+    size_t region = (size_t)CHEB_RING_SLOTS * K * (M + 2);
+    if (D > 0) {
+        region = std::max(region + 2 * (size_t)K * (M + 2), ((size_t)D + 2) * K);
+        // cos table, node values / coefficients, DCT matrix
+        n += 2 * (size_t)D + (((size_t)(D + 1) * K + 1) & ~(size_t)1) + ((size_t)D / 2 + 1) * ((size_t)D + 4);
+    }
+    return (n + region) * sizeof(double);
 }
 
 template <int M, int KP, int KPL>

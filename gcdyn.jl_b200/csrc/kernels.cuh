@@ -296,16 +296,17 @@ struct ChebSmem {                      // carve-up of the stage's shared-memory 
         costab = sm;
         V = costab + 2 * D;
         if (D > 0) {
-            EO = V + ((((size_t)(D + 1) * K) + 1) & ~(size_t)1);
-            cosm = EO + 2 * (size_t)(H + 1) * K;
+            cosm = V + ((((size_t)(D + 1) * K) + 1) & ~(size_t)1);
             sgrid = cosm + (size_t)(H + 1) * (D + 4);
         } else {                                        // no Chebyshev stage: only the ring and its grid/flags exist
-            EO = cosm = sgrid = sm;
+            cosm = sgrid = sm;
         }
         shc = sgrid + (S_cap + 1);
         sflag = reinterpret_cast<int*>(sgrid + 2 * S_cap + 1);
         ring = sgrid + 2 * (S_cap + 1) + (((size_t)S_cap + 4) / 2 & ~(size_t)1);   // even offset: 16-byte aligned rows
         rowbuf = ring + (size_t)CHEB_RING_SLOTS * K * L;
+        EO = ring;     // the folded halves live where the ring and the row buffers were: those are dead once the
+                       // trajectory is complete (the host sizes the region as the larger of the two uses)
     }
 };
 
