@@ -278,8 +278,9 @@ int carve_pack(gcdyn_ctx* ctx, int P, int K, PsetPack* pk) {
 // Dynamic shared memory of traj_kernel: [ĉ broadcast buffer | δΓ (K > 32 only)] for the integrating warp, then the
 // Chebyshev stage's scratch [cos table | node values | coefficients | folded halves | grid].  Mirrors the kernel.
 size_t traj_smem_bytes(int K, int D, int S_cap, int M) {
-    const size_t KS = ((size_t)K + 3) & ~(size_t)3;
-    size_t n = 2 * KS + (K <= 32 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
+    // broadcast buffers (2 × KP, KP = K rounded up to the instantiated width) and, for K > 64, δΓ transposed
+    const size_t KP = K <= 32 ? (((size_t)K + 3) & ~(size_t)3) : (K <= 64 ? (((size_t)K + 7) & ~(size_t)7) : (((size_t)K + 3) & ~(size_t)3));
+    size_t n = 2 * KP + (K <= 64 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
     // grid/flags of the published cells (ChebSmem)
     n += 2 * (size_t)S_cap + 4 + ((size_t)S_cap + 8) / 2;
     // ring of published cells + two row buffers while integrating; the folded DCT halves afterwards (same memory)
@@ -292,13 +293,13 @@ size_t traj_smem_bytes(int K, int D, int S_cap, int M) {
     return (n + region) * sizeof(double);
 }
 
-template <int M, int KP, int KPL>
+template <int M, int KP, int KPL, int NPW = 1>
 int launch_traj_inst(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, const ChebCfg& cc,
                      double* tab, cudaStream_t st) {
     const size_t smem = traj_smem_bytes(pv.K, cc.D, cfg.S_cap, M);
     if (smem > 48 * 1024)
-        CU_TRY(ctx, cudaFuncSetAttribute(traj_kernel<M, KP, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    traj_kernel<M, KP, KPL><<<pv.P, TRAJ_THREADS, smem, st>>>(pv, pk, cfg, cc, tab);
+        CU_TRY(ctx, cudaFuncSetAttribute(traj_kernel<M, KP, KPL, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    traj_kernel<M, KP, KPL, NPW><<<pv.P, TRAJ_THREADS, smem, st>>>(pv, pk, cfg, cc, tab);
     CU_TRY(ctx, cudaGetLastError());
     return GCDYN_OK;
 }
@@ -315,7 +316,11 @@ int launch_traj_m(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, cons
     if (K <= 24) return launch_traj_inst<M, 24, 1>(ctx, pv, pk, cfg, cc, tab, st);
     if (K <= 28) return launch_traj_inst<M, 28, 1>(ctx, pv, pk, cfg, cc, tab, st);
     if (K <= 32) return launch_traj_inst<M, 32, 1>(ctx, pv, pk, cfg, cc, tab, st);
-    if (K <= 64) return launch_traj_inst<M, 0, 2>(ctx, pv, pk, cfg, cc, tab, st);
+    // 32 < K ≤ 64: two integrating warps, one type per thread, δΓ row in registers
+    if (K <= 40) return launch_traj_inst<M, 40, 1, 2>(ctx, pv, pk, cfg, cc, tab, st);
+    if (K <= 48) return launch_traj_inst<M, 48, 1, 2>(ctx, pv, pk, cfg, cc, tab, st);
+    if (K <= 56) return launch_traj_inst<M, 56, 1, 2>(ctx, pv, pk, cfg, cc, tab, st);
+    if (K <= 64) return launch_traj_inst<M, 64, 1, 2>(ctx, pv, pk, cfg, cc, tab, st);
     return launch_traj_inst<M, 0, 4>(ctx, pv, pk, cfg, cc, tab, st);
 }
 

@@ -539,8 +539,11 @@ __device__ __forceinline__ void cheb_finish(const ParamsView& pv, const PsetPack
 }
 
 // ------------------------------------------------------------------------------------------------
-// traj_kernel: one CTA of 4 warps per pset; warp 0 integrates (the others wait at the barrier), then the whole
-// CTA runs the Chebyshev stage.  Within warp 0; lane l owns types l, l+32, … (KPL per lane).
+// traj_kernel: one CTA of 4 warps per pset.  NPW warps integrate — one (K ≤ 32: lane l owns type l; K > 64: lane l
+// owns types l, l+32, …, KPL per lane, δΓ in shared memory) or two (32 < K ≤ 64: thread t of the pair owns type t and
+// keeps its row of δΓ in registers; the pair exchanges ĉ_n through shared memory and a named barrier per Taylor
+// stage) — the other warps build the table and the Chebyshev node values behind them; then the whole CTA finishes the
+// Chebyshev stage.
 //
 // Taylor recurrence for the h-scaled coefficients ĉ_n of p(τ_s + θh) = Σ ĉ_n θ^n:
 //   ĉ_{n+1} = h/(n+1) · [ −(λ+μ) ĉ_n + [n=0] μ(1−σ) + λ Σ_{m≤n} ĉ_m ĉ_{n−m} + δ Γ ĉ_n ]
@@ -551,11 +554,13 @@ __device__ __forceinline__ void cheb_finish(const ParamsView& pv, const PsetPack
 // KPL == 1 (K ≤ KP ≤ 32): the lane's row of δΓ lives in registers, ĉ_n is broadcast through shared memory.
 // KPL  > 1: δΓ is staged transposed in shared memory (lane-contiguous rows).
 // ------------------------------------------------------------------------------------------------
-template <int M, int KP, int KPL>
+template <int M, int KP, int KPL, int NPW>
 __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetPack pk, TrajCfg cfg, ChebCfg cc,
                                                             double* __restrict__ tab) {
     extern __shared__ __align__(16) double smem[];
     constexpr int L = M + 2;
+    constexpr int NPROD = 32 * NPW, NCONS = TRAJ_THREADS - NPROD;   // integrating / consumer threads
+    static_assert(NPW == 1 || (NPW == 2 && KPL == 1), "two integrating warps own one type per lane");
     const int p = blockIdx.x;
     const int K = pv.K;
 #ifdef GCDYN_TRAJ_TRACE
@@ -582,26 +587,65 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
     }
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int i = 0; i < CHEB_RING_SLOTS; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, TRAJ_THREADS - 32); }
+        for (int i = 0; i < CHEB_RING_SLOTS; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, NCONS); }
     }
     __syncthreads();
     pdl_launch_dependents();                            // the contraction's CTAs may become resident behind this grid
-    int pw = 0;
+    // roles: prod_rank = 0..NPW−1 for the integrating warps (−1 otherwise), cons_rank = 0.. for the others
+    int pw = 0, prod_rank = -1, cons_rank = -1;
     {
         int lo = s_wid[0];
 #pragma unroll
         for (int w = 1; w < TRAJ_THREADS / 32; ++w) lo = min(lo, s_wid[w]);
-        const int want = (lo >> 2) & 3;
+        bool isp[TRAJ_THREADS / 32];
+        int np = 0;
+        if (NPW == 1) {
+            const int want = (lo >> 2) & 3;
 #pragma unroll
-        for (int w = TRAJ_THREADS / 32 - 1; w >= 0; --w) if ((s_wid[w] & 3) == want) pw = w;
+            for (int w = TRAJ_THREADS / 32 - 1; w >= 0; --w) if ((s_wid[w] & 3) == want) pw = w;
+#pragma unroll
+            for (int w = 0; w < TRAJ_THREADS / 32; ++w) isp[w] = (w == pw);
+            np = 1;
+        } else {
+            // two CTAs on an SM: one integrates on sub-partitions {0,1}, the other on {2,3}
+            const int want = ((lo >> 2) & 1) * 2;
+#pragma unroll
+            for (int w = 0; w < TRAJ_THREADS / 32; ++w) { isp[w] = ((s_wid[w] & 3) >> 1) == (want >> 1); np += isp[w] ? 1 : 0; }
+            if (np != NPW) {                            // irregular slot allocation: any two warps will do
+#pragma unroll
+                for (int w = 0; w < TRAJ_THREADS / 32; ++w) isp[w] = w < NPW;
+            }
+        }
+        int pr = 0, cr = 0;
+#pragma unroll
+        for (int w = 0; w < TRAJ_THREADS / 32; ++w) {
+            if (w == warp) { if (isp[w]) prod_rank = pr; else cons_rank = cr; }
+            if (isp[w]) ++pr; else ++cr;
+        }
     }
-    if (warp != pw) {
-        const int ct = (warp < pw ? warp : warp - 1) * 32 + lane;
-        prep_pset(pv, pk, p, 0, ct, TRAJ_THREADS - 32, false);
-        cell_consume<M>(pv, cfg, cc, cheb, p, tab, cs, s_full, s_empty, ct, TRAJ_THREADS - 32);
+    if (prod_rank < 0) {
+        const int ct = cons_rank * 32 + lane;
+        prep_pset(pv, pk, p, 0, ct, NCONS, false);
+        cell_consume<M>(pv, cfg, cc, cheb, p, tab, cs, s_full, s_empty, ct, NCONS);
     }
     TRACE_STAMP(1);
-    if (warp == pw) {
+    if (prod_rank >= 0) {
+    const int pt = prod_rank * 32 + lane;               // index among the integrating threads
+    // exchange between the integrating warps (NPW == 2): named barrier 2 and a double-buffered pair of slots
+    __shared__ unsigned long long s_xch[2][2];
+    int xtog = 0;
+    auto prod_sync = [&]() {
+        if (NPW == 1) __syncwarp();
+        else asm volatile("bar.sync 2, %0;" ::"r"(NPROD) : "memory");
+    };
+    auto prod_max_u64 = [&](unsigned long long v) -> unsigned long long {      // v is already warp-uniform
+        if (NPW == 1) return v;
+        if (lane == 0) s_xch[xtog][prod_rank] = v;
+        asm volatile("bar.sync 2, %0;" ::"r"(NPROD) : "memory");
+        const unsigned long long a0 = s_xch[xtog][0], a1 = s_xch[xtog][1];
+        xtog ^= 1;
+        return a0 > a1 ? a0 : a1;
+    };
     const int KS = KPL == 1 ? KP : ((K + 3) & ~3);     // broadcast buffer length (multiple of 4)
     double* cb = smem;                                  // 2 × KS
     double* GT = smem + 2 * KS;                         // KPL > 1 only: GT[j*K + i] = δ Γ[i,j]
@@ -615,7 +659,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
     double rate = 0.0;
 #pragma unroll
     for (int q = 0; q < KPL; ++q) {
-        const int i = lane + 32 * q;
+        const int i = pt + NPROD * q;
         own[q] = i < K;
         lam[q] = own[q] ? birth_rate(pv, p, i) : 0.0;
         const double gam = own[q] ? delta * -G[i + (size_t)i * K] : 0.0;
@@ -625,16 +669,19 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
         if (!(r <= rate)) rate = r;
     }
     rate = warp_max_nan(rate);
+    if (NPW > 1) {                                      // non-negative doubles (and NaN) order like their bit patterns
+        rate = __longlong_as_double((long long)prod_max_u64((unsigned long long)__double_as_longlong(fabs(rate))));
+    }
 
     double g[KPL == 1 ? KP : 1];
     if constexpr (KPL == 1) {
 #pragma unroll
-        for (int j = 0; j < KP; ++j) g[j] = (own[0] && j < K) ? delta * G[lane + (size_t)j * K] : 0.0;
+        for (int j = 0; j < KP; ++j) g[j] = (own[0] && j < K) ? delta * G[pt + (size_t)j * K] : 0.0;
     } else {
         for (int e = lane; e < K * K; e += 32) GT[e] = delta * G[e];   // G[i + j*K] → GT[j*K + i]
     }
-    for (int e = lane; e < 2 * KS; e += 32) cb[e] = 0.0;
-    __syncwarp();
+    for (int e = pt; e < 2 * KS; e += NPROD) cb[e] = 0.0;
+    prod_sync();
 
     const bool adaptive = cfg.S_fixed <= 0;
     // (the table block of this pset — [τ_s | 1/h_s | pad][rows (cell, type) of L doubles] — is written by the consumers)
@@ -673,8 +720,8 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
             double* buf = cb + (n & 1) * KS;
 #pragma unroll
             for (int q = 0; q < KPL; ++q)
-                if (own[q]) buf[lane + 32 * q] = c[n][q];
-            __syncwarp();
+                if (own[q]) buf[pt + NPROD * q] = c[n][q];
+            prod_sync();
             double dot[KPL];
             if constexpr (KPL == 1) {
                 double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
@@ -694,7 +741,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
                 for (int q = 0; q < KPL; ++q) d[q][0] = d[q][1] = 0.0;
                 int irow[KPL];
 #pragma unroll
-                for (int q = 0; q < KPL; ++q) irow[q] = own[q] ? lane + 32 * q : 0;
+                for (int q = 0; q < KPL; ++q) irow[q] = own[q] ? pt + NPROD * q : 0;
                 int j = 0;
 #pragma unroll 4
                 for (; j + 1 < K; j += 2) {
@@ -743,7 +790,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
             const double v = fabs(c[M][q]) + fabs(c[M - 1][q]);
             if (own[q] && !(v <= ind)) ind = v;
         }
-        const unsigned ind_hi = __reduce_max_sync(FULL, (unsigned)__double2hiint(ind));
+        const unsigned ind_hi = (unsigned)prod_max_u64(__reduce_max_sync(FULL, (unsigned)__double2hiint(ind)));
         const float ind_l2 = (float)((int)ind_hi - 0x3ff00000) * (1.0f / 1048576.0f);
         const float ratio = exp2f((tol_l2 - ind_l2) * (1.0f / (float)M));     // ≈ (tol/ind)^(1/M)
         if (adaptive && !(ind_hi < tol_hi)) {
@@ -769,18 +816,18 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
 #pragma unroll
             for (int q = 0; q < KPL; ++q) {
                 if (own[q]) {
-                    double2* dst = reinterpret_cast<double2*>(slot + (size_t)(lane + 32 * q) * L);
+                    double2* dst = reinterpret_cast<double2*>(slot + (size_t)(pt + NPROD * q) * L);
 #pragma unroll
                     for (int n = 0; n < M; n += 2) dst[n >> 1] = make_double2(c[n][q], c[n + 1][q]);
                     dst[M >> 1] = make_double2(c[M][q], 0.0);
                 }
             }
-            if (lane == 0) {
+            if (pt == 0) {
                 cs.sgrid[s] = tau; cs.sgrid[s + 1] = last ? cfg.T : tau + hc; cs.shc[s] = hc;
                 cs.sflag[s] = last ? CELL_LAST : 0;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_full + slot_i);
+            prod_sync();
+            if (pt == 0) mbar_arrive(s_full + slot_i);
         }
 #pragma unroll
         for (int q = 0; q < KPL; ++q) {
@@ -809,7 +856,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
     if (failed) {                                       // tell the consumers to stop (the regular exit flagged its last cell)
         const int slot_i = s % CHEB_RING_SLOTS;
         if (s >= CHEB_RING_SLOTS) mbar_wait(s_empty + slot_i, (uint32_t)(s / CHEB_RING_SLOTS - 1) & 1u);
-        if (lane == 0) { cs.sflag[s] = CELL_FAIL; mbar_arrive(s_full + slot_i); }
+        if (pt == 0) { cs.sflag[s] = CELL_FAIL; mbar_arrive(s_full + slot_i); }
     }
     TRACE_STAMP(3);
 #ifdef GCDYN_TRAJ_TRACE
@@ -818,17 +865,17 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
     // conditioning term and diagnostics
 #pragma unroll
     for (int q = 0; q < KPL; ++q) {
-        const int i = lane + 32 * q;
+        const int i = pt + NPROD * q;
         if (own[q]) pk.logcond[(size_t)p * K + i] = log1p(-pcur[q]);   // log(1 − p_i(T)), mbp.jl:244-245
     }
     const bool unresolved = failed || !(errmax_hi < tol_hi);
-    const bool anybad = __any_sync(FULL, bad) || unresolved;
-    if (lane == 0) {
+    const bool anybad = prod_max_u64(__any_sync(FULL, bad) ? 1ULL : 0ULL) != 0ULL || unresolved;
+    if (pt == 0) {
         pk.perr[p] = __hiloint2double((int)min(errmax_hi + 1u, 0x7ff00000u), 0);   // upper bound of the largest accepted indicator
         pk.S[p] = s > 0 ? s : 1;
         pk.pstatus[p] = anybad ? ST_SOLVER : 0;
     }
-    }   // warp 0
+    }   // integrating warps
     if (!cheb) return;
     __syncthreads();                                    // node values, status of this pset are complete and visible
     TRACE_STAMP(4);
