@@ -16,7 +16,7 @@
 //                                                            with a shared Γ the Σ count·log Γ_xy part is a
 //                                                            per-tree constant added in the GEMM epilogue)
 // Psets whose series is not resolved, or whose node-term logs are not finite where the forest needs them,
-// are re-done by sweep_kernel (exact item sums).
+// are re-done exactly (item sums from the Taylor table) inside finish_kernel.
 #pragma once
 #include "kernels.cuh"
 

@@ -1,16 +1,22 @@
 // Device kernels of libgcdyn_b200 (sm_100a, FP64).  See DESIGN.md §3-§5.
 //
 // Pipeline of one batched ODE likelihood evaluation (P parameter sets × T trees):
-//   traj_kernel   per pset (one warp): rates and node-term logs (λ, μ, γ of mbp.jl:27-97), then a
-//                 Taylor-series integration of the extinction ODE (dp_dt!, mbp.jl:266-278) on a uniform
-//                 grid of S_p cells with S_p chosen adaptively per pset; emits, per cell and type, the
-//                 polynomial of F_x(τ) = ∫(−Λ_x + 2 λ_x p_x) — the branch density of dp_logq_dt!,
-//                 mbp.jl:285-300 — and log(1 − p_x(T)) (mbp.jl:244-245)
+//   traj_kernel   one CTA of four warps per pset.  One warp (two for 32 < K ≤ 64) integrates the extinction ODE
+//                 (dp_dt!, mbp.jl:266-278) with a fixed-order Taylor series on an adaptive grid of cells and
+//                 publishes every accepted cell through a shared-memory ring; the other warps compute rates and
+//                 node-term logs (λ, μ, γ of mbp.jl:27-97), build per cell and type the polynomial of
+//                 F_x(τ) = ∫(−Λ_x + 2 λ_x p_x) — the branch density of dp_logq_dt!, mbp.jl:285-300 — write that
+//                 table, and evaluate F at the Chebyshev nodes; the CTA then produces the pset's row of GEMM
+//                 coefficients (cheb_gemm.cuh) and log(1 − p_x(T)) (mbp.jl:244-245)
+//   gemm_kernel   (cheb_gemm.cuh) LL[p][t] = Σ_j A[p][j]·Mt[t][j] with DMMA, split over the column range
+//   finish_kernel (cheb_gemm.cuh) combines the splits, applies −Inf/status rules, recomputes flagged psets exactly
+//                 from the table, and sums over trees → out_pset[p]   (mbp.jl:258)
+// Small batches without cached moments, or GCDYN_FLAG_SWEEP_ONLY:
 //   sweep_kernel  persistent CTAs over (pset, tree-chunk) units; the pset's table is staged into shared
 //                 memory by the bulk-copy engine (cp.async.bulk + mbarrier); a warp per tree sums
 //                 w·F_type(τ) + node terms (mbp.jl:167-191) over the tree's lookup items,
 //                 warp-shuffle reduction → out_tree[p*T + t]
-//   reduce_kernel per pset: fixed-order sum over trees → out_pset[p]   (mbp.jl:258)
+//   reduce_kernel per pset: fixed-order sum over trees → out_pset[p]
 #pragma once
 #include <cstdint>
 #include <cstdio>
