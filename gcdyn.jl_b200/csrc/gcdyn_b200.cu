@@ -1453,6 +1453,21 @@ extern "C" int gcdyn_mh_state(gcdyn_mh* m, double* theta, double* loglik, int64_
     GUARD_END(ctx)
 }
 
+extern "C" int gcdyn_mh_restore(gcdyn_mh* m, const double* theta, const double* loglik, const int64_t* accepted, int64_t iteration) {
+    gcdyn_ctx* ctx = m ? m->ctx : nullptr;
+    GUARD_BEGIN
+    if (!m || !theta || !loglik || !accepted || iteration < 0) return fail(ctx, GCDYN_EINVAL, "bad argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaMemcpy(m->v.theta, theta, (size_t)m->C * gcdyn::MH_DIM * 8, cudaMemcpyHostToDevice));
+    CU_TRY(ctx, cudaMemcpy(m->v.ll, loglik, (size_t)m->C * 8, cudaMemcpyHostToDevice));
+    CU_TRY(ctx, cudaMemcpy(m->v.accepted, accepted, (size_t)m->C * 8, cudaMemcpyHostToDevice));
+    m->iteration = iteration;
+    m->have_ll = true;
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
 extern "C" void gcdyn_mh_destroy(gcdyn_mh* m) {
     if (!m) return;
     int prev = 0;

@@ -134,6 +134,7 @@ def _lib():
         "gcdyn_mh_create": (C.c_int, [vp, vp, C.POINTER(MhDesc), C.c_double, vp, C.POINTER(vp)]),
         "gcdyn_mh_run": (C.c_int, [vp, C.c_int64, _p_f64, _p_f64]),
         "gcdyn_mh_state": (C.c_int, [vp, _p_f64, _p_f64, _p_i64, _p_i64]),
+        "gcdyn_mh_restore": (C.c_int, [vp, _p_f64, _p_f64, _p_i64, C.c_int64]),
         "gcdyn_mh_destroy": (None, [vp]),
     }
     for name, (res, args) in sig.items():

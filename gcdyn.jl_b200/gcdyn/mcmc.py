@@ -82,10 +82,12 @@ class CounterRNG:
 
 
 def device_metropolis(forest: Forest, template: SigmoidalBranchingProcess, present_time, theta0, iterations, *,
-                      step=0.05, lower, upper, seed=0, comm=None, history=True) -> MetropolisResult:
+                      step=0.05, lower, upper, seed=0, comm=None, history=True, checkpoint=None) -> MetropolisResult:
     """`gcdyn_mh_*`: the same sampler as `random_walk_metropolis(..., rng="counter")`, but proposals, likelihood,
     all-reduce (`comm`: a `gcdyn.sharding.PeerAllReduce` when the forest is a shard) and accept/reject all run on
-    the device; the host only enqueues.  `upper[2:]` must be finite."""
+    the device; the host only enqueues.  `upper[2:]` must be finite.  `checkpoint` = the `.checkpoint` of an earlier
+    result: the chains continue from there with the random numbers of the following iterations, so a split run
+    reproduces an uninterrupted one."""
     import ctypes as C
     from .likelihood import MhDesc, _lib, _check, _ptr, _p_f64, _p_i64
     lib = _lib()
@@ -104,7 +106,12 @@ def device_metropolis(forest: Forest, template: SigmoidalBranchingProcess, prese
                                comm._h if comm is not None else None, C.byref(h)), ctxh)
     try:
         th = np.empty((n, 6)); ll = np.empty(n); acc = np.zeros(n, dtype=np.int64); it = C.c_int64()
-        _check(lib.gcdyn_mh_run(h, 0, None, None), ctxh)          # initial log-likelihood
+        if checkpoint is not None:
+            cth, cll, cacc, cit = checkpoint
+            _check(lib.gcdyn_mh_restore(h, _ptr(np.ascontiguousarray(cth, dtype=np.float64), _p_f64),
+                                        _ptr(np.ascontiguousarray(cll, dtype=np.float64), _p_f64),
+                                        _ptr(np.ascontiguousarray(cacc, dtype=np.int64), _p_i64), int(cit)), ctxh)
+        _check(lib.gcdyn_mh_run(h, 0, None, None), ctxh)          # initial log-likelihood (kept when restored)
         _check(lib.gcdyn_mh_state(h, _ptr(th, _p_f64), _ptr(ll, _p_f64), _ptr(acc, _p_i64), C.byref(it)), ctxh)
         if history:
             chain = np.empty((iterations + 1, n, 6)); lls = np.empty((iterations + 1, n))
@@ -117,7 +124,9 @@ def device_metropolis(forest: Forest, template: SigmoidalBranchingProcess, prese
             chain, lls = th[None].copy(), ll[None].copy()
     finally:
         lib.gcdyn_mh_destroy(h)
-    return MetropolisResult(chain=chain, loglik=lls, accepted=acc)
+    res = MetropolisResult(chain=chain, loglik=lls, accepted=acc)
+    res.checkpoint = (th.copy(), ll.copy(), acc.copy(), int(it.value))
+    return res
 
 
 def random_walk_metropolis(forest: Forest, template: SigmoidalBranchingProcess, present_time, theta0,

@@ -252,6 +252,9 @@ int  gcdyn_mh_create(gcdyn_ctx* ctx, const gcdyn_forest* forest, const gcdyn_mh_
 int  gcdyn_mh_run(gcdyn_mh* mh, int64_t iterations, double* theta_hist, double* loglik_hist);
 /* Current state: theta [n_chains*6], loglik [n_chains], accepted [n_chains] (host; any may be NULL). */
 int  gcdyn_mh_state(gcdyn_mh* mh, double* theta, double* loglik, int64_t* accepted, int64_t* iteration);
+/* Restore a checkpoint written from gcdyn_mh_state: the chain continues with the random numbers of iteration+1, so a
+ * restored run reproduces an uninterrupted one. */
+int  gcdyn_mh_restore(gcdyn_mh* mh, const double* theta, const double* loglik, const int64_t* accepted, int64_t iteration);
 void gcdyn_mh_destroy(gcdyn_mh* mh);
 
 #ifdef __cplusplus

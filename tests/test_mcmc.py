@@ -108,3 +108,24 @@ def test_batched_finite_difference_gradient_matches_high_precision_oracle_gradie
         d = lambda h: (f(th + h * e) - f(th - h * e)) / (2 * h)
         want = (4.0 * d(1e-3) - d(2e-3)) / 3.0                    # O(h^4)
         assert abs(grad[k] - want) <= 2e-6 * max(1.0, abs(want)), (k, grad[k], want)
+
+
+@pytest.mark.gpu
+def test_device_chain_resumes_from_a_checkpoint(ctx):
+    """30 iterations in one go == 12 iterations, checkpoint, new sampler, restore, 18 more (same counter-based stream)."""
+    from gcdyn.mcmc import device_metropolis
+    rng = np.random.default_rng(35)
+    tpl = _template()
+    T = 3.0
+    trees = gcdyn.rand_tree(tpl, T, tpl.type_space[2], 8, rng=rng)
+    forest = gcdyn.Forest(trees, tpl.type_space, T, ctx=ctx)
+    th = theta_of(tpl)
+    kw = dict(step=0.04, seed=23, lower=th - 0.6, upper=th + 0.6)
+    th0 = th + 0.03 * rng.standard_normal((8, 6))
+    whole = device_metropolis(forest, tpl, T, th0, 30, **kw)
+    first = device_metropolis(forest, tpl, T, th0, 12, **kw)
+    rest = device_metropolis(forest, tpl, T, th0, 18, checkpoint=first.checkpoint, **kw)
+    assert first.checkpoint[3] == 12 and rest.checkpoint[3] == 30
+    assert np.array_equal(first.chain, whole.chain[:13])
+    assert np.array_equal(rest.chain[1:], whole.chain[13:]) and np.array_equal(rest.loglik[1:], whole.loglik[13:])
+    assert np.array_equal(rest.accepted, whole.accepted)
