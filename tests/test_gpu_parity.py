@@ -289,7 +289,7 @@ def test_edge_cases(ctx):
 
 
 def test_many_types_uses_multi_type_lanes(ctx):
-    """K = 40 (> 32): two types per lane in the trajectory kernel."""
+    """K = 40 (32 < K ≤ 64): two integrating warps, one type per thread; K = 70 (> 64): several types per lane."""
     import oracle
     rng = np.random.default_rng(14)
     K = 40
@@ -306,6 +306,32 @@ def test_many_types_uses_multi_type_lanes(ctx):
     got = gcdyn.loglikelihood(model, trees, 2.5)
     want = oracle.loglikelihood_shared(model, trees, 2.5)
     assert abs(got - want) <= SUM_RTOL * abs(want)
+
+
+@pytest.mark.parametrize("K,order", [(33, 16), (48, 8), (64, 24), (65, 16), (32, 20)])
+def test_type_count_boundaries_of_the_trajectory_kernel(ctx, K, order):
+    """The kernel switches layout at K = 32 (one warp) / 33..64 (two integrating warps, register rows of width 40, 48,
+    56, 64) / 65.. (types strided over lanes, δΓ in shared memory).  Each side of every boundary: batch of 9 psets
+    through the GEMM path == the item sweep, one pset == the oracle, a failed pset does not stall the others."""
+    import oracle
+    rng = np.random.default_rng(100 + K)
+    ts = np.linspace(-2, 2, K)
+    mk = lambda f: gcdyn.SigmoidalBranchingProcess(1.5, 0.0, 2.5 * f, 0.5, 1.0, 1.0, 0.5, 0.1, ts)
+    models = [mk(f) for f in np.linspace(0.85, 1.15, 9)]
+    trees = gcdyn.rand_tree(models[4], 2.5, ts[K // 2], 4, rng=rng)
+    forest = gcdyn.Forest(trees, ts, 2.5, ctx=ctx)
+    params = pack_params(models)
+    out, tp, st = evaluate(forest, params, 2.5, per_tree=True, order=order)
+    out_s, tp_s, st_s = evaluate(forest, params, 2.5, per_tree=True, order=order, flags=4)
+    assert not st.any() and not st_s.any()
+    assert rel(tp, tp_s) <= 1e-10
+    want = oracle.loglikelihood_shared(models[2], trees, 2.5)
+    assert abs(out[2] - want) <= SUM_RTOL * abs(want)
+    params.mu = params.mu.copy()
+    params.mu[6] = np.nan
+    out_b, _, st_b = evaluate(forest, params, 2.5, per_tree=True, order=order)
+    keep = np.arange(9) != 6
+    assert np.all(st_b[6] & 2) and np.isneginf(out_b[6]) and np.array_equal(out_b[keep], out[keep])
 
 
 def test_shards_sum_to_the_whole(ctx):
