@@ -273,14 +273,26 @@ class PackedParams:
     def __init__(self, **kw):
         self.__dict__.update(kw)
 
+    _FIELDS = ("lam", "xscale", "xshift", "yscale", "yshift", "type_space", "mu", "delta", "rho", "sigma", "Gamma")
+
     def struct(self):
-        return Params(
+        """The `gcdyn_params` view of the arrays.  Building the ctypes pointers costs more than a small evaluation
+        takes on the GPU, so the struct is cached for as long as the SAME array objects are attached (the cache
+        keeps them alive, so an identity check is enough; their contents may change freely)."""
+        arrays = tuple(getattr(self, f) for f in self._FIELDS)
+        scalars = (self.n_psets, self.n_types, self.response, self.gamma_pset_stride)
+        cache = self.__dict__.get("_struct_cache")
+        if cache is not None and cache[1] == scalars and all(a is b for a, b in zip(cache[0], arrays)):
+            return cache[2]
+        st = Params(
             n_psets=self.n_psets, n_types=self.n_types, response=self.response,
             gamma_pset_stride=self.gamma_pset_stride,
             lambda_=_ptr(self.lam, _p_f64), xscale=_ptr(self.xscale, _p_f64), xshift=_ptr(self.xshift, _p_f64),
             yscale=_ptr(self.yscale, _p_f64), yshift=_ptr(self.yshift, _p_f64),
             type_space=_ptr(self.type_space, _p_f64), mu=_ptr(self.mu, _p_f64), delta=_ptr(self.delta, _p_f64),
             rho=_ptr(self.rho, _p_f64), sigma=_ptr(self.sigma, _p_f64), Gamma=_ptr(self.Gamma, _p_f64))
+        self.__dict__["_struct_cache"] = (arrays, scalars, st)
+        return st
 
 
 def pack_params(models, response="table"):
