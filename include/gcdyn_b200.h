@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GCDYN_B200_VERSION 100  /* major*100 + minor */
+#define GCDYN_B200_VERSION 110  /* major*100 + minor; 1.10 adds gcdyn_comm_*, gcdyn_loglik_batch_sharded, gcdyn_mh_* */
 
 /* return codes */
 #define GCDYN_OK            0
