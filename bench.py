@@ -122,6 +122,16 @@ def cpu_reference_rate(flat, par, T, n_trees, n_psets, nthreads=None):
     return n_trees * n_psets / dt, dt
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown CPU"
+
+
 def cpu_baseline(flat, par, T, budget_s=12.0):
     cores = host_threads()
     n_trees = min(flat.n_trees, 64)
@@ -136,11 +146,17 @@ def cpu_baseline(flat, par, T, budget_s=12.0):
         else:
             n_psets = int(min(P, max(n_psets + 1, n_psets * grow)))
         rate, dt = cpu_reference_rate(flat, par, T, n_trees, n_psets)
+    # the reference itself is serial (mbp.jl:258): one thread on a smaller sample of the same workload
+    n1 = max(8, int(min(Tn, n_trees * n_psets / max(cores, 1) / 4)))
+    rate1, dt1 = cpu_reference_rate(flat, par, T, min(n1, Tn), 1, nthreads=1)
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "single_thread_value": rate1,
             "sample": f"first {n_trees} trees x first {n_psets} parameter sets of the same workload, "
-                      f"{dt:.1f} s, oracle/refcpu.c (C restatement of mbp.jl:110-259 as written: one adaptive "
-                      f"RK5(4) solve per node, reltol=abstol=1e-3), OpenMP over (tree,pset) pairs; "
-                      f"the real Julia reference cannot run in this image"}
+                      f"{dt:.1f} s on {cores} threads of {cpu_model()}, oracle/refcpu.c (C restatement of mbp.jl:110-259 as "
+                      f"written: one adaptive RK5(4) solve per node, reltol=abstol=1e-3), OpenMP over (tree,pset) pairs; "
+                      f"single_thread_value: first {min(n1, Tn)} trees x 1 parameter set, {dt1:.1f} s on one thread "
+                      f"(the reference is serial); the real Julia reference cannot run in this image "
+                      f"(bench/ref_julia.jl times it for readers who have Julia, unexecuted here)"}
 
 
 def run_reference(args):
