@@ -366,3 +366,35 @@ def test_failed_trajectory_in_a_gemm_batch_does_not_stall_the_other_warps(ctx):
     # the same through the item sweep (no Chebyshev stage: the consumers only build the table)
     out_s, _, st_s = evaluate(forest, bad, T, per_tree=True, flags=4)
     assert np.all(st_s[4] & 2) and np.isneginf(out_s[4]) and rel(out_s[keep], good[keep]) <= 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [12, 40, 70])
+def test_per_pset_gamma_and_device_sigmoid_across_kernel_layouts(ctx, K):
+    """Every pset with its OWN mutation matrix (K² type-change columns in the GEMM, Γ read per pset by the integrating
+    and the table-building warps) and the sigmoid evaluated on the device, in each layout of the trajectory kernel."""
+    import oracle
+    rng = np.random.default_rng(200 + K)
+    ts = np.linspace(-2, 2, K)
+
+    def gamma(seed):
+        g = np.random.default_rng(seed).uniform(0.2, 1.0, (K, K))
+        np.fill_diagonal(g, 0.0)
+        g /= g.sum(axis=1, keepdims=True)
+        np.fill_diagonal(g, -1.0)
+        return g
+
+    models = [gcdyn.SigmoidalBranchingProcess(1.5, 0.1 * i, 2.5, 0.5, 1.0, 0.8 + 0.05 * i, gamma(i), 0.5, 0.1, ts)
+              for i in range(9)]
+    trees = gcdyn.rand_tree(models[0], 2.5, ts[K // 2], 5, rng=rng)
+    forest = gcdyn.Forest(trees, ts, 2.5, ctx=ctx)
+    p_tab, p_sig = pack_params(models), pack_params(models, response="sigmoid")
+    assert p_tab.gamma_pset_stride == K * K
+    out, tp, st = evaluate(forest, p_tab, 2.5, per_tree=True)
+    out_sig, _, _ = evaluate(forest, p_sig, 2.5)
+    out_sw, tp_sw, _ = evaluate(forest, p_tab, 2.5, per_tree=True, flags=4)
+    assert not st.any()
+    assert rel(out_sig, out) <= 1e-12 and rel(tp, tp_sw) <= 1e-10
+    for i in (0, 8):
+        want = oracle.loglikelihood_shared(models[i], trees, 2.5)
+        assert abs(out[i] - want) <= SUM_RTOL * abs(want), i
