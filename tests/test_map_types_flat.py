@@ -62,3 +62,37 @@ def test_likelihood_of_a_flat_rebinned_forest(ctx):
     got = gcdyn.loglikelihood(coarse, f1, T)
     want = gcdyn.loglikelihood(coarse, [gcdyn.map_types(lambda x: float(centres[binof(x)]), t) for t in trees], T)
     assert got == want
+
+
+def _hand_tree():
+    """root(1.0) → tc(→2.0) → tc(→3.0) → birth → [tc(→1.0) → survivor, death]; types on a 3-point space."""
+    N = gcdyn.TreeNode
+    r = N("root", 0.0, 1.0)
+    a = N("type_change", 0.4, 2.0); gcdyn.attach(r, a)
+    b = N("type_change", 0.7, 3.0); gcdyn.attach(a, b)
+    c = N("birth", 1.0, 3.0); gcdyn.attach(b, c)
+    d = N("type_change", 1.5, 1.0); gcdyn.attach(c, d)
+    gcdyn.attach(d, N("sampled_survival", 2.0, 1.0))
+    gcdyn.attach(c, N("sampled_death", 1.8, 3.0))
+    return r
+
+
+@pytest.mark.parametrize("bins", [
+    {1.0: 1.0, 2.0: 1.0, 3.0: 3.0},      # the TOP node becomes a self-loop: its child moves up to the root
+    {1.0: 1.0, 2.0: 3.0, 3.0: 3.0},      # the second type change of a chain disappears
+    {1.0: 2.0, 2.0: 2.0, 3.0: 2.0},      # everything collapses: every type change is pruned, child order changes
+])
+def test_hand_built_chains_of_type_changes(bins):
+    ts_old = np.array([1.0, 2.0, 3.0])
+    ts_new = np.array(sorted(set(bins.values())))
+    T = 2.0
+    tree = _hand_tree()
+    flat = flatten([tree], ts_old, T)
+    imap = np.array([int(np.nonzero(ts_new == bins[x])[0][0]) for x in ts_old])
+    for prune in (True, False):
+        got = map_types_flat(flat, imap, len(ts_new), prune_self_loops=prune)
+        want = flatten([gcdyn.map_types(lambda x: bins[x], tree, prune_self_loops=prune)], ts_new, T)
+        for f in FIELDS:
+            assert np.array_equal(getattr(got, f), getattr(want, f)), (f, prune, bins)
+    pruned = map_types_flat(flat, imap, len(ts_new))
+    assert pruned.n_nodes == flat.n_nodes - sum(1 for a, b in ((1.0, 2.0), (2.0, 3.0), (3.0, 1.0)) if bins[a] == bins[b])
