@@ -65,7 +65,7 @@ def _run(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + world), path]
     try:
-        r = subprocess.run(cmd, env=dict(os.environ), capture_output=True, text=True, timeout=300)
+        r = subprocess.run(cmd, env=dict(os.environ), capture_output=True, text=True, timeout=100)
     finally:
         os.unlink(path)
     # every assertion lives in the workers; torchrun exits non-zero if any rank fails
