@@ -1468,6 +1468,10 @@ extern "C" int gcdyn_mh_restore(gcdyn_mh* m, const double* theta, const double* 
     GUARD_END(ctx)
 }
 
+extern "C" double gcdyn_mh_uniform(uint64_t seed, uint64_t iteration, uint64_t chain, uint64_t slot) {
+    return gcdyn::mh_uniform(seed, iteration, chain, slot);
+}
+
 extern "C" void gcdyn_mh_destroy(gcdyn_mh* m) {
     if (!m) return;
     int prev = 0;

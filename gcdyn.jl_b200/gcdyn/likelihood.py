@@ -136,6 +136,7 @@ def _lib():
         "gcdyn_mh_state": (C.c_int, [vp, _p_f64, _p_f64, _p_i64, _p_i64]),
         "gcdyn_mh_restore": (C.c_int, [vp, _p_f64, _p_f64, _p_i64, C.c_int64]),
         "gcdyn_mh_destroy": (None, [vp]),
+        "gcdyn_mh_uniform": (C.c_double, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)       # AttributeError here = header and library out of sync

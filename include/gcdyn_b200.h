@@ -256,6 +256,9 @@ int  gcdyn_mh_state(gcdyn_mh* mh, double* theta, double* loglik, int64_t* accept
  * restored run reproduces an uninterrupted one. */
 int  gcdyn_mh_restore(gcdyn_mh* mh, const double* theta, const double* loglik, const int64_t* accepted, int64_t iteration);
 void gcdyn_mh_destroy(gcdyn_mh* mh);
+/* The sampler's counter-based uniform in (0,1) for (seed, iteration, chain, slot), computed on the host with the same
+ * code the kernels run (slots 2j, 2j+1: Box-Muller pair of coordinate j; slot 12: the accept draw).  No device needed. */
+double gcdyn_mh_uniform(uint64_t seed, uint64_t iteration, uint64_t chain, uint64_t slot);
 
 #ifdef __cplusplus
 }

@@ -129,3 +129,20 @@ def test_device_chain_resumes_from_a_checkpoint(ctx):
     assert np.array_equal(first.chain, whole.chain[:13])
     assert np.array_equal(rest.chain[1:], whole.chain[13:]) and np.array_equal(rest.loglik[1:], whole.loglik[13:])
     assert np.array_equal(rest.accepted, whole.accepted)
+
+
+def test_counter_rng_mirror_is_bit_identical_to_the_library():
+    """`CounterRNG.uniform` (NumPy) against `gcdyn_mh_uniform` (the kernels' own hash, compiled for the host): same bits."""
+    from gcdyn.likelihood import _lib
+    from gcdyn.mcmc import CounterRNG
+    lib = _lib()
+    rng = np.random.default_rng(0)
+    for seed in (0, 1, 21, 2**63 + 12345, 2**64 - 1):
+        r = CounterRNG(seed)
+        its = rng.integers(0, 2**40, 50)
+        chains = rng.integers(0, 70000, 50)
+        slots = rng.integers(0, 13, 50)
+        for it, c, s in zip(its, chains, slots):
+            want = lib.gcdyn_mh_uniform(int(seed) & (2**64 - 1), int(it), int(c), int(s))
+            got = float(r.uniform(int(it), np.array([c]), np.array([s]))[0])
+            assert got == want and 0.0 < got < 1.0
