@@ -70,3 +70,27 @@ def test_chebyshev_moment_model_matches_oracle(name, key):
         assert tail <= 1e-11 and rel(out, exp[key][p]) <= 1e-10
         # an unresolved series announces itself through its tail (what triggers the sweep fallback on the GPU)
         assert tail16 > 1e-9 and rel(coarse, exp[key][p]) > rel(out, exp[key][p])
+
+
+def test_high_word_log2_used_by_the_step_controller():
+    """traj_kernel's step control reads log2(ind) off the HIGH WORD of the double: (hi − 0x3ff00000)/2^20 = exponent +
+    linear mantissa.  Error < 0.0861 (the classic bound of log2(1+m) − m), monotone in x, so (tol/ind)^(1/M) is within
+    0.8 % for M ≥ 16 and the accept test hi(ind) < hi(tol) is never looser than ind < tol."""
+    import numpy as np
+    x = np.concatenate([np.exp(np.random.default_rng(0).uniform(np.log(1e-300), np.log(1e300), 200000)),
+                        [1e-11, 2.3546e-12, 1.0, 0.5, 2.0 ** -1022]])
+    hi = (x.view(np.uint64) >> np.uint64(32)).astype(np.int64)
+    approx = (hi - 0x3FF00000) / 2.0 ** 20
+    err = np.log2(x) - approx
+    assert err.min() >= -1e-6 and err.max() < 0.0861          # the truncated low word only lowers approx by < 2^-20
+    order = np.argsort(x)
+    assert np.all(np.diff(hi[order]) >= 0)                     # monotone: integer compare == ordering of the doubles
+    for M in (8, 12, 16, 20, 24):
+        worst = 2.0 ** (0.0861 * 2 / M) - 1.0                  # both tol and ind are approximated
+        assert worst < (0.016 if M == 8 else 0.011 if M == 12 else 0.0076)
+    tol = 1e-11
+    tol_hi = int(np.array([tol]).view(np.uint64)[0] >> np.uint64(32))
+    accepted = x[hi < tol_hi]
+    assert accepted.max() < tol                                # never accepts what ind ≤ tol would reject
+    rejected_below_tol = x[(hi >= tol_hi) & (x < tol)]
+    assert rejected_below_tol.size == 0 or rejected_below_tol.min() > tol * (1 - 2e-6)
