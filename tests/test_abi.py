@@ -60,3 +60,21 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(d, f), encoding="utf-8").read()
                 assert not re.search(r"(import|from)\s+(oracle|refcpu|algo_model)\b", text), f
                 assert "librefcpu" not in text, f
+
+
+def test_header_is_plain_c99_and_cxx11(tmp_path):
+    """The boundary is a C ABI: the header must compile on its own as strict C99 (what a Julia/C consumer sees) and as
+    C++11, warnings as errors."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "gcdyn_b200.h"\n'
+                   'int main(void) { gcdyn_opts o = {0, 0, 0.0, 0, 0}; gcdyn_mh_desc d; gcdyn_params p; gcdyn_forest_desc f;\n'
+                   '  (void)o; (void)d; (void)p; (void)f; return GCDYN_B200_VERSION >= 110 ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-c", str(src),
+                    "-o", str(tmp_path / "a.o")], check=True)
+    subprocess.run(["g++", "-std=c++11", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-x", "c++", "-c", str(src),
+                    "-o", str(tmp_path / "b.o")], check=True)
