@@ -38,6 +38,50 @@ def test_ctypes_structs_match_header_layout():
     assert ctypes.sizeof(likelihood.Opts) == 4 + 4 + 8 + 4 + 4
 
 
+def test_ctypes_field_offsets_equal_the_c_compiler_s(tmp_path):
+    """Offsets of every field of the four boundary structs as gcc lays them out == offsets of the ctypes mirrors, in order."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    header = open(os.path.join(ROOT, "include", "gcdyn_b200.h")).read()
+    structs = {"gcdyn_forest_desc": likelihood.ForestDesc, "gcdyn_params": likelihood.Params,
+               "gcdyn_opts": likelihood.Opts, "gcdyn_mh_desc": likelihood.MhDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gcdyn_b200.h"', 'int main(void) {']
+    names = {}
+    for cname in structs:
+        end = header.index("} %s;" % cname)
+        start = header.rindex("typedef struct {", 0, end) + len("typedef struct {")
+        body = header[start:end]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):                      # "double rho, sigma" declares two fields
+                fields.append(re.findall(r"[A-Za-z_][A-Za-z_0-9]*", part)[-1])
+        names[cname] = fields
+        for f in fields:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, f, cname, f))
+        lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "off.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "off"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for line in out.splitlines():
+        c, f, v = line.split()
+        got.setdefault(c, []).append((f, int(v)))
+    for cname, cls in structs.items():
+        c_offsets = [v for f, v in got[cname] if f != "sizeof"]
+        py_offsets = [getattr(cls, f).offset for f, _ in cls._fields_]
+        assert c_offsets == py_offsets, (cname, names[cname], c_offsets, py_offsets)
+        assert dict(got[cname])["sizeof"] == ctypes.sizeof(cls), cname
+
+
 def test_no_cpu_fallback_without_a_device():
     lib = likelihood._lib()
     if lib.gcdyn_device_count() > 0:
