@@ -122,3 +122,32 @@ def test_header_is_plain_c99_and_cxx11(tmp_path):
                     "-o", str(tmp_path / "a.o")], check=True)
     subprocess.run(["g++", "-std=c++11", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-x", "c++", "-c", str(src),
                     "-o", str(tmp_path / "b.o")], check=True)
+
+
+def test_julia_struct_mirrors_follow_the_header():
+    """The Julia backend cannot be executed here; at least its `struct` mirrors must list the header's fields in the header's
+    order with layout-compatible types (a `ccall` passes them by reference)."""
+    header = open(os.path.join(ROOT, "include", "gcdyn_b200.h")).read()
+    julia = open(os.path.join(ROOT, "gcdyn.jl_b200", "julia", "b200_backend.jl")).read()
+    pairs = {"gcdyn_forest_desc": "GcdynForestDesc", "gcdyn_params": "GcdynParams", "gcdyn_opts": "GcdynOpts",
+             "gcdyn_mh_desc": "GcdynMhDesc"}
+    ctype = {"int32_t": "Int32", "int64_t": "Int64", "uint64_t": "UInt64", "double": "Float64", "uint8_t": "UInt8"}
+    for cname, jname in pairs.items():
+        end = header.index("} %s;" % cname)
+        body = header[header.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        want = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            base = re.match(r"(const\s+)?([A-Za-z_0-9]+)", decl).group(2)
+            for part in decl.split(","):
+                name = re.findall(r"[A-Za-z_][A-Za-z_0-9]*", part)[-1]
+                is_ptr = "*" in part or ("*" in decl.split(",")[0] and part is decl.split(",")[0])
+                want.append((name, "Ptr{%s}" % ctype[base] if is_ptr else ctype[base]))
+        jbody = re.search(r"^struct %s\n(.*?)^end" % jname, julia, re.S | re.M).group(1)
+        got = [tuple(x.strip().split("::")) for x in jbody.strip().splitlines()]
+        assert [g[0] for g in got] == [w[0] for w in want], (cname, got, want)
+        for (gn, gt), (wn, wt) in zip(got, want):
+            assert gt == wt or (wt.startswith("Ptr") and gt.startswith("Ptr")), (cname, gn, gt, wt)
