@@ -151,3 +151,30 @@ def test_julia_struct_mirrors_follow_the_header():
         assert [g[0] for g in got] == [w[0] for w in want], (cname, got, want)
         for (gn, gt), (wn, wt) in zip(got, want):
             assert gt == wt or (wt.startswith("Ptr") and gt.startswith("Ptr")), (cname, gn, gt, wt)
+
+
+def test_julia_ccalls_pass_as_many_arguments_as_the_header_declares():
+    header = open(os.path.join(ROOT, "include", "gcdyn_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    julia = open(os.path.join(ROOT, "gcdyn.jl_b200", "julia", "b200_backend.jl")).read()
+    declared = {}
+    for m in re.finditer(r"\b(gcdyn_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, re.S):
+        args = m.group(2).strip()
+        declared[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    used = 0
+    for m in re.finditer(r"ccall\(\(:(gcdyn_[a-z0-9_]+), LIBGCDYN\),\s*[A-Za-z]+,\s*\(", julia):
+        name = m.group(1)
+        i, depth, start = m.end(), 1, m.end()
+        while depth:                                   # the matching ')' of the argument-type tuple
+            depth += {"(": 1, ")": -1}.get(julia[i], 0)
+            i += 1
+        types = julia[start:i - 1]
+        flat, d = [], 0
+        for ch in types:                               # commas at depth 0 separate types (Ptr{...}, Ref{...} have none inside)
+            d += {"{": 1, "}": -1}.get(ch, 0)
+            flat.append("," if (ch == "," and d == 0) else ch if ch != "," else ";")
+        n = len([t for t in "".join(flat).split(",") if t.strip()])
+        assert name in declared, name
+        assert n == declared[name], (name, n, declared[name], types)
+        used += 1
+    assert used >= 12
