@@ -1,5 +1,8 @@
-"""Phase timing of traj_kernel (clock64 stamps, -DGCDYN_TRAJ_TRACE build):
-GCDYN_B200_LIB=tools/_trace/libgcdyn_trace.so python tools/trace_probe.py"""
+"""Phase timing of traj_kernel (clock64 stamps per pset, dumped through gcdyn_trace_dump).  Needs the trace build:
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fopenmp -shared -lgomp \
+       -DGCDYN_TRAJ_TRACE -o tools/_trace/libgcdyn_trace.so gcdyn.jl_b200/csrc/gcdyn_b200.cu
+  GCDYN_B200_LIB=tools/_trace/libgcdyn_trace.so python tools/trace_probe.py
+The stamps perturb the kernel (≈1.5× slower); use the numbers relative to each other."""
 import sys, ctypes as C
 sys.path[:0] = ["/root/repo", "/root/repo/gcdyn.jl_b200"]
 import numpy as np, torch, gcdyn, workloads
