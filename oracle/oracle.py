@@ -463,3 +463,68 @@ def loglik_flat_shared(flat, par, p, present_time, rtol=1e-13, atol=1e-13):
     sums = np.add.reduceat(contrib, tree_off[:-1]) if n else np.zeros(len(tree_off) - 1)
     pT = sol.sol(T)[:K]
     return sums - np.log1p(-pT)[g("root_type_idx")]
+
+
+def alt_flat(flat, par, p, present_time, method):
+    """Per-tree values [T] of the alternates (extra_likelihoods.jl:10-34, :45-102, :115-151) for parameter set `p` on a
+    flattened forest — the per-node formulas of `naive_loglikelihood` / `_stadler_sum` above applied node by node.
+    method ∈ {"naive", "stadler", "stadler_uncond"(= "stadler_unconditioned")}."""
+    g = lambda name: np.asarray(getattr(flat, name) if hasattr(flat, name) else flat[name])
+    G = np.asarray(par["Gamma"], dtype=np.float64)
+    G = G[p] if G.ndim == 3 else G
+    m = Params(par["lam"][p], par["mu"][p], par["delta"][p], G, par["rho"][p], par["sigma"][p],
+               np.arange(len(par["lam"][p])))
+    ev, xs, ys = g("event"), g("btype_idx"), g("type_idx")
+    ts, te, off = g("t_start"), g("t_end"), g("tree_off")
+    names = EVENTS
+    out = np.zeros(len(off) - 1)
+    T = present_time
+    for t in range(len(off) - 1):
+        result = 0.0
+        for i in range(int(off[t]), int(off[t + 1])):
+            x, y, e = int(xs[i]), int(ys[i]), names[int(ev[i])]
+            lam, mu, gam = m.lam[x], m.mu, m.gamma_out(x)
+            Lam = lam + mu + gam
+            rate = 0.0 if y == x else (m.gamma_to(x, y) if y >= 0 else float("nan"))
+            if method == "naive":
+                dt = te[i] - ts[i]
+                if e == "birth":
+                    result += _exp_logpdf(1 / Lam, dt) + _log(lam / Lam)
+                elif e == "sampled_death":
+                    result += _exp_logpdf(1 / Lam, dt) + _log(mu / Lam)
+                elif e == "type_change":
+                    result += _exp_logpdf(1 / Lam, dt) + _log(rate) - _log(Lam)
+                elif e == "sampled_survival":
+                    result += _exp_logccdf_as_written(1 / Lam, dt) + _log(m.rho)
+                elif e == "unsampled_survival":
+                    result += _exp_logccdf_as_written(1 / Lam, dt) + _log(1 - m.rho)
+                else:
+                    raise ValueError(f"Tree contains incompatible event {e}")
+            else:
+                c = math.sqrt(Lam ** 2 - 4 * mu * (1 - m.sigma) * lam)
+                xx, yy = (-Lam - c) / 2, (-Lam + c) / 2
+                helper = lambda tt: (yy + lam * (1 - m.rho)) * math.exp(-c * tt) - xx - lam * (1 - m.rho)
+                t_s, t_e = T - ts[i], T - te[i]
+                result += c * (t_e - t_s) + 2 * (_log(helper(t_e)) - _log(helper(t_s)))
+                if e == "birth":
+                    result += _log(lam)
+                elif e == "sampled_death":
+                    result += _log(m.sigma) + _log(mu)
+                elif e == "type_change":
+                    result += _log(rate)
+                elif e == "sampled_survival":
+                    result += _log(m.rho)
+                else:
+                    raise ValueError(f"Tree contains incompatible event {e}")
+        if method == "stadler":
+            r = int(g("root_type_idx")[t])
+            lam, mu, gam = m.lam[r], m.mu, m.gamma_out(r)
+            Lam = lam + mu + gam
+            c = math.sqrt(Lam ** 2 - 4 * mu * (1 - m.sigma) * lam)
+            xx, yy = (-Lam - c) / 2, (-Lam + c) / 2
+            rt = T - 0
+            pr = (-1 / lam * ((yy + lam * (1 - m.rho)) * xx * math.exp(-c * rt) - yy * (xx + lam * (1 - m.rho)))
+                  / ((yy + lam * (1 - m.rho)) * math.exp(-c * rt) - (xx + lam * (1 - m.rho))))
+            result -= _log(1 - pr)
+        out[t] = result
+    return out
