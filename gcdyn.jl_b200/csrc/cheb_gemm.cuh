@@ -1,9 +1,11 @@
 // Chebyshev-moment formulation of the per-tree sums.
 //
-// F_x(τ) is smooth on [0, T], so for every parameter set it is represented by ONE Chebyshev series per type,
-//     F_x(τ) ≈ Σ_{d≤D} a[p][d][x] · T_d(u),  u = 2τ/T − 1,
-// and the per-tree sum over lookup items becomes a dense contraction with pset-independent per-tree
-// statistics Mt[t][d][x] = Σ_{items of tree t, type x} w · T_d(u_item):
+// F_x(τ) is smooth on [0, T], so for every parameter set it is represented by ONE degree-D polynomial per type — the
+// interpolant through the D+1 Chebyshev–Gauss–Lobatto nodes τ_k = T(1 + cos(πk/D))/2,
+//     F_x(τ) ≈ Σ_k F_x(τ_k) · ℓ_k(u),  u = 2τ/T − 1,   ℓ_k(u) = (2/D) w_k Σ''_d cos(πkd/D) T_d(u),
+// and the per-tree sum over lookup items becomes a dense contraction with pset-independent per-tree statistics in the
+// NODAL basis, Mt[t][k][x] = Σ_{items of tree t, type x} w · ℓ_k(u_item) (built once per forest from the Chebyshev
+// moments Σ w·T_d(u_item) by one cosine transform), against the node values the trajectory kernel produces anyway:
 //     LL[p][t] = Σ_j A[p][j] · Mt[t][j]
 // i.e. a [P × J] · [J × T] FP64 GEMM executed with DMMA (mma.sync.m8n8k4.f64).  Column space j:
 //     [0, K)            births by branch type            ×  log λ_x                      (mbp.jl:175)
@@ -11,7 +13,7 @@
 //     [K+2, 2K+2)       root type one-hot                 ×  −log(1 − p_x(T))             (mbp.jl:244-245)
 //     2K+2              number of type changes            ×  log δ   (only when Γ is shared by all psets)
 //     2K+3              padding
-//     [C1, C1+(Dcap+1)K)  Chebyshev moments, degree-major ×  a[d][x]
+//     [C1, C1+(D+1)K)   nodal moments, node-major           ×  F_x(τ_k)
 //     [Jtc, Jtc+K²)     type changes x→y                  ×  log δΓ_xy  (only when every pset has its own Γ;
 //                                                            with a shared Γ the Σ count·log Γ_xy part is a
 //                                                            per-tree constant added in the GEMM epilogue)
@@ -137,13 +139,103 @@ __global__ void __launch_bounds__(256) moments_kernel(ForestView fv, double T, i
     }
 }
 
-// column sums: colsum[c] = Σ_t Mt[t][c]  (one thread per column, fixed order)
-__global__ void colsum_kernel(const double* __restrict__ Mt, int64_t T, long long Jst, double* __restrict__ colsum) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Jst) return;
+// nodal_transform_kernel: one CTA per tree, in place: Chebyshev moments M[d][x] → nodal moments
+//     N[k][x] = (2/D) w_k Σ''_{d ≤ D} cos(πkd/D) M[d][x]        (Σ'': d = 0 and d = D halved;  w_0 = w_D = 1/2)
+// so that Σ_k f(τ_k) N[k][x] = Σ''_d a_d M[d][x] with a_d the Chebyshev coefficients of the interpolant through f(τ_k).
+__global__ void __launch_bounds__(256) nodal_transform_kernel(int K, int D, int C1, long long Jst, double* __restrict__ Mt) {
+    extern __shared__ __align__(16) double nsm[];          // [2D] cos table | [(D+1)*K] moments of this tree
+    double* ctab = nsm;
+    double* Mo = nsm + 2 * D;
+    double* row = Mt + (size_t)blockIdx.x * Jst + C1;
+    const int NV = (D + 1) * K;
+    for (int m = threadIdx.x; m < 2 * D; m += blockDim.x) ctab[m] = cospi((double)m / (double)D);
+    for (int i = threadIdx.x; i < NV; i += blockDim.x) Mo[i] = row[i];
+    __syncthreads();
+    const double scale = 2.0 / (double)D;
+    for (int i = threadIdx.x; i < NV; i += blockDim.x) {
+        const int k = i / K, x = i - k * K;
+        double s0 = 0.0, s1 = 0.0;
+        int idx = 0;                                        // (k·d) mod 2D
+        for (int d = 0; d <= D; ++d) {
+            const double wd = (d == 0 || d == D) ? 0.5 : 1.0;
+            const double t = wd * Mo[d * K + x] * ctab[idx];
+            if (d & 1) s1 += t; else s0 += t;
+            idx += k;
+            if (idx >= 2 * D) idx -= 2 * D;
+        }
+        const double wk = (k == 0 || k == D) ? 0.5 : 1.0;
+        row[i] = scale * wk * (s0 + s1);
+    }
+}
+
+// column sums: colsum[c] = Σ_t Mt[t][c].  A CTA owns 32 columns; its 8 warps take the trees t ≡ w (mod 8) in order,
+// then the 8 partial sums are added in warp order: fixed order, coalesced rows.
+__global__ void __launch_bounds__(256) colsum_kernel(const double* __restrict__ Mt, int64_t T, long long Jst,
+                                                     double* __restrict__ colsum) {
+    __shared__ double part[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long c = (long long)blockIdx.x * 32 + lane;
     double s = 0.0;
-    for (int64_t t = 0; t < T; ++t) s += Mt[(size_t)t * Jst + c];
-    colsum[c] = s;
+    if (c < Jst)
+        for (int64_t t = w; t < T; t += 8) s += Mt[(size_t)t * Jst + c];
+    part[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && c < Jst) {
+        double tot = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += part[i][lane];
+        colsum[c] = tot;
+    }
+}
+
+// degree_probe_kernel (one CTA, off the critical path, run now and then): full Chebyshev coefficients of a few psets'
+// interpolants from their node values → the smallest degree whose tail Σ_{k>d}|a_k| is below tol for every sampled pset
+// and type.  The host reads the result (pinned memory) at a later call and re-sizes the nodal grid when a smaller one
+// suffices.  out[0] = that degree, out[1] = the grid degree it was measured on.
+__global__ void __launch_bounds__(512) degree_probe_kernel(const double* __restrict__ A, MomentView mv, const int* __restrict__ need_sweep,
+                                                           int P, double tol, int* __restrict__ out) {
+    extern __shared__ __align__(16) double psm[];          // [2D] cos | [(D+1)*K] values | [(D+1)*K] |a_d|
+    const int K = mv.K, D = mv.D, NV = (D + 1) * K;
+    double* ctab = psm;
+    double* V = psm + 2 * D;
+    double* Ac = V + NV;
+    __shared__ int s_deff;
+    if (threadIdx.x == 0) s_deff = 4;
+    for (int m = threadIdx.x; m < 2 * D; m += blockDim.x) ctab[m] = cospi((double)m / (double)D);
+    const int nsample = P < 16 ? P : 16;
+    for (int si = 0; si < nsample; ++si) {
+        const int p = (int)((long long)si * P / nsample);
+        __syncthreads();
+        if (need_sweep[p]) continue;                       // CTA-uniform
+        const double* row = A + (size_t)p * mv.Jst + mv.C1;
+        for (int i = threadIdx.x; i < NV; i += blockDim.x) V[i] = row[i];
+        __syncthreads();
+        for (int i = threadIdx.x; i < NV; i += blockDim.x) {
+            const int d = i / K, x = i - d * K;
+            double s0 = 0.0, s1 = 0.0;
+            int idx = 0;
+            for (int k = 0; k <= D; ++k) {
+                const double wk = (k == 0 || k == D) ? 0.5 : 1.0;
+                const double t = wk * V[k * K + x] * ctab[idx];
+                if (k & 1) s1 += t; else s0 += t;
+                idx += d;
+                if (idx >= 2 * D) idx -= 2 * D;
+            }
+            Ac[i] = fabs((2.0 / (double)D) * (s0 + s1)) * ((d == 0 || d == D) ? 0.5 : 1.0);
+        }
+        __syncthreads();
+        for (int x = threadIdx.x; x < K; x += blockDim.x) {
+            double tail = 0.0;
+            int found = 4;
+            for (int d = D; d > 4; --d) {
+                tail += Ac[d * K + x];
+                if (!(tail <= tol)) { found = d; break; }
+            }
+            atomicMax(&s_deff, found);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { out[0] = s_deff; out[1] = D; }
 }
 
 // Shared Γ: per-tree constant Σ_{x→y} count · log Γ_xy (the pset-independent part of Σ log δΓ_xy), one warp per tree.
@@ -188,8 +280,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 
 // blockIdx.z = split of the column range (split-K): each split writes its own partial[z][p][t]; finish_kernel adds them.
 __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A, MomentView mv, int use_tc_block,
-                                                   const int* __restrict__ d_common, int P, int64_t T,
-                                                   double* __restrict__ partial) {
+                                                   int P, int64_t T, double* __restrict__ partial) {
     extern __shared__ __align__(16) double gsm[];          // GT_STAGES × (A tile | B tile)
     auto As = [&](int st) { return gsm + (size_t)st * 2 * GT_TILE * GT_LD; };
     auto Bs = [&](int st) { return gsm + (size_t)st * 2 * GT_TILE * GT_LD + GT_TILE * GT_LD; };
@@ -198,13 +289,10 @@ __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A,
     const int64_t t0 = (int64_t)blockIdx.x * GT_TILE;
     const long long Jst = mv.Jst;
     const double* Mt = mv.Mt;
-    pdl_wait();                                            // A, d_common come from the trajectory kernel
+    pdl_wait();                                            // A comes from the trajectory kernel
     pdl_launch_dependents();
-    // segment 1: count columns + Chebyshev columns up to the batch's effective degree; segment 2: K² block
-    long long J1 = mv.C1 + (long long)(*d_common + 1) * mv.K;
-    J1 = (J1 + 3) & ~3LL;
-    const long long J1max = (mv.C1 + (long long)(mv.Dcap + 1) * mv.K + 3) & ~3LL;
-    if (J1 > J1max) J1 = J1max;
+    // segment 1: count columns + nodal columns; segment 2: K² block
+    const long long J1 = mv.J1;
     const int n1 = (int)((J1 + GT_KC - 1) / GT_KC);
     const long long J2 = use_tc_block ? ((long long)mv.K * mv.K + 3) & ~3LL : 0;
     const int n2 = (int)((J2 + GT_KC - 1) / GT_KC);
@@ -287,11 +375,11 @@ __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A,
 // over trees → out_pset[p] (mbp.jl:258), in the same order reduce_kernel uses.
 // ------------------------------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(256) finish_kernel(ForestView fv, PsetPack pk, const double* __restrict__ tab,
+__global__ void __launch_bounds__(256) finish_kernel(ForestView fv, ParamsView pv, PsetPack pk, const double* __restrict__ tab,
                                                      long long tab_stride, int S_cap, int grid_doubles, double Tpres,
                                                      const double* __restrict__ partial, int splits,
                                                      const double* __restrict__ tree_const,
-                                                     const int* __restrict__ need_sweep, int P,
+                                                     const int* __restrict__ need_sweep, int P, int D, int* __restrict__ nflag, int* __restrict__ feedback,
                                                      double* __restrict__ out_tree, int32_t* __restrict__ status,
                                                      double* __restrict__ out_pset) {
     __shared__ double part[8];
@@ -299,17 +387,22 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, PsetPack pk,
     const int K = fv.K;
     const int64_t T = fv.n_trees;
     pdl_wait();                                            // partial sums come from the contraction
-    if (blockIdx.x == 0 && threadIdx.x == 0) {             // leave d_common zeroed for the next evaluation
-        int* dc = const_cast<int*>(need_sweep) + P;
-        dc[1] = dc[0];
-        dc[0] = 0;
-    }
     const int pst = pk.pstatus[p];
+    // psets whose interpolant was not resolved on this grid are summed exactly below.  When they are a quarter of the
+    // batch the grid no longer fits the parameters: tell the host (pinned word), the next call widens it.
+    if (threadIdx.x == 0 && feedback && (need_sweep[p] & 1) && !(pst & ST_SOLVER)) {
+        const int before = atomicAdd(nflag, 1);
+        if (4 * before < P && 4 * (before + 1) >= P) *feedback = D;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     double* orow = out_tree + (size_t)p * T;
     double acc = 0.0;
     bool have_acc = false;
     if (need_sweep[p] && !(pst & ST_SOLVER)) {
+        if (pv.gamma_stride == 0) {                          // shared Γ: traj_kernel left the K² type-change logs to us
+            prep_tc_logs(pv, pk, p, threadIdx.x, blockDim.x);
+            __syncthreads();
+        }
         const double* tp = tab + (size_t)p * tab_stride;
         const double* nt = pk.nt + (size_t)p * pk.ntw;
         const double lmusig = nt[K + K * K], lrho = nt[K + K * K + 1];

@@ -34,4 +34,8 @@ GCDYN_HD double hrate_target_start(int M) {
     return M <= 8 ? 0.15 : M <= 12 ? 0.55 : M <= 16 ? 1.0 : M <= 20 ? 1.4 : 1.8;
 }
 
+// Widest cell, as h·rate, the a-posteriori width control of traj_kernel may take: beyond ≈ M/3 the last two Taylor terms
+// of a mode e^{±rate·τ} are no longer decreasing and stop being a usable estimate of the truncation error.
+GCDYN_HD double hrate_cap(int M) { return 0.35 * (double)M; }
+
 }  // namespace gcdyn

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -64,7 +65,6 @@ struct gcdyn_ctx {
     // workspace (grow-only)
     DevBuf params_blob, pack, table, out_tree, out_pset, status, probe, gemm_a, flags, partial;
     PinBuf pin_in, pin_out;
-    const int* dcommon_clean = nullptr;   // the d_common slot finish_kernel has left zeroed (see enqueue_eval)
     // diagnostics of the last evaluation
     int last_steps = 0, last_order = 0, last_launches = 0, last_P = 0;
     PsetPack last_pack{};
@@ -72,6 +72,7 @@ struct gcdyn_ctx {
     bool profile = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int last_cheb_D = 0;
+    const int* last_feedback = nullptr;   // pinned feedback words of the forest the last evaluation ran on
     bool gemm_attr_set = false;
     bool ev_valid = false;
 };
@@ -83,14 +84,33 @@ struct gcdyn_forest {
     int64_t n_chunks = 0;
     int64_t* d_chunk_off = nullptr;
     int64_t max_tree_items = 0;
-    // Chebyshev moments of the forest for one present_time (built lazily, cached)
+    // nodal Chebyshev moments of the forest for one (present_time, grid degree) (built lazily, cached)
     mutable MomentView mom{};
     mutable double mom_T = -1.0;
     mutable double* d_Mt = nullptr;
+    mutable size_t Mt_cap = 0;            // doubles
     mutable double* d_colsum = nullptr;
+    mutable size_t colsum_cap = 0;        // doubles
+    mutable bool mom_refused = false;     // the moments did not fit (or do not pay): this forest takes the item sweep
+    // grid-degree control: the calibrated degree (0 = not calibrated yet) and the present_time it belongs to; feedback
+    // words {degree of a grid some pset was NOT resolved on, probe: sufficient degree, probe: grid it was measured on}
+    mutable int D_cur = 0;
+    mutable double D_T = -1.0;
+    mutable int* h_feedback = nullptr;    // pinned, written by finish_kernel / degree_probe_kernel
     // shared-Γ constant Σ count·log Γ_xy per tree, cached for the last Γ seen
     mutable double* d_tree_const = nullptr;
     mutable std::vector<double> tc_gamma;
+};
+
+struct gcdyn_comm {
+    gcdyn_ctx* ctx = nullptr;
+    int rank = 0, world = 1, cap = 0;
+    void* window = nullptr;               // this rank's allocation: data then flags
+    void* peer[gcdyn::PEER_MAX_WORLD] = {};   // peers' windows as mapped here (peer[rank] == window)
+    bool connected = false;
+    unsigned long long seq = 0;
+    unsigned long long timeout_ns = 20000000000ULL;   // bounded wait for the peers' flags ($GCDYN_PEER_TIMEOUT_MS)
+    int* h_err = nullptr;                 // pinned: raised by the kernel when a peer did not arrive in time
 };
 
 struct gcdyn_sim {
@@ -275,28 +295,22 @@ int carve_pack(gcdyn_ctx* ctx, int P, int K, PsetPack* pk) {
     return GCDYN_OK;
 }
 
-// Dynamic shared memory of traj_kernel: [ĉ broadcast buffer | δΓ (K > 32 only)] for the integrating warp, then the
-// Chebyshev stage's scratch [cos table | node values | coefficients | folded halves | grid].  Mirrors the kernel.
-size_t traj_smem_bytes(int K, int D, int S_cap, int M) {
-    // broadcast buffers (2 × KP, KP = K rounded up to the instantiated width) and, for K > 64, δΓ transposed
-    const size_t KP = K <= 32 ? (((size_t)K + 3) & ~(size_t)3) : (K <= 64 ? (((size_t)K + 7) & ~(size_t)7) : (((size_t)K + 3) & ~(size_t)3));
-    size_t n = 2 * KP + (K <= 64 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
-    // grid/flags of the published cells (ChebSmem)
-    n += 2 * (size_t)S_cap + 4 + ((size_t)S_cap + 8) / 2;
-    // ring of published cells + two row buffers while integrating; the folded DCT halves afterwards (same memory)
-    size_t region = (size_t)CHEB_RING_SLOTS * K * (M + 2);
-    if (D > 0) {
-        region = std::max(region + 2 * (size_t)K * (M + 2), ((size_t)D + 2) * K);
-        // cos table, node values / coefficients, DCT matrix
-        n += 2 * (size_t)D + (((size_t)(D + 1) * K + 1) & ~(size_t)1) + ((size_t)D / 2 + 1) * ((size_t)D + 4);
-    }
-    return (n + region) * sizeof(double);
+// Dynamic shared memory of traj_kernel: [d_n broadcast buffers | δΓ (K > 64 only)] for the integrating warps, then
+// TrajSmem: [cos table | node values | check | ring meta | ring of A_n | two row buffers].  Mirrors the kernel.
+size_t traj_smem_bytes(int K, int D, int M) {
+    const size_t KSB = K <= 32 ? (((size_t)K + 3) & ~(size_t)3) : (K <= 64 ? (((size_t)K + 7) & ~(size_t)7) : (((size_t)K + 3) & ~(size_t)3));
+    size_t n = 2 * KSB + (K <= 64 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
+    const size_t KS = ((size_t)K + 1) & ~(size_t)1;
+    if (D > 0) n += 2 * (size_t)D + (((size_t)D + 3) & ~(size_t)1) + ((((size_t)D + 1) * K + 1) & ~(size_t)1) + 24 * (size_t)K;
+    n += (size_t)RING_SLOTS * 4 + (size_t)RING_SLOTS * (M + 1) * KS;
+    if (D > 0) n += 2 * (size_t)K * (M + 2);
+    return n * sizeof(double);
 }
 
 template <int M, int KP, int KPL, int NPW = 1>
 int launch_traj_inst(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, const TrajCfg& cfg, const ChebCfg& cc,
                      double* tab, cudaStream_t st) {
-    const size_t smem = traj_smem_bytes(pv.K, cc.D, cfg.S_cap, M);
+    const size_t smem = traj_smem_bytes(pv.K, cc.D, M);
     if (smem > 48 * 1024)
         CU_TRY(ctx, cudaFuncSetAttribute(traj_kernel<M, KP, KPL, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     traj_kernel<M, KP, KPL, NPW><<<pv.P, TRAJ_THREADS, smem, st>>>(pv, pk, cfg, cc, tab);
@@ -371,48 +385,94 @@ int launch_sweep(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& p
     return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
 }
 
-// Chebyshev interpolation degree for this batch: generous (the kernel trims to the effective degree),
-// even, ≤ the moment cap and small enough for cheb_kernel's shared memory.
-int cheb_degree(double T, double rate_max, int K, int Dcap, int S_cap, int M, int smem_optin) {
-    double want = T * rate_max + 12.0;
-    if (!(want == want)) want = 32.0;
-    const int ladder[] = {32, 48, 64, 96, 128};
-    int D = 128;
-    for (int d : ladder) if ((double)d >= want) { D = d; break; }
-    D = std::min(D, Dcap);
-    while (D > 16 && traj_smem_bytes(K, D, S_cap, M) + 1024 > (size_t)smem_optin) D -= 16;
-    return D & ~3;   // cheb_stage handles degrees in groups of four
+// Degrees the nodal Chebyshev grid may take.
+const int D_LADDER[] = {8, 12, 16, 20, 24, 28, 32, 36, 40, 48, 56, 64, 80, 96, 112, 128};
+int degree_ladder_ceil(int d) {
+    for (int v : D_LADDER) if (v >= d) return v;
+    return 128;
 }
 
-// Build (once per forest and present_time) the per-tree Chebyshev moments and count columns.
-int ensure_moments(gcdyn_ctx* ctx, const gcdyn_forest* f, double T, cudaStream_t st, int* launches) {
-    if (f->mom.Mt && f->mom_T == T) return GCDYN_OK;
+// Degree of the Chebyshev–Gauss–Lobatto grid.  The FIRST evaluation on a forest (per present_time) calibrates it: it runs
+// on a generous grid sized from the rates, a probe measures the degree the batch's interpolants really need (full
+// Chebyshev spectrum of a few psets), the call synchronises ONCE, adopts that degree and repeats itself on it.  From
+// then on the degree is a property of the forest handle — every later evaluation uses it, so results are bit-identical
+// from call to call.  Psets the grid does not resolve are summed exactly (slower, still correct); only when a quarter of
+// a batch is in that state — the parameters have moved to another regime — does finish_kernel report back through a
+// pinned word, and the next call takes the next rung.
+size_t fit_degree_smem(int K, int D) { return (2 * (size_t)D + ((size_t)D + 1) * K) * 8 + 1024; }
+int clamp_degree(int D, int K, int M, int smem_optin) {
+    while (D > 8 && (traj_smem_bytes(K, D, M) + 1024 > (size_t)smem_optin || fit_degree_smem(K, D) > (size_t)smem_optin)) D -= 4;
+    return D;
+}
+int initial_degree(double T, double rate, int K, int M, int smem_optin) {
+    double want = 2.0 * T * rate + 16.0;
+    if (!(want == want) || want > 128.0) want = 128.0;
+    return clamp_degree(degree_ladder_ceil((int)std::ceil(want)), K, M, smem_optin);
+}
+
+// Build (once per forest, present_time and grid degree) the per-tree nodal Chebyshev moments and count columns.
+// Returns GCDYN_OK with f->mom.Mt == nullptr when the moments are refused (they do not fit or do not pay): the caller
+// then takes the exact item sweep, which needs none of this memory.
+int ensure_moments(gcdyn_ctx* ctx, const gcdyn_forest* f, double T, int D, cudaStream_t st, int* launches) {
+    if (f->mom.Mt && f->mom_T == T && f->mom.D == D) return GCDYN_OK;
+    f->mom.Mt = nullptr;
+    if (f->mom_refused) return GCDYN_OK;
     const int K = f->v.K;
-    const int Dcap = 128;
     const int C1 = 2 * K + 4;
-    long long Jtc = C1 + (long long)(Dcap + 1) * K;
-    Jtc = (Jtc + 3) & ~3LL;
+    long long J1 = C1 + (long long)(D + 1) * K;
+    J1 = (J1 + 3) & ~3LL;
+    long long Jtc = J1;
     long long Jst = Jtc + (long long)K * K;
     Jst = (Jst + 3) & ~3LL;
     const int64_t Tn = f->v.n_trees;
-    if (!f->d_Mt) {
-        CU_TRY(ctx, cudaMalloc(&f->d_Mt, std::max<size_t>((size_t)Tn * (size_t)Jst * 8, 8)));
-        CU_TRY(ctx, cudaMalloc(&f->d_colsum, (size_t)Jst * 8));
+    // cost model: the contraction does 2·Jst flops per (tree, pset) on the tensor pipe, the sweep ≈ 40 flops per item at
+    // a far lower rate; with fewer than ≈ Jst/100 items per tree the sweep wins.  Memory: never take more than half of
+    // what is free.
+    const size_t need = std::max<size_t>((size_t)Tn * (size_t)Jst, 1);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const bool pays = (double)Tn * (double)Jst <= 100.0 * (double)std::max<int64_t>(f->v.n_items, 1);
+    const bool fits = need <= f->Mt_cap || need * 8 <= free_b / 2;
+    if (!pays || !fits) { f->mom_refused = true; return GCDYN_OK; }
+    if (need > f->Mt_cap || (size_t)Jst > f->colsum_cap) {
+        if (f->d_Mt) cudaFree(f->d_Mt);
+        if (f->d_colsum) cudaFree(f->d_colsum);
+        f->d_Mt = f->d_colsum = nullptr; f->Mt_cap = f->colsum_cap = 0;
+        cudaError_t e1 = cudaMalloc(&f->d_Mt, need * 8);
+        cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&f->d_colsum, (size_t)Jst * 8) : e1;
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {     // not an error of the evaluation: the sweep path needs no moments
+            cudaGetLastError();
+            if (f->d_Mt) cudaFree(f->d_Mt);
+            f->d_Mt = f->d_colsum = nullptr;
+            f->mom_refused = true;
+            return GCDYN_OK;
+        }
+        f->Mt_cap = need; f->colsum_cap = (size_t)Jst;
+    }
+    if (!f->h_feedback) {
+        CU_TRY(ctx, cudaHostAlloc(&f->h_feedback, 4 * sizeof(int), cudaHostAllocMapped));
+        f->h_feedback[0] = f->h_feedback[1] = f->h_feedback[2] = f->h_feedback[3] = 0;
     }
     const size_t smem = ((size_t)C1 + (size_t)K * K) * 4;
     if (smem > 48 * 1024)
         CU_TRY(ctx, cudaFuncSetAttribute(counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (Tn > 0) {
-        counts_kernel<<<(unsigned)Tn, 128, smem, st>>>(f->v, Dcap, Jtc, Jst, f->d_Mt);
+        counts_kernel<<<(unsigned)Tn, 128, smem, st>>>(f->v, D, Jtc, Jst, f->d_Mt);
         CU_TRY(ctx, cudaGetLastError());
         const long long warps = (long long)Tn * K;
-        moments_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(f->v, T, Dcap, Jst, C1, f->d_Mt);
+        moments_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(f->v, T, D, Jst, C1, f->d_Mt);
         CU_TRY(ctx, cudaGetLastError());
+        const size_t nsm = (2 * (size_t)D + ((size_t)D + 1) * K) * 8;
+        if (nsm > 48 * 1024)
+            CU_TRY(ctx, cudaFuncSetAttribute(nodal_transform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsm));
+        nodal_transform_kernel<<<(unsigned)Tn, 256, nsm, st>>>(K, D, C1, Jst, f->d_Mt);
+        CU_TRY(ctx, cudaGetLastError());
+        *launches += 3;
     }
-    colsum_kernel<<<(unsigned)((Jst + 127) / 128), 128, 0, st>>>(f->d_Mt, Tn, Jst, f->d_colsum);
+    colsum_kernel<<<(unsigned)((Jst + 31) / 32), 256, 0, st>>>(f->d_Mt, Tn, Jst, f->d_colsum);
     CU_TRY(ctx, cudaGetLastError());
-    *launches += 3;
-    f->mom.K = K; f->mom.C1 = C1; f->mom.Dcap = Dcap; f->mom.Jtc = Jtc; f->mom.Jst = Jst;
+    *launches += 1;
+    f->mom.K = K; f->mom.C1 = C1; f->mom.D = D; f->mom.J1 = J1; f->mom.Jtc = Jtc; f->mom.Jst = Jst;
     f->mom.Mt = f->d_Mt; f->mom.colsum = f->d_colsum;
     f->mom_T = T;
     f->tc_gamma.clear();
@@ -436,24 +496,24 @@ cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t s
 }
 
 template <int M>
-int launch_finish_m(gcdyn_ctx* ctx, const gcdyn_forest* f, const PsetPack& pk, const double* tab, const TrajCfg& cfg, double T,
+int launch_finish_m(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, const PsetPack& pk, const double* tab, const TrajCfg& cfg, double T,
                     const double* partial, int splits, const double* tree_const, const int* need_sweep, int P,
                     double* out_tree, int32_t* status, double* out_pset, cudaStream_t st) {
     cudaLaunchConfig_t lc = pdl_config(dim3((unsigned)P), dim3(256), 0, st);
-    CU_TRY(ctx, cudaLaunchKernelEx(&lc, finish_kernel<M>, f->v, pk, tab, cfg.tab_stride, cfg.S_cap, cfg.grid_doubles, T, partial,
-                                   splits, tree_const, need_sweep, P, out_tree, status, out_pset));
+    CU_TRY(ctx, cudaLaunchKernelEx(&lc, finish_kernel<M>, f->v, pv, pk, tab, cfg.tab_stride, cfg.S_cap, cfg.grid_doubles, T, partial,
+                                   splits, tree_const, need_sweep, P, f->mom.D, const_cast<int*>(need_sweep) + P, f->h_feedback, out_tree, status, out_pset));
     return GCDYN_OK;
 }
 
-int launch_finish(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& pk, const double* tab, const TrajCfg& cfg,
+int launch_finish(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const ParamsView& pv, const PsetPack& pk, const double* tab, const TrajCfg& cfg,
                   double T, const double* partial, int splits, const double* tree_const, const int* need_sweep, int P,
                   double* out_tree, int32_t* status, double* out_pset, cudaStream_t st) {
     switch (M) {
-        case 8: return launch_finish_m<8>(ctx, f, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
-        case 12: return launch_finish_m<12>(ctx, f, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
-        case 16: return launch_finish_m<16>(ctx, f, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
-        case 20: return launch_finish_m<20>(ctx, f, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
-        case 24: return launch_finish_m<24>(ctx, f, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
+        case 8: return launch_finish_m<8>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
+        case 12: return launch_finish_m<12>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
+        case 16: return launch_finish_m<16>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
+        case 20: return launch_finish_m<20>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
+        case 24: return launch_finish_m<24>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
     }
     return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
 }
@@ -492,36 +552,39 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         const size_t tab_bytes = (size_t)P * (size_t)cfg.tab_stride * 8;
         CU_TRY(ctx, ctx->table.ensure(tab_bytes));
         // ---- per-tree sums: Chebyshev-moment GEMM (DMMA), with the item sweep as exact fallback.  The Chebyshev
-        //      stage (node values, DCT, coefficient row, fallback flag) runs as the tail of traj_kernel.
-        const bool use_gemm = !(flags & GCDYN_FLAG_SWEEP_ONLY) && Tn > 0 &&
-                              (P >= 8 || (f->mom.Mt && f->mom_T == T));
+        //      stage (node values = coefficient row, resolution check, fallback flag) runs inside traj_kernel.
+        bool use_gemm = !(flags & GCDYN_FLAG_SWEEP_ONLY) && Tn > 0 && !f->mom_refused &&
+                        (P >= 8 || (f->mom.Mt && f->mom_T == T));
         const int* only_flagged = nullptr;
         ChebCfg cc{};
         int* need_sweep = nullptr;
-        int* d_common = nullptr;
+        bool calibrating = false;
         if (use_gemm) {
-            rc = ensure_moments(ctx, f, T, st, &launches);
+            int D;
+            if (f->D_cur == 0 || f->D_T != T) {
+                D = initial_degree(T, rate_typical > 0.0 ? std::min(rate_typical, rate_max) : rate_max, K, M, ctx->smem_optin);
+                calibrating = true;
+            } else {
+                if (f->h_feedback && f->h_feedback[0] == f->D_cur && f->D_cur < 128)      // some pset was not resolved on it
+                    f->D_cur = clamp_degree(degree_ladder_ceil(f->D_cur + 1), K, M, ctx->smem_optin);
+                D = f->D_cur;
+            }
+            rc = ensure_moments(ctx, f, T, D, st, &launches);
             if (rc) return rc;
+            if (!f->mom.Mt) use_gemm = false;              // refused: too large for the free memory, or the sweep is cheaper
+        }
+        if (use_gemm) {
             CU_TRY(ctx, ctx->gemm_a.ensure((size_t)P * (size_t)f->mom.Jst * 8));
-            // flags: [need_sweep P][d_common][d_common of the last finished evaluation]; finish_kernel leaves d_common
-            // zeroed for the next call, so the memset is only needed when the slot moved or a call failed midway
             CU_TRY(ctx, ctx->flags.ensure((size_t)(P + 2) * 4));
             need_sweep = ctx->flags.as<int>();
-            d_common = need_sweep + P;
-            if (ctx->dcommon_clean != d_common) CU_TRY(ctx, cudaMemsetAsync(d_common, 0, 4, st));
-            ctx->dcommon_clean = nullptr;
             cc.T = T;
             cc.tol = 1e-11;
-            cc.tab_stride = cfg.tab_stride;
-            cc.S_cap = cfg.S_cap;
-            cc.grid_doubles = cfg.grid_doubles;
-            cc.D = cheb_degree(T, rate_typical > 0.0 ? std::min(rate_typical, rate_max) : rate_max, K, f->mom.Dcap, cfg.S_cap, M,
-                               ctx->smem_optin);
+            cc.D = f->mom.D;
             cc.compact_tc = pv.gamma_stride == 0 ? 1 : 0;
             cc.mv = f->mom;
             cc.A = ctx->gemm_a.as<double>();
             cc.need_sweep = need_sweep;
-            cc.d_common = d_common;
+            cc.nflag = need_sweep + P;
         }
         rc = launch_traj(ctx, M, pv, pk, cfg, cc, ctx->table.as<double>(), st);
         if (rc) return rc;
@@ -561,17 +624,37 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             {
                 cudaLaunchConfig_t lc = pdl_config(grid, dim3(128), GT_SMEM_BYTES, st);
                 CU_TRY(ctx, cudaLaunchKernelEx(&lc, gemm_kernel, (const double*)ctx->gemm_a.as<double>(), mv, cc.compact_tc ? 0 : 1,
-                                               (const int*)d_common, P, (int64_t)Tn, ctx->partial.as<double>()));
+                                               P, (int64_t)Tn, ctx->partial.as<double>()));
             }
             ++launches;
             if (prof) { cudaEventRecord(ctx->ev[4], st); cudaEventRecord(ctx->ev[5], st); }
-            rc = launch_finish(ctx, M, f, pk, ctx->table.as<double>(), cfg, T, ctx->partial.as<double>(), splits, tree_const,
+            rc = launch_finish(ctx, M, f, pv, pk, ctx->table.as<double>(), cfg, T, ctx->partial.as<double>(), splits, tree_const,
                                need_sweep, P, d_out_tree, d_status, d_out_pset, st);
             if (rc) return rc;
-            ctx->dcommon_clean = d_common;
             ++launches;
             if (prof) { cudaEventRecord(ctx->ev[6], st); ctx->ev_valid = true; }
+            if (calibrating) {
+                // first evaluation on this forest: measure the degree the batch really needs, adopt it, and repeat
+                int adopt = cc.D;
+                const size_t psm = (2 * (size_t)cc.D + 2 * ((size_t)cc.D + 1) * K) * 8;
+                if (psm + 1024 <= (size_t)ctx->smem_optin) {
+                    if (psm > 48 * 1024)
+                        CU_TRY(ctx, cudaFuncSetAttribute(degree_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+                    degree_probe_kernel<<<1, 512, psm, st>>>((const double*)ctx->gemm_a.as<double>(), mv, (const int*)need_sweep, P,
+                                                             cc.tol, f->h_feedback + 1);
+                    CU_TRY(ctx, cudaGetLastError());
+                    CU_TRY(ctx, cudaStreamSynchronize(st));
+                    if (f->h_feedback[2] == cc.D && f->h_feedback[1] > 4)
+                        adopt = std::min(cc.D, clamp_degree(degree_ladder_ceil(f->h_feedback[1] + 3), K, M, ctx->smem_optin));
+                }
+                f->D_cur = adopt;
+                f->D_T = T;
+                if (adopt != cc.D)
+                    return enqueue_eval(ctx, f, pv, rate_max, T, method, M, S_fixed, tol, flags, host_gamma_shared, d_out_pset,
+                                        d_out_tree == ctx->out_tree.as<double>() ? nullptr : d_out_tree, d_status, st, pk_out, rate_typical);
+            }
             ctx->last_cheb_D = cc.D;
+            ctx->last_feedback = f->h_feedback;
             ctx->last_steps = cfg.S_cap;
             ctx->last_order = M;
             ctx->last_launches = launches;
@@ -640,6 +723,7 @@ void free_forest(gcdyn_forest* f) {
     if (f->d_Mt) cudaFree(f->d_Mt);
     if (f->d_colsum) cudaFree(f->d_colsum);
     if (f->d_tree_const) cudaFree(f->d_tree_const);
+    if (f->h_feedback) cudaFreeHost(f->h_feedback);
     cudaSetDevice(prev);
     delete f;
 }
@@ -808,6 +892,16 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
     rc = enqueue_eval(ctx, f, pv, rate_max_of(pr), T, method, M, o.steps, tol, o.flags,
                       pr->gamma_pset_stride == 0 ? pr->Gamma : nullptr, comm ? ctx->out_pset.as<double>() : h_out, nullptr,
                       status ? ctx->status.as<int32_t>() : nullptr, st, nullptr);
+    if (rc && comm) {
+        // a rank-local failure must still release the peers: contribute NaN (every rank then sees NaN sums, and this rank
+        // returns its error) instead of leaving them to wait for a flag that never comes
+        const std::string why = ctx->err;
+        cudaGetLastError();
+        if (ctx->out_pset.p && cudaMemsetAsync(ctx->out_pset.p, 0xFF, (size_t)P * 8, st) == cudaSuccess &&
+            comm_enqueue(comm, ctx->out_pset.as<double>(), h_out, P, st) == GCDYN_OK)
+            cudaStreamSynchronize(st);
+        return fail(ctx, rc, why);
+    }
     if (rc) return rc;
     if (comm) {                       // trees sharded over ranks: sum the partial [P] over the peers, result → pinned host
         rc = comm_enqueue(comm, ctx->out_pset.as<double>(), h_out, P, st);
@@ -821,6 +915,10 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
     }
     CU_TRY(ctx, cudaStreamSynchronize(st));
     std::memcpy(out_pset, h_out, (size_t)P * 8);
+    if (comm && comm->h_err && *comm->h_err) {
+        *comm->h_err = 0;
+        return fail(ctx, GCDYN_ECUDA, "peer all-reduce timed out: a rank did not arrive (its evaluation failed or it is gone)");
+    }
     return GCDYN_OK;
 }
 
@@ -1024,16 +1122,16 @@ int gcdyn_last_cheb_degree(gcdyn_ctx* ctx, int32_t* interp_degree, int32_t* effe
     GUARD_BEGIN
     if (!ctx) return fail(ctx, GCDYN_EINVAL, "ctx is NULL");
     if (interp_degree) *interp_degree = ctx->last_cheb_D;
+    if (effective_degree) *effective_degree = 0;
+    if (n_fallback) *n_fallback = 0;
     if ((effective_degree || n_fallback) && ctx->last_cheb_D > 0 && ctx->flags.p && ctx->last_P > 0) {
-        std::vector<int> h(ctx->last_P + 2);
+        std::vector<int> h(ctx->last_P);
         CU_TRY(ctx, cudaSetDevice(ctx->device));
         CU_TRY(ctx, cudaDeviceSynchronize());
-        CU_TRY(ctx, cudaMemcpy(h.data(), ctx->flags.p, (size_t)(ctx->last_P + 2) * 4, cudaMemcpyDeviceToHost));
-        if (effective_degree) *effective_degree = h[ctx->last_P + 1];
+        CU_TRY(ctx, cudaMemcpy(h.data(), ctx->flags.p, (size_t)ctx->last_P * 4, cudaMemcpyDeviceToHost));
         if (n_fallback) { int n = 0; for (int p = 0; p < ctx->last_P; ++p) n += h[p] != 0; *n_fallback = n; }
-    } else {
-        if (effective_degree) *effective_degree = 0;
-        if (n_fallback) *n_fallback = 0;
+        // the degree the calibration probe found sufficient for its batch
+        if (effective_degree && ctx->last_feedback) *effective_degree = ctx->last_feedback[1];   // measured at calibration
     }
     return GCDYN_OK;
     GUARD_END(ctx)
@@ -1189,15 +1287,6 @@ int gcdyn_probe_fp64_peak(gcdyn_ctx* ctx, double* tflops) {
 }  // extern "C"
 
 // ---- peer all-reduce (multi-GPU) ---------------------------------------------------------------------------
-struct gcdyn_comm {
-    gcdyn_ctx* ctx = nullptr;
-    int rank = 0, world = 1, cap = 0;
-    void* window = nullptr;               // this rank's allocation: data then flags
-    void* peer[gcdyn::PEER_MAX_WORLD] = {};   // peers' windows as mapped here (peer[rank] == window)
-    bool connected = false;
-    unsigned long long seq = 0;
-};
-
 namespace {
 size_t comm_data_bytes(int world, int cap) { return (size_t)2 * world * cap * sizeof(double); }
 }
@@ -1212,6 +1301,12 @@ extern "C" int gcdyn_comm_create(gcdyn_ctx* ctx, int32_t rank, int32_t world, in
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     gcdyn_comm* c = new gcdyn_comm();
     c->ctx = ctx; c->rank = rank; c->world = world; c->cap = (max_psets + 1) & ~1;
+    if (const char* ev = std::getenv("GCDYN_PEER_TIMEOUT_MS")) {
+        const double ms = std::atof(ev);
+        if (ms > 0.0) c->timeout_ns = (unsigned long long)(ms * 1e6);
+    }
+    if (cudaHostAlloc(&c->h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); c->h_err = nullptr; }
+    else *c->h_err = 0;
     const size_t bytes = comm_data_bytes(world, c->cap) + (size_t)world * sizeof(unsigned long long);
     cudaError_t e = cudaMalloc(&c->window, bytes);
     if (e == cudaSuccess) e = cudaMemset(c->window, 0, bytes);
@@ -1260,7 +1355,7 @@ int comm_enqueue(gcdyn_comm* c, const double* d_in, double* out, int n_psets, cu
     }
     ++c->seq;
     cudaLaunchConfig_t lc = pdl_config(dim3(1), dim3(1024), 0, st);
-    CU_TRY(ctx, cudaLaunchKernelEx(&lc, gcdyn::peer_allreduce_kernel, pv, d_in, out, n_psets, c->seq));
+    CU_TRY(ctx, cudaLaunchKernelEx(&lc, gcdyn::peer_allreduce_kernel, pv, d_in, out, n_psets, c->seq, c->timeout_ns, c->h_err));
     return GCDYN_OK;
 }
 }  // namespace
@@ -1294,6 +1389,7 @@ extern "C" void gcdyn_comm_destroy(gcdyn_comm* c) {
     for (int r = 0; r < c->world; ++r)
         if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
     if (c->window) cudaFree(c->window);
+    if (c->h_err) cudaFreeHost(c->h_err);
     cudaSetDevice(prev);
     delete c;
 }
@@ -1387,6 +1483,12 @@ int mh_loglik(gcdyn_mh* m, double* dst, cudaStream_t st) {
     gcdyn_ctx* ctx = m->ctx;
     int rc = enqueue_eval(ctx, m->forest, m->pv, m->rate_bound, m->T, GCDYN_METHOD_ODE, 16, 0, 1e-11, 0, m->host_gamma.data(),
                           dst, nullptr, nullptr, st, nullptr, m->rate_typical);
+    if (rc && m->comm) {              // release the peers with NaN sums (see batch_impl), then report the local error
+        const std::string why = ctx->err;
+        cudaGetLastError();
+        if (cudaMemsetAsync(dst, 0xFF, (size_t)m->C * 8, st) == cudaSuccess) comm_enqueue(m->comm, dst, dst, m->C, st);
+        return fail(ctx, rc, why);
+    }
     if (rc) return rc;
     if (m->comm) return comm_enqueue(m->comm, dst, dst, m->C, st);
     return GCDYN_OK;
@@ -1435,6 +1537,10 @@ extern "C" int gcdyn_mh_run(gcdyn_mh* m, int64_t iterations, double* theta_hist,
         CU_TRY(ctx, cudaMemcpyAsync(loglik_hist, d_hl, (size_t)iterations * C * 8, cudaMemcpyDeviceToHost, st));
     }
     CU_TRY(ctx, cudaStreamSynchronize(st));
+    if (m->comm && m->comm->h_err && *m->comm->h_err) {
+        *m->comm->h_err = 0;
+        return fail(ctx, GCDYN_ECUDA, "peer all-reduce timed out: a rank did not arrive (its evaluation failed or it is gone)");
+    }
     return GCDYN_OK;
     GUARD_END(ctx)
 }

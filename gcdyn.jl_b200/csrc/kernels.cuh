@@ -6,8 +6,8 @@
 //                 publishes every accepted cell through a shared-memory ring; the other warps compute rates and
 //                 node-term logs (λ, μ, γ of mbp.jl:27-97), build per cell and type the polynomial of
 //                 F_x(τ) = ∫(−Λ_x + 2 λ_x p_x) — the branch density of dp_logq_dt!, mbp.jl:285-300 — write that
-//                 table, and evaluate F at the Chebyshev nodes; the CTA then produces the pset's row of GEMM
-//                 coefficients (cheb_gemm.cuh) and log(1 − p_x(T)) (mbp.jl:244-245)
+//                 table, and evaluate F at the Chebyshev nodes — those values are the pset's row of GEMM coefficients
+//                 (cheb_gemm.cuh keeps the forest's moments in the nodal basis) — and log(1 − p_x(T)) (mbp.jl:244-245)
 //   gemm_kernel   (cheb_gemm.cuh) LL[p][t] = Σ_j A[p][j]·Mt[t][j] with DMMA, split over the column range
 //   finish_kernel (cheb_gemm.cuh) combines the splits, applies −Inf/status rules, recomputes flagged psets exactly
 //                 from the table, and sums over trees → out_pset[p]   (mbp.jl:258)
@@ -117,8 +117,19 @@ __device__ __forceinline__ double birth_rate(const ParamsView& pv, int p, int i)
 }
 
 // Rates and node-term logs of one pset, computed cooperatively by `nthr` threads (tid = 0..nthr-1).
+__device__ __forceinline__ void prep_tc_logs(const ParamsView& pv, const PsetPack& pk, int p, int tid, int nthr) {
+    const int K = pv.K;
+    const double delta = pv.delta[p];
+    const double* G = pv.Gamma + (size_t)p * pv.gamma_stride;   // column-major: Γ[i,j] = G[i + j*K]
+    double* nt = pk.nt + (size_t)p * pk.ntw;
+    for (int e = tid; e < K * K; e += nthr) {
+        const int x = e / K, y = e - x * K;
+        nt[K + e] = (x == y) ? -CUDART_INF : log(delta * G[x + (size_t)y * K]);   // γ(model, from, to), mbp.jl:84-97
+    }
+}
+
 __device__ __forceinline__ void prep_pset(const ParamsView& pv, const PsetPack& pk, int p, int method, int tid, int nthr,
-                                          bool init_status = true) {
+                                          bool init_status = true, bool tc_logs = true) {
     const int K = pv.K;
     const double mu = pv.mu[p], delta = pv.delta[p], rho = pv.rho[p], sigma = pv.sigma[p];
     const double* G = pv.Gamma + (size_t)p * pv.gamma_stride;   // column-major: Γ[i,j] = G[i + j*K]
@@ -138,10 +149,7 @@ __device__ __forceinline__ void prep_pset(const ParamsView& pv, const PsetPack& 
             pk.st_B[(size_t)p * K + i] = x + lam * (1.0 - rho);
         }
     }
-    for (int e = tid; e < K * K; e += nthr) {
-        const int x = e / K, y = e - x * K;
-        nt[K + e] = (x == y) ? -CUDART_INF : log(delta * G[x + (size_t)y * K]);   // γ(model, from, to), mbp.jl:84-97
-    }
+    if (tc_logs) prep_tc_logs(pv, pk, p, tid, nthr);
     if (tid == 0) {
         nt[K + K * K] = log(mu) + log(sigma);   // mbp.jl:171
         nt[K + K * K + 1] = log(rho);           // mbp.jl:168
@@ -173,25 +181,24 @@ __global__ void stadler_cond_kernel(ParamsView pv, PsetPack pk, double present_t
 
 struct MomentView {
     int K;
-    int C1;                // 2K + 4: start of the Chebyshev block
-    int Dcap;              // moments exist for d = 0..Dcap
+    int C1;                // 2K + 4: start of the nodal block
+    int D;                 // degree of the Chebyshev–Gauss–Lobatto grid: nodes k = 0..D, τ_k = T(1 + cos(πk/D))/2
+    long long J1;          // end of the nodal block, rounded up to a multiple of 4
     long long Jtc;         // start of the K² type-change block
     long long Jst;         // row stride of Mt and A (doubles), multiple of 4
     const double* Mt;      // [T][Jst]
-    const double* colsum;  // [Jst] forest-level column sums (only count columns are consulted)
+    const double* colsum;  // [Jst] forest-level column sums
 };
 
 struct ChebCfg {
     double T;
-    double tol;            // accepted Chebyshev tail (absolute, on F)
-    int D;                 // interpolation degree (≤ Dcap), even
+    double tol;            // accepted size of the interpolant's last three Chebyshev coefficients (absolute, on F)
+    int D;                 // = mv.D; 0: no Chebyshev stage (item sweep only)
     int compact_tc;        // 1: Γ shared — log δ column + per-tree constant; 0: K² type-change columns
-    int S_cap, grid_doubles;   // layout of a pset's table block: [τ_s | 1/h_s | pad][rows]
-    long long tab_stride;
     MomentView mv;
-    double* A;             // [P][Jst] coefficient rows of the GEMM
-    int* need_sweep;       // [P] fallback flags
-    int* d_common;         // [1] max effective degree over the psets the GEMM takes
+    double* A;             // [P][Jst] coefficient rows of the GEMM: count columns | F_x(τ_k), node-major | K² block
+    int* need_sweep;       // [P] fallback flags: 1 = interpolant unresolved, 2 = non-finite node-term logs
+    int* nflag;            // [1] psets of this batch that were unresolved (reset by traj_kernel, counted by finish_kernel)
 };
 
 // Cell containing τ on a pset's (non-uniform) grid: largest s < S with grid[s] ≤ τ.
@@ -260,6 +267,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra.uni WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+#ifndef GCDYN_CONS_POLL
+#define GCDYN_CONS_POLL 0
+#endif
+// A whole warp waits for a phase: variant 0 every lane polls; 1 lane 0 polls with a short sleep between attempts and the
+// others park at the warp barrier; 2 lane 0 polls back to back.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+#if GCDYN_CONS_POLL == 0
+    mbar_wait(bar, parity);
+#else
+    if ((threadIdx.x & 31) == 0) {
+        for (;;) {
+            uint32_t ok;
+            asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+            if (ok) break;
+#if GCDYN_CONS_POLL == 1
+            __nanosleep(100);
+#endif
+        }
+    }
+    __syncwarp();
+#endif
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
@@ -267,68 +297,142 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 // ------------------------------------------------------------------------------------------------
-// Chebyshev stage of one pset inside traj_kernel.  While warp 0 integrates, warps 1..3 (`cheb_consume`) build
-// the cosine tables and evaluate F_x at the D+1 Chebyshev–Gauss–Lobatto nodes cell by cell, as soon as warp 0
-// publishes a cell (release/acquire on a shared-memory counter; table rows are read back through L2).  After the
-// CTA barrier `cheb_finish` runs on all threads: DCT-I → a[d][x]; effective degree; count-column coefficients;
-// fallback flag.
+// traj_kernel: one CTA of 4 warps per pset.
+//
+// Integration (NPW warps: one for K ≤ 32 — lane l owns type l; two for 32 < K ≤ 64 — thread t of the pair owns type t;
+// one for K > 64 — lane l owns types l, l+32, …, δΓ staged in shared memory).  The ODE is polynomial
+// (dp_dt!, mbp.jl:266-278), so the DERIVATIVES d_n = p^(n)(τ_s) at the start of a cell follow a recurrence that does not
+// involve the cell width h:
+//     d_1     = G d_0 + (λ d_0 − a) d_0 + b                          a = λ + μ,  b = μ(1 − σ),  G = δΓ
+//     d_{n+1} = G d_n + κ d_n + λ n! R_n,     κ = 2λ d_0 − a,   R_n = Σ_{m=1}^{n−1} A_m A_{n−m},   A_n = d_n / n!
+// Per Taylor stage the critical path is: broadcast d_n through shared memory → K-term dot product whose first chain is
+// seeded with κ d_n + λ n! R_n (both known before the broadcast returns) → two DADDs.  The convolution, the factorials
+// and the publication of A_n sit in the shadow of the broadcast.  Only AFTER the M derivatives are known is the width
+// chosen — the largest h with |A_M| h^M + |A_{M−1}| h^{M−1} ≤ tol/2 over the pset's types (high-word log2, one MUFU.EX2),
+// capped at hrate_cap(M)/rate — so no cell is ever rejected or recomputed, and p(τ_s + h) = Σ A_n h^n is one Estrin
+// evaluation.  A result outside [0, 1] (isoutofdomain, mbp.jl:146,204,231) halves h and re-evaluates the same
+// polynomial: the reference's reject-and-shrink at no extra derivative work; a width below 1e-10·T is a solver failure
+// (the reference's dt < dtmin → non-success retcode → -Inf, mbp.jl:154-158).
+//
+// The other warps: rates and node-term logs first (λ, μ, γ of mbp.jl:27-97), then per published cell (A_0..A_M per
+// type, τ_s, h through a 6-slot shared-memory ring guarded by mbarriers) the polynomial of
+// F_x(τ) = ∫(−Λ_x + 2 λ_x p_x) — the branch density of dp_logq_dt!, mbp.jl:285-300 — on the cell,
+//     row[0] = F(τ_s),  row[1] = h(2λA_0 − Λ),  row[n+1] = 2λ A_n h^{n+1}/(n+1),     θ = (τ − τ_s)/h,
+// written to the table in global memory (exact item sums of flagged psets) and evaluated at the Chebyshev–Gauss–Lobatto
+// nodes inside the cell.  Those node values ARE the pset's GEMM coefficients (the forest's moments are kept in the
+// nodal basis, cheb_gemm.cuh), so nothing but a resolution check and the count columns remains after the last cell.
 // ------------------------------------------------------------------------------------------------
 #ifdef GCDYN_TRAJ_TRACE
 __device__ long long g_trace_out[1024 * 24];
 #define TRACE_STAMP(i) do { if ((threadIdx.x & 31) == 0) g_trace[i] = clock64(); } while (0)
-#define TRACE_ARG , long long* g_trace
-#define TRACE_PASS , g_trace
 #else
 #define TRACE_STAMP(i) do { } while (0)
-#define TRACE_ARG
-#define TRACE_PASS
 #endif
 
-constexpr int CHEB_RING_SLOTS = 3;   // cells in flight between the integrating warp and the consumer warps
+#ifndef GCDYN_RING_SLOTS
+#define GCDYN_RING_SLOTS 6
+#endif
+constexpr int RING_SLOTS = GCDYN_RING_SLOTS;                 // cells in flight between the integrating warp(s) and the consumer warps
 constexpr int CELL_LAST = 1, CELL_FAIL = 2;   // flags of a published cell
 
-struct ChebSmem {                      // carve-up of the stage's shared-memory scratch
+__host__ __device__ constexpr double factd(int n) { double f = 1.0; for (int i = 2; i <= n; ++i) f *= (double)i; return f; }
+
+template <int N>
+__device__ __forceinline__ double powi(double h) {
+    if constexpr (N == 0) return 1.0;
+    else if constexpr (N & 1) return h * powi<N - 1>(h);
+    else { const double t = powi<N / 2>(h); return t * t; }
+}
+
+// Σ_{n ≤ M} A[n] h^n by Estrin's scheme (depth ⌈log2(M+1)⌉ instead of M dependent FMAs)
+template <int LEN, int N>
+__device__ __forceinline__ void estrin_level(double (&cur)[N], double pw) {
+#pragma unroll
+    for (int i = 0; 2 * i < LEN; ++i) cur[i] = (2 * i + 1 < LEN) ? fma(cur[2 * i + 1], pw, cur[2 * i]) : cur[2 * i];
+    if constexpr ((LEN + 1) / 2 > 1) estrin_level<(LEN + 1) / 2, N>(cur, pw * pw);
+}
+template <int M>
+__device__ __forceinline__ double estrin(const double (&A)[M + 1], double h) {
+    double cur[M + 1];
+#pragma unroll
+    for (int i = 0; i <= M; ++i) cur[i] = A[i];
+    estrin_level<M + 1, M + 1>(cur, h);
+    return cur[0];
+}
+
+struct TrajSmem {                      // carve-up of the kernel's dynamic shared memory behind the broadcast buffers
     double* costab;                    // [2D]  cos(π m / D)
-    double* V;                         // [(D+1)*K] node values, later the coefficients a[d][x]
-    double* EO;                        // [2][(H+1)*K] folded node values
-    double* cosm;                      // [H+1][D+4]  cos(π k d / D), zero for d > D
-    double* sgrid;                     // [S_cap+1] τ_s as published by warp 0
-    double* shc;                       // [S_cap]   h_s
-    int* sflag;                        // [S_cap+1] CELL_LAST / CELL_FAIL of a published cell
-    double* ring;                      // [CHEB_RING_SLOTS][K*L] Taylor coefficients ĉ_0..ĉ_M of the cells in flight
+    double* tauk;                      // [D+2] τ_k = T(1 + cos(πk/D))/2
+    double* V;                         // [(D+1)*K] node values F_x(τ_k)
+    double* chk;                       // [8][3][K] partial sums of a_D, a_{D−1}, a_{D−2} of the interpolant (resolution check)
+    double* meta;                      // [RING_SLOTS][4]  τ_s, τ_{s+1}, h_s, flags of the cells in flight
+    double* ring;                      // [RING_SLOTS][(M+1)*KS]  A_n[x], n-major (conflict-free for lanes = types)
     double* rowbuf;                    // [2][K*L] table rows of the cell being evaluated at the Chebyshev nodes
-    __device__ ChebSmem(double* sm, int K, int D, int S_cap, int L) {
-        const int H = D / 2;
+    int KS;
+    __device__ TrajSmem(double* sm, int K, int D, int M) {
+        KS = (K + 1) & ~1;
         costab = sm;
-        V = costab + 2 * D;
-        if (D > 0) {
-            cosm = V + ((((size_t)(D + 1) * K) + 1) & ~(size_t)1);
-            sgrid = cosm + (size_t)(H + 1) * (D + 4);
-        } else {                                        // no Chebyshev stage: only the ring and its grid/flags exist
-            cosm = sgrid = sm;
-        }
-        shc = sgrid + (S_cap + 1);
-        sflag = reinterpret_cast<int*>(sgrid + 2 * S_cap + 1);
-        ring = sgrid + 2 * (S_cap + 1) + (((size_t)S_cap + 4) / 2 & ~(size_t)1);   // even offset: 16-byte aligned rows
-        rowbuf = ring + (size_t)CHEB_RING_SLOTS * K * L;
-        EO = ring;     // the folded halves live where the ring and the row buffers were: those are dead once the
-                       // trajectory is complete (the host sizes the region as the larger of the two uses)
+        tauk = costab + 2 * D;
+        V = tauk + (D > 0 ? ((D + 3) & ~1) : 0);
+        chk = V + (D > 0 ? ((((size_t)(D + 1) * K) + 1) & ~(size_t)1) : 0);
+        meta = chk + (D > 0 ? 24 * (size_t)K : 0);
+        ring = meta + RING_SLOTS * 4;
+        rowbuf = ring + (size_t)RING_SLOTS * (M + 1) * KS;
     }
 };
 
-// The three warps that do not integrate (ct = 0..nct-1).  For every cell the integrating warp publishes (ĉ_0..ĉ_M per
-// type, τ_s, h_s) they build the table rows of F — row[0] = F(τ_s), row[1] = h(2λĉ_0 − Λ), row[n+1] = 2hλ ĉ_n/(n+1) —
-// keep the running F(τ_s) per type, write rows and grid to the table in global memory and, when the Chebyshev stage
-// is on, evaluate F_x at the Chebyshev–Gauss–Lobatto nodes inside the cell.  Node k sits at τ_k = T(1 + cos(πk/D))/2,
-// so cells (increasing τ) meet the nodes in decreasing k; a node belongs to the largest cell with τ_s ≤ τ_k
-// (find_cell's rule), the last cell takes the rest.
+// Count columns of the pset's coefficient row that do not depend on the trajectory (everything but −log(1 − p_x(T))),
+// written by the consumer warps while the integration runs.  A non-finite log the forest actually uses flags the pset
+// (bit 2): finish_kernel then sums its items exactly, where 0·log 0 terms are never formed.
+__device__ __forceinline__ void early_count_columns(const ParamsView& pv, const PsetPack& pk, const ChebCfg& cfg, int p,
+                                                    int tid, int nthr, int* s_flag) {
+    const MomentView& mv = cfg.mv;
+    const int K = mv.K, C1 = mv.C1;
+    double* Arow = cfg.A + (size_t)p * mv.Jst;
+    const double* nt = pk.nt + (size_t)p * pk.ntw;
+    for (int c = tid; c < C1; c += nthr) {
+        if (c >= K + 2 && c < 2 * K + 2) continue;                     // −log(1 − p_x(T)): the integrating lanes, at the end
+        double v = 0.0;
+        if (c < K) v = nt[c];                                         // log λ_x
+        else if (c == K) v = nt[K + K * K];                           // log μ + log σ
+        else if (c == K + 1) v = nt[K + K * K + 1];                   // log ρ
+        else if (c == 2 * K + 2) v = cfg.compact_tc ? log(pv.delta[p]) : 0.0;
+        if (!isfinite(v)) {
+            if (mv.colsum[c] != 0.0) atomicOr(s_flag, 2);
+            v = 0.0;
+        }
+        Arow[c] = v;
+    }
+    if (!cfg.compact_tc) {
+        for (int e = tid; e < K * K; e += nthr) {
+            double v = nt[K + e];
+            const bool diag = (e / K) == (e % K);          // self-loop column: trees using it are −Inf anyway
+            if (!isfinite(v)) {
+                if (!diag && mv.colsum[mv.Jtc + e] != 0.0) atomicOr(s_flag, 2);
+                v = 0.0;
+            }
+            Arow[mv.Jtc + e] = v;
+        }
+    }
+    // the GEMM rounds its column ranges up to multiples of 4: keep the padding finite
+    if (tid < 4) {
+        const long long j = C1 + (long long)(mv.D + 1) * K + tid;
+        if (j < mv.Jtc) Arow[j] = 0.0;
+        const long long j2 = mv.Jtc + (long long)K * K + tid;
+        if (j2 < mv.Jst) Arow[j2] = 0.0;
+    }
+}
+
+// The warps that do not integrate (ct = 0..nct-1).  Node k of the Chebyshev grid sits at τ_k = T(1 + cos(πk/D))/2, so
+// cells (increasing τ) meet the nodes in decreasing k; a node belongs to the largest cell with τ_s ≤ τ_k (find_cell's
+// rule), the last cell takes the rest.
 template <int M>
 __device__ __forceinline__ void cell_consume(const ParamsView& pv, const TrajCfg& tc, const ChebCfg& cfg, bool cheb, int p,
-                                             double* __restrict__ tab, const ChebSmem& cs, uint64_t* full, uint64_t* empty,
-                                             int ct, int nct) {
+                                             double* __restrict__ tab, const TrajSmem& ts, uint64_t* full, uint64_t* empty,
+                                             int ct, int nct, const PsetPack& pk, int* s_flag) {
     constexpr int L = M + 2;
-    constexpr int TPT = 2;                              // types per consumer thread: K ≤ 128 (KPL ≤ 4), nct = 96
-    const int K = pv.K, D = cfg.D, H = D / 2, CW = D + 4;
+    constexpr int TPT = 2;                              // types per consumer thread: K ≤ 128, nct ≥ 64
+    const int K = pv.K, D = cfg.D, KS = ts.KS;
     const double mu = pv.mu[p], delta = pv.delta[p];
     const double* G = pv.Gamma + (size_t)p * pv.gamma_stride;
     double lamx[TPT], Lamx[TPT], Fc[TPT];
@@ -341,50 +445,51 @@ __device__ __forceinline__ void cell_consume(const ParamsView& pv, const TrajCfg
         Fc[j] = 0.0;
     }
     if (cheb) {
-        for (int m = ct; m < 2 * D; m += nct) cs.costab[m] = cospi((double)m / (double)D);
-        asm volatile("bar.sync 1, %0;" ::"r"(nct) : "memory");
-        for (int idx = ct; idx < (H + 1) * CW; idx += nct) {
-            const int k = idx / CW, d = idx - k * CW;
-            cs.cosm[idx] = d <= D ? cs.costab[(k * d) % (2 * D)] : 0.0;
+        for (int m = ct; m < 2 * D; m += nct) {
+            const double c = cospi((double)m / (double)D);
+            ts.costab[m] = c;
+            if (m <= D) ts.tauk[m] = cfg.T * (1.0 + c) * 0.5;
         }
+        asm volatile("bar.sync 1, %0;" ::"r"(nct) : "memory");      // cos table and the node-term logs of prep_pset are complete
+        early_count_columns(pv, pk, cfg, p, ct, nct, s_flag);
     }
     double* tabp = tab + (size_t)p * tc.tab_stride;
     double* gridp = tabp;
     double* invhp = tabp + (tc.S_cap + 1);
     double* rowsp = tabp + tc.grid_doubles;
+    double* Anod = cheb ? cfg.A + (size_t)p * cfg.mv.Jst + cfg.mv.C1 : nullptr;
     int kn = D;
     for (int sc = 0;; ++sc) {
-        const int slot_i = sc % CHEB_RING_SLOTS;
-        mbar_wait(full + slot_i, (uint32_t)(sc / CHEB_RING_SLOTS) & 1u);
-        const int flag = cs.sflag[sc];
+        const int slot_i = sc % RING_SLOTS;
+        mbar_wait_warp(full + slot_i, (uint32_t)(sc / RING_SLOTS) & 1u);
+        const double* meta = ts.meta + slot_i * 4;
+        const int flag = (int)meta[3];
         if (flag & CELL_FAIL) {
             if (ct == 0) gridp[sc] = tc.T;
             break;
         }
-        const double t0 = cs.sgrid[sc], t1 = cs.sgrid[sc + 1], hc = cs.shc[sc];
+        const double t0 = meta[0], t1 = meta[1], hc = meta[2];
         const double ih = 1.0 / hc;
-        const double* slot = cs.ring + (size_t)slot_i * K * L;
-        double* rb = cs.rowbuf + (size_t)(sc & 1) * K * L;
+        const double* slot = ts.ring + (size_t)slot_i * (M + 1) * KS;
+        double* rb = ts.rowbuf + (size_t)(sc & 1) * K * L;
 #pragma unroll
         for (int j = 0; j < TPT; ++j) {
             const int x = ct + j * nct;
             if (x < K) {
-                double c[L], row[L];
-#pragma unroll
-                for (int n = 0; n < L; n += 2) {
-                    const double2 v = *reinterpret_cast<const double2*>(slot + (size_t)x * L + n);
-                    c[n] = v.x;
-                    c[n + 1] = v.y;
-                }
+                double row[L];
+                const double a0 = slot[x];
+                const double l2 = 2.0 * lamx[j];
                 row[0] = Fc[j];
-                row[1] = hc * (2.0 * lamx[j] * c[0] - Lamx[j]);
-                const double h2l = 2.0 * hc * lamx[j];
-                double fs[4] = {0.0, 0.0, 0.0, 0.0};         // smallest terms first, four partial sums
+                row[1] = hc * (l2 * a0 - Lamx[j]);
+                double hp = hc;                               // h^(n+1)
 #pragma unroll
-                for (int n = M; n >= 1; --n) {
-                    row[n + 1] = (h2l * (1.0 / (double)(n + 1))) * c[n];
-                    fs[n & 3] += row[n + 1];
+                for (int n = 1; n <= M; ++n) {
+                    hp *= hc;
+                    row[n + 1] = (l2 * (1.0 / (double)(n + 1))) * (slot[(size_t)n * KS + x] * hp);
                 }
+                double fs[4] = {0.0, 0.0, 0.0, 0.0};          // smallest terms first, four partial sums
+#pragma unroll
+                for (int n = M; n >= 1; --n) fs[n & 3] += row[n + 1];
                 Fc[j] += ((fs[0] + fs[1]) + (fs[2] + fs[3])) + row[1];
                 double2* dst = reinterpret_cast<double2*>(rowsp + ((size_t)sc * K + x) * L);
 #pragma unroll
@@ -408,12 +513,17 @@ __device__ __forceinline__ void cell_consume(const ParamsView& pv, const TrajCfg
             asm volatile("bar.sync 1, %0;" ::"r"(nct) : "memory");
             int klo = kn;                               // nodes klo+1..kn lie in this cell
             if (flag & CELL_LAST) klo = -1;
-            else while (klo >= 0 && cfg.T * (1.0 + cs.costab[klo]) * 0.5 < t1) --klo;
+            else while (klo >= 0 && ts.tauk[klo] < t1) --klo;
+#ifdef GCDYN_EXP_NO_NODES
+            const int nitems = 0;
+#else
             const int nitems = (kn - klo) * K;
+#endif
             for (int it = ct; it < nitems; it += nct) {
                 const int k = kn - it / K, x = it % K;
-                const double tau = cfg.T * (1.0 + cs.costab[k]) * 0.5;
-                cs.V[k * K + x] = eval_row<M, true>(rb + (size_t)x * L, (tau - t0) * ih);
+                const double v = eval_row<M, true>(rb + (size_t)x * L, (ts.tauk[k] - t0) * ih);
+                ts.V[k * K + x] = v;
+                Anod[k * K + x] = v;
             }
             kn = klo;
         }
@@ -421,166 +531,89 @@ __device__ __forceinline__ void cell_consume(const ParamsView& pv, const TrajCfg
     }
 }
 
-template <int M>
-__device__ __forceinline__ void cheb_finish(const ParamsView& pv, const PsetPack& pk, const ChebCfg& cfg, int p,
-                                            const ChebSmem& cs TRACE_ARG) {
+// After the last cell, all threads: resolution check of the degree-D interpolant (its last three Chebyshev coefficients
+// must be below tol — otherwise the pset is flagged and finish_kernel sums its items exactly from the table) and the
+// fallback flag.
+__device__ __forceinline__ void nodal_finish(const PsetPack& pk, const ChebCfg& cfg, int p, const TrajSmem& ts, int* s_flag) {
     const MomentView& mv = cfg.mv;
-    double* __restrict__ A = cfg.A;
-    int* __restrict__ need_sweep = cfg.need_sweep;
-    int* __restrict__ d_common = cfg.d_common;
-    const int K = mv.K, C1 = mv.C1, D = cfg.D;
-    const int H = D / 2, CW = D + 4, NV = (D + 1) * K;
-    double* V = cs.V;
-    double* Acoef = V;
-    double* EO = cs.EO;
-    const double* cosm = cs.cosm;
-    __shared__ int s_deff, s_flag;
+    const int K = mv.K, C1 = mv.C1, D = cfg.D, NV = (D + 1) * K;
+    double* V = ts.V;
+    double* Arow = cfg.A + (size_t)p * mv.Jst;
     const int pst = pk.pstatus[p];
-    if (threadIdx.x == 0) { s_deff = 8; s_flag = (pst & ST_SOLVER) ? 1 : 0; }
-    if (pst & ST_SOLVER) {                               // CTA-uniform: a failed trajectory has no usable nodes
-        for (int idx = threadIdx.x; idx < NV; idx += blockDim.x) V[idx] = 0.0;
-        __syncthreads();
+    if (pst & ST_SOLVER) {                               // CTA-uniform: a failed trajectory has no usable nodes; it is
+        for (int idx = threadIdx.x; idx < NV; idx += blockDim.x) Arow[C1 + idx] = 0.0;   // -Inf through its status
+        if (threadIdx.x == 0) cfg.need_sweep[p] = 0;
+        return;
     }
-    TRACE_STAMP(6);
-    // DCT-I with the symmetry cos(π(D−k)d/D) = (−1)^d cos(πkd/D): fold the node values into an even and an
-    // odd half, E_k = w_k (V_k + V_{D−k}), O_k = w_k (V_k − V_{D−k}), k = 0..D/2, w_0 = w_{D/2} = 1/2.
-    for (int idx = threadIdx.x; idx < (H + 1) * K; idx += blockDim.x) {
-        const int k = idx / K, x = idx - k * K;
-        const double w = (k == 0 || k == H) ? 0.5 : 1.0;
-        const double a = V[k * K + x], b = V[(D - k) * K + x];
-        EO[idx] = w * (a + b);
-        EO[(H + 1) * K + idx] = w * (a - b);
-    }
-    __syncthreads();
-    TRACE_STAMP(7);
-    // a thread owns four consecutive degrees 4g..4g+3 of one type: even degrees contract E, odd degrees O
-    {
-        const int NG = D / 4 + 1;
-        const double scale = 2.0 / (double)D;
-        for (int w = threadIdx.x; w < NG * K; w += blockDim.x) {
-            const int g = w / K, x = w - g * K;
-            const double* E = EO + x;
-            const double* O = EO + (size_t)(H + 1) * K + x;
-            const double* cg = cosm + 4 * g;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll 5
-            for (int k = 0; k <= H; ++k) {
-                const double e = E[k * K], o = O[k * K];
-                const double2 c01 = *reinterpret_cast<const double2*>(cg + (size_t)k * CW);
-                const double2 c23 = *reinterpret_cast<const double2*>(cg + (size_t)k * CW + 2);
-                a0 = fma(e, c01.x, a0);
-                a1 = fma(o, c01.y, a1);
-                a2 = fma(e, c23.x, a2);
-                a3 = fma(o, c23.y, a3);
-            }
-            const int d0 = 4 * g;
-            Acoef[d0 * K + x] = (d0 == 0 || d0 == D) ? 0.5 * scale * a0 : scale * a0;
-            if (d0 + 1 <= D) Acoef[(d0 + 1) * K + x] = scale * a1;
-            if (d0 + 2 <= D) Acoef[(d0 + 2) * K + x] = scale * a2;
-            if (d0 + 3 <= D) Acoef[(d0 + 3) * K + x] = (d0 + 3 == D) ? 0.5 * scale * a3 : scale * a3;
+    // a_{D−j} = (2/D) Σ''_k V_k (−1)^k cos(π k j / D) for j = 0, 1, 2 (a_D halved).  NSEG threads per type share the
+    // node range; the partial sums are combined in segment order.
+    const int NSEG = min(8, max(1, (int)blockDim.x / K));
+    for (int w = threadIdx.x; w < NSEG * K; w += blockDim.x) {
+        const int seg = w / K, x = w - seg * K;
+        const int k0 = (int)((long long)(D + 1) * seg / NSEG), k1 = (int)((long long)(D + 1) * (seg + 1) / NSEG);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int k = k0; k < k1; ++k) {
+            const double wk = (k == 0 || k == D) ? 0.5 : 1.0;
+            const double v = (k & 1) ? -wk * V[k * K + x] : wk * V[k * K + x];
+            s0 += v;
+            s1 = fma(v, ts.costab[k], s1);
+            s2 = fma(v, ts.costab[(2 * k) % (2 * D)], s2);
         }
+        ts.chk[(seg * 3 + 0) * K + x] = s0;
+        ts.chk[(seg * 3 + 1) * K + x] = s1;
+        ts.chk[(seg * 3 + 2) * K + x] = s2;
     }
     __syncthreads();
-    TRACE_STAMP(8);
-    // effective degree (a thread per type): the largest d whose tail Σ_{k≥d}|a_k| exceeds tol.  The sum runs downwards
-    // from D and stops at the first excess — for a resolved series that is after the D − d_eff smallest coefficients.
-    // The series counts as unresolved if its last three terms are not small.
+    bool unresolved = false;
     for (int x = threadIdx.x; x < K; x += blockDim.x) {
-        const double last3 = fabs(Acoef[D * K + x]) + fabs(Acoef[(D - 1) * K + x]) + fabs(Acoef[(D - 2) * K + x]);
-        if (!(last3 <= cfg.tol)) atomicExch(&s_flag, 1);
-        double tail = 0.0;
-        int found = 8;
-        for (int d = D; d > 8; --d) {
-            tail += fabs(Acoef[d * K + x]);
-            if (!(tail <= cfg.tol)) { found = d; break; }
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int seg = 0; seg < NSEG; ++seg) {
+            a0 += ts.chk[(seg * 3 + 0) * K + x];
+            a1 += ts.chk[(seg * 3 + 1) * K + x];
+            a2 += ts.chk[(seg * 3 + 2) * K + x];
         }
-        if (found > 8) atomicMax(&s_deff, found);
+        const double last3 = (2.0 / (double)D) * (0.5 * fabs(a0) + fabs(a1) + fabs(a2));
+        if (!(last3 <= cfg.tol)) unresolved = true;
     }
-    __syncthreads();
-    TRACE_STAMP(9);
-    const int deff = s_deff;
-    double* Arow = A + (size_t)p * mv.Jst;
-    for (int idx = threadIdx.x; idx < (D + 1) * K; idx += blockDim.x) {
-        Arow[C1 + idx] = Acoef[idx];          // all interpolation coefficients are valid; the GEMM stops at d_common
-    }
-    // the GEMM rounds its column ranges up to multiples of 4: keep the padding finite
-    if (threadIdx.x < 4) {
-        const long long j = C1 + (long long)(D + 1) * K + threadIdx.x;
-        if (j < mv.Jtc) Arow[j] = 0.0;
-        const long long j2 = mv.Jtc + (long long)K * K + threadIdx.x;
-        if (j2 < mv.Jst) Arow[j2] = 0.0;
-    }
-    // count columns
-    const double* nt = pk.nt + (size_t)p * pk.ntw;
-    for (int c = threadIdx.x; c < C1; c += blockDim.x) {
-        double v = 0.0;
-        if (c < K) v = nt[c];                                         // log λ_x
-        else if (c == K) v = nt[K + K * K];                           // log μ + log σ
-        else if (c == K + 1) v = nt[K + K * K + 1];                   // log ρ
-        else if (c < 2 * K + 2) v = -pk.logcond[(size_t)p * K + (c - K - 2)];
-        else if (c == 2 * K + 2) v = cfg.compact_tc ? log(pv.delta[p]) : 0.0;
-        if (!isfinite(v)) {
-            if (mv.colsum[c] != 0.0) atomicExch(&s_flag, 1);
-            v = 0.0;
-        }
-        Arow[c] = v;
-    }
-    if (!cfg.compact_tc) {
-        for (int e = threadIdx.x; e < K * K; e += blockDim.x) {
-            double v = nt[K + e];
-            const bool diag = (e / K) == (e % K);          // self-loop column: trees using it are −Inf anyway
-            if (!isfinite(v)) {
-                if (!diag && mv.colsum[mv.Jtc + e] != 0.0) atomicExch(&s_flag, 1);
-                v = 0.0;
-            }
-            Arow[mv.Jtc + e] = v;
-        }
-    }
-    __syncthreads();
-    TRACE_STAMP(10);
-    if (threadIdx.x == 0) {
-        need_sweep[p] = s_flag;
-        if (!s_flag) atomicMax(d_common, deff);
-    }
+    const int any_unres = __syncthreads_or(unresolved ? 1 : 0);
+    if (threadIdx.x == 0) cfg.need_sweep[p] = *s_flag | (any_unres ? 1 : 0);
 }
 
-// ------------------------------------------------------------------------------------------------
-// traj_kernel: one CTA of 4 warps per pset.  NPW warps integrate — one (K ≤ 32: lane l owns type l; K > 64: lane l
-// owns types l, l+32, …, KPL per lane, δΓ in shared memory) or two (32 < K ≤ 64: thread t of the pair owns type t and
-// keeps its row of δΓ in registers; the pair exchanges ĉ_n through shared memory and a named barrier per Taylor
-// stage) — the other warps build the table and the Chebyshev node values behind them; then the whole CTA finishes the
-// Chebyshev stage.
-//
-// Taylor recurrence for the h-scaled coefficients ĉ_n of p(τ_s + θh) = Σ ĉ_n θ^n:
-//   ĉ_{n+1} = h/(n+1) · [ −(λ+μ) ĉ_n + [n=0] μ(1−σ) + λ Σ_{m≤n} ĉ_m ĉ_{n−m} + δ Γ ĉ_n ]
-// which is dp_dt! (mbp.jl:266-278) expanded order by order.  Cells are NON-uniform: after every cell the
-// width is re-sized from the error indicator (|ĉ_M| + |ĉ_{M−1}| ~ h^M), a cell above tol is redone smaller.
-// Table row for (cell s, type x), L = M+2, θ = (τ − τ_s)/h_s:
-//   row[0] = F(τ_s),  row[1] = h(2λĉ_0 − Λ),  row[n+1] = 2hλ ĉ_n/(n+1).
-// KPL == 1 (K ≤ KP ≤ 32): the lane's row of δΓ lives in registers, ĉ_n is broadcast through shared memory.
-// KPL  > 1: δΓ is staged transposed in shared memory (lane-contiguous rows).
-// ------------------------------------------------------------------------------------------------
 template <int M, int KP, int KPL, int NPW>
-__global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetPack pk, TrajCfg cfg, ChebCfg cc,
+__global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, PsetPack pk, TrajCfg cfg, ChebCfg cc,
                                                             double* __restrict__ tab) {
     extern __shared__ __align__(16) double smem[];
-    constexpr int L = M + 2;
     constexpr int NPROD = 32 * NPW, NCONS = TRAJ_THREADS - NPROD;   // integrating / consumer threads
     static_assert(NPW == 1 || (NPW == 2 && KPL == 1), "two integrating warps own one type per lane");
     const int p = blockIdx.x;
     const int K = pv.K;
 #ifdef GCDYN_TRAJ_TRACE
     __shared__ long long g_trace[16];
-    __shared__ int g_attempts;
 #endif
     TRACE_STAMP(0);
 #ifdef GCDYN_TRAJ_TRACE
     if (threadIdx.x == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_trace[14] = gt; }
 #endif
-    __shared__ __align__(8) uint64_t s_full[CHEB_RING_SLOTS], s_empty[CHEB_RING_SLOTS];   // ring of cells → Chebyshev warps
+    __shared__ __align__(8) uint64_t s_full[RING_SLOTS], s_empty[RING_SLOTS];   // ring of cells → consumer warps
+    __shared__ int s_flag;                              // fallback reasons collected while the integration runs
     const bool cheb = cc.D > 0;                         // CTA-uniform
-    const size_t traj_doubles = 2 * (size_t)(KPL == 1 ? KP : ((K + 3) & ~3)) + (KPL == 1 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
-    const ChebSmem cs(smem + traj_doubles, K, cheb ? cc.D : 0, cfg.S_cap, L);
+    {   // pull this pset's parameters towards the SM before anything depends on them: one memory round trip instead of
+        // one per dependent group of loads (the caller's L2 may be cold)
+        auto pf = [](const void* a) { asm volatile("prefetch.global.L1 [%0];" ::"l"(a)); };
+        const int t = threadIdx.x;
+        if (t == 0) { pf(pv.mu + p); pf(pv.delta + p); pf(pv.rho + p); pf(pv.sigma + p); }
+        if (pv.response == 2) {
+            if (t == 1) { pf(pv.xscale + p); pf(pv.xshift + p); pf(pv.yscale + p); pf(pv.yshift + p); }
+            for (int i = t * 16; i < K; i += 16 * TRAJ_THREADS) pf(pv.type_space + i);
+        } else if (pv.response == 0) {
+            for (int i = t * 16; i < K; i += 16 * TRAJ_THREADS) pf(pv.lambda + (size_t)p * K + i);
+        } else if (t == 1) pf(pv.lambda + p);
+        const char* g0 = reinterpret_cast<const char*>(pv.Gamma + (size_t)p * pv.gamma_stride);
+        for (size_t off = (size_t)t * 128; off < (size_t)K * K * 8; off += (size_t)128 * TRAJ_THREADS) pf(g0 + off);
+    }
+    const int KSB = KPL == 1 ? KP : ((K + 3) & ~3);     // broadcast buffer length (multiple of 4)
+    const size_t traj_doubles = 2 * (size_t)KSB + (KPL == 1 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
+    const TrajSmem ts(smem + traj_doubles, K, cheb ? cc.D : 0, M);
     // The integrating warp is chosen from the hardware warp slots so that CTAs sharing an SM integrate on different
     // sub-partitions (two integrations on one FP64 pipe: +32 % per Taylor stage, tools/traj_micro.cu).  Slot groups
     // of four are the usual allocation for a 4-warp CTA; any other allocation only loses the benefit.
@@ -592,13 +625,17 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
         if (lane == 0) s_wid[warp] = (int)wid;
     }
     if (threadIdx.x == 0) {
+        s_flag = 0;
+        if (blockIdx.x == 0 && cheb) *cc.nflag = 0;
 #pragma unroll
-        for (int i = 0; i < CHEB_RING_SLOTS; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, NCONS); }
+        for (int i = 0; i < RING_SLOTS; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, NCONS); }
     }
     __syncthreads();
+#ifndef GCDYN_EXP_LATE_PDL
     pdl_launch_dependents();                            // the contraction's CTAs may become resident behind this grid
+#endif
     // roles: prod_rank = 0..NPW−1 for the integrating warps (−1 otherwise), cons_rank = 0.. for the others
-    int pw = 0, prod_rank = -1, cons_rank = -1;
+    int prod_rank = -1, cons_rank = -1;
     {
         int lo = s_wid[0];
 #pragma unroll
@@ -606,6 +643,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
         bool isp[TRAJ_THREADS / 32];
         int np = 0;
         if (NPW == 1) {
+            int pw = 0;
             const int want = (lo >> 2) & 3;
 #pragma unroll
             for (int w = TRAJ_THREADS / 32 - 1; w >= 0; --w) if ((s_wid[w] & 3) == want) pw = w;
@@ -631,36 +669,37 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
     }
     if (prod_rank < 0) {
         const int ct = cons_rank * 32 + lane;
-        prep_pset(pv, pk, p, 0, ct, NCONS, false);
-        cell_consume<M>(pv, cfg, cc, cheb, p, tab, cs, s_full, s_empty, ct, NCONS);
+        prep_pset(pv, pk, p, 0, ct, NCONS, false, !(cheb && cc.compact_tc));
+        cell_consume<M>(pv, cfg, cc, cheb, p, tab, ts, s_full, s_empty, ct, NCONS, pk, &s_flag);
+#ifdef GCDYN_TRAJ_TRACE
+        if (ct == 0) g_trace[6] = clock64();
+#endif
     }
-    TRACE_STAMP(1);
     if (prod_rank >= 0) {
     const int pt = prod_rank * 32 + lane;               // index among the integrating threads
     // exchange between the integrating warps (NPW == 2): named barrier 2 and a double-buffered pair of slots
-    __shared__ unsigned long long s_xch[2][2];
+    __shared__ unsigned s_xch[2][2][2];
     int xtog = 0;
     auto prod_sync = [&]() {
         if (NPW == 1) __syncwarp();
         else asm volatile("bar.sync 2, %0;" ::"r"(NPROD) : "memory");
     };
-    auto prod_max_u64 = [&](unsigned long long v) -> unsigned long long {      // v is already warp-uniform
-        if (NPW == 1) return v;
-        if (lane == 0) s_xch[xtog][prod_rank] = v;
+    auto prod_max2 = [&](unsigned& v0, unsigned& v1) {      // v0, v1 are already warp-uniform
+        if (NPW == 1) return;
+        if (lane == 0) { s_xch[xtog][0][prod_rank] = v0; s_xch[xtog][1][prod_rank] = v1; }
         asm volatile("bar.sync 2, %0;" ::"r"(NPROD) : "memory");
-        const unsigned long long a0 = s_xch[xtog][0], a1 = s_xch[xtog][1];
+        v0 = max(s_xch[xtog][0][0], s_xch[xtog][0][1]);
+        v1 = max(s_xch[xtog][1][0], s_xch[xtog][1][1]);
         xtog ^= 1;
-        return a0 > a1 ? a0 : a1;
     };
-    const int KS = KPL == 1 ? KP : ((K + 3) & ~3);     // broadcast buffer length (multiple of 4)
-    double* cb = smem;                                  // 2 × KS
-    double* GT = smem + 2 * KS;                         // KPL > 1 only: GT[j*K + i] = δ Γ[i,j]
+    double* cb = smem;                                  // 2 × KSB
+    double* GT = smem + 2 * KSB;                        // KPL > 1 only: GT[j*K + i] = δ Γ[i,j]
 
     const double mu = pv.mu[p], delta = pv.delta[p], rho = pv.rho[p], sigma = pv.sigma[p];
     const double* G = pv.Gamma + (size_t)p * pv.gamma_stride;
     const double b = mu * (1.0 - sigma);
 
-    double lam[KPL], a[KPL], Lam[KPL];
+    double lam[KPL], a[KPL];
     bool own[KPL];
     double rate = 0.0;
 #pragma unroll
@@ -669,14 +708,20 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
         own[q] = i < K;
         lam[q] = own[q] ? birth_rate(pv, p, i) : 0.0;
         const double gam = own[q] ? delta * -G[i + (size_t)i * K] : 0.0;
-        Lam[q] = lam[q] + mu + gam;
         a[q] = lam[q] + mu;
         const double r = own[q] ? fabs(lam[q]) + fabs(mu) + 2.0 * fabs(gam) : 0.0;
         if (!(r <= rate)) rate = r;
     }
     rate = warp_max_nan(rate);
     if (NPW > 1) {                                      // non-negative doubles (and NaN) order like their bit patterns
-        rate = __longlong_as_double((long long)prod_max_u64((unsigned long long)__double_as_longlong(fabs(rate))));
+        unsigned rh = (unsigned)__double2hiint(fabs(rate)), rl = (unsigned)__double2loint(fabs(rate));
+        // compare (hi, lo) lexicographically through two rounds: the hi words first
+        unsigned h0 = rh, dummy = 0u;
+        prod_max2(h0, dummy);
+        unsigned l0 = (rh == h0) ? rl : 0u;
+        dummy = 0u;
+        prod_max2(l0, dummy);
+        rate = __hiloint2double((int)h0, (int)l0);
     }
 
     double g[KPL == 1 ? KP : 1];
@@ -686,51 +731,58 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
     } else {
         for (int e = lane; e < K * K; e += 32) GT[e] = delta * G[e];   // G[i + j*K] → GT[j*K + i]
     }
-    for (int e = pt; e < 2 * KS; e += NPROD) cb[e] = 0.0;
+    for (int e = pt; e < 2 * KSB; e += NPROD) cb[e] = 0.0;
     prod_sync();
 
     const bool adaptive = cfg.S_fixed <= 0;
-    // (the table block of this pset — [τ_s | 1/h_s | pad][rows (cell, type) of L doubles] — is written by the consumers)
     double pcur[KPL];
 #pragma unroll
     for (int q = 0; q < KPL; ++q) pcur[q] = own[q] ? 1.0 - rho : 0.0;   // p(0) = 1 − ρ, mbp.jl:130,141,226
-    // first cell width: optimistic guess from the fastest rate; the controller below corrects it
-    double h = adaptive ? hrate_target_start(M) / rate : cfg.T / (double)cfg.S_fixed;
-    if (!(h > 0.0) || !(h <= 0.25 * cfg.T)) h = adaptive ? 0.25 * cfg.T : cfg.T / (double)cfg.S_fixed;
+    // widest cell the controller may take: beyond h·rate ≈ M/3 the last two Taylor terms stop being a usable estimate
+    double hcap = hrate_cap(M) / rate;
+    if (!(hcap <= cfg.T)) hcap = cfg.T;                 // also rate == 0, NaN
     double tau = 0.0;
-    // Step control works on the HIGH WORD of the indicator (sign, exponent, 20 mantissa bits): non-negative doubles
-    // order like their bit patterns and NaN sorts above +Inf, so one integer REDUX gives the warp maximum, the accept
-    // test is an integer compare (at most 1e-6 stricter than ind ≤ tol) and log2(ind) ≈ (hi − 0x3ff00000)/2^20
-    // (exponent plus linear mantissa, error < 0.09) is all the accuracy (tol/ind)^(1/M) needs.  Every lane sees the
-    // same value, so accept/reject decisions are warp-uniform and deterministic.
+    // Width control works on the HIGH WORDS of |A_M| and |A_{M−1}| (non-negative doubles order like their bit patterns,
+    // NaN sorts above +Inf): one integer REDUX each gives the maxima over the types, log2(x) ≈ (hi − 0x3ff00000)/2^20
+    // (exponent + linear mantissa, never above the true value by construction of the bound below, short by < 0.0861),
+    // so h = min((tol/4/max|A_M|)^(1/M), (tol/4/max|A_{M−1}|)^(1/(M−1))) keeps the indicator below 0.53·tol.  Every
+    // lane sees the same values: decisions are warp-uniform and deterministic.
     const unsigned tol_hi = (unsigned)__double2hiint(cfg.tol);
-    const float tol_l2 = (float)((int)tol_hi - 0x3ff00000) * (1.0f / 1048576.0f);
-    const float decade = exp2f(__log2f(0.1f) * (1.0f / (float)M));      // 0.1^(1/M)
+    const float l2aim = (float)((int)(unsigned)__double2hiint(0.25 * cfg.tol) - 0x3ff00000) * (1.0f / 1048576.0f);
     unsigned errmax_hi = 0u;
-    bool bad = false, failed = false;
-    int s = 0, rejects = 0;
+    bool failed = false;
+    int s = 0;
     TRACE_STAMP(2);
 #ifdef GCDYN_TRAJ_TRACE
-    long long tr_a = 0, tr_b = 0, tr_c = 0, tr_t = clock64();
+    long long tr_wait = 0, tr_stage = 0, tr_epi = 0, tr_t = clock64();
+#define TRACE_ACC(v) do { const long long t__ = clock64(); v += t__ - tr_t; tr_t = t__; } while (0)
+#else
+#define TRACE_ACC(v) do { } while (0)
 #endif
     for (;;) {
-        double hc = h;
-        bool last = false;
-        if (adaptive) { const double rem = cfg.T - tau; if (hc >= rem * (1.0 - 1e-3)) { hc = rem; last = true; } }
-        else if (s + 1 >= cfg.S_fixed) { hc = cfg.T - tau; last = true; }
-        double c[M + 1][KPL];
+        const int slot_i = s % RING_SLOTS;
+        if (s >= cfg.S_cap) { failed = true; break; }
+        if (s >= RING_SLOTS) mbar_wait(s_empty + slot_i, (uint32_t)(s / RING_SLOTS - 1) & 1u);   // consumers left it
+        TRACE_ACC(tr_wait);
+        double* slot = ts.ring + (size_t)slot_i * (M + 1) * ts.KS;
+        double A[KPL][M + 1];
+        double dn[KPL], kappa[KPL], seed[KPL];
 #pragma unroll
-        for (int q = 0; q < KPL; ++q) c[0][q] = pcur[q];
+        for (int q = 0; q < KPL; ++q) {
+            A[q][0] = dn[q] = pcur[q];
+            kappa[q] = fma(2.0 * lam[q], dn[q], -a[q]);
+            seed[q] = fma(dn[q], fma(lam[q], dn[q], -a[q]), b);       // stage 0: λ d_0² − a d_0 + b
+        }
 #pragma unroll
         for (int n = 0; n < M; ++n) {
-            double* buf = cb + (n & 1) * KS;
+            double* buf = cb + (n & 1) * KSB;
 #pragma unroll
             for (int q = 0; q < KPL; ++q)
-                if (own[q]) buf[pt + NPROD * q] = c[n][q];
+                if (own[q]) buf[pt + NPROD * q] = dn[q];
             prod_sync();
-            double dot[KPL];
+            double dnew[KPL];
             if constexpr (KPL == 1) {
-                double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+                double d0 = seed[0], d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
                 for (int j = 0; j < KP; j += 4) {
                     const double2 v01 = *reinterpret_cast<const double2*>(buf + j);
@@ -740,11 +792,12 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
                     d2 = fma(g[j + 2], v23.x, d2);
                     d3 = fma(g[j + 3], v23.y, d3);
                 }
-                dot[0] = (d0 + d1) + (d2 + d3);
+                if (own[0]) slot[(size_t)n * ts.KS + pt] = A[0][n];      // publication rides behind the loads
+                dnew[0] = (d0 + d1) + (d2 + d3);
             } else {
                 double d[KPL][2];
 #pragma unroll
-                for (int q = 0; q < KPL; ++q) d[q][0] = d[q][1] = 0.0;
+                for (int q = 0; q < KPL; ++q) { d[q][0] = seed[q]; d[q][1] = 0.0; }
                 int irow[KPL];
 #pragma unroll
                 for (int q = 0; q < KPL; ++q) irow[q] = own[q] ? pt + NPROD * q : 0;
@@ -765,136 +818,159 @@ __global__ void __launch_bounds__(TRAJ_THREADS) traj_kernel(ParamsView pv, PsetP
                     for (int q = 0; q < KPL; ++q) d[q][0] = fma(GT[(size_t)j * K + irow[q]], v0, d[q][0]);
                 }
 #pragma unroll
-                for (int q = 0; q < KPL; ++q) dot[q] = d[q][0] + d[q][1];
-            }
-            const double hn = hc * (1.0 / (double)(n + 1));
-#pragma unroll
-            for (int q = 0; q < KPL; ++q) {
-                // Σ_{m≤n} ĉ_m ĉ_{n−m} = 2 Σ_{m<n/2} ĉ_m ĉ_{n−m} (+ ĉ_{n/2}² when n is even)
-                double cv0 = 0.0, cv1 = 0.0;
-#pragma unroll
-                for (int m = 0; 2 * m < n; ++m) {
-                    if (m & 1) cv1 = fma(c[m][q], c[n - m][q], cv1);
-                    else cv0 = fma(c[m][q], c[n - m][q], cv0);
-                }
-                double conv = 2.0 * (cv0 + cv1);
-                if ((n & 1) == 0) conv = fma(c[n / 2][q], c[n / 2][q], conv);
-                double rhs = fma(lam[q], conv, dot[q]);
-                rhs = fma(-a[q], c[n][q], rhs);
-                if (n == 0) rhs += b;
-                c[n + 1][q] = rhs * hn;
-            }
-        }
-#ifdef GCDYN_TRAJ_TRACE
-        if (s == 0 && rejects == 0) TRACE_STAMP(11);
-        if (s > 0) { const long long t = clock64(); tr_a += t - tr_t; tr_t = t; }
-#endif
-        // error indicator of this cell: the last two Taylor terms, maximum over the pset's types
-        double ind = 0.0;
-#pragma unroll
-        for (int q = 0; q < KPL; ++q) {
-            const double v = fabs(c[M][q]) + fabs(c[M - 1][q]);
-            if (own[q] && !(v <= ind)) ind = v;
-        }
-        const unsigned ind_hi = (unsigned)prod_max_u64(__reduce_max_sync(FULL, (unsigned)__double2hiint(ind)));
-        const float ind_l2 = (float)((int)ind_hi - 0x3ff00000) * (1.0f / 1048576.0f);
-        const float ratio = exp2f((tol_l2 - ind_l2) * (1.0f / (float)M));     // ≈ (tol/ind)^(1/M)
-        if (adaptive && !(ind_hi < tol_hi)) {
-            // reject: the indicator scales like h^M — shrink the cell accordingly and redo it
-            float f = 0.9f * ratio;
-            if (!(f >= 0.2f)) f = 0.2f;
-            if (f > 0.9f) f = 0.9f;
-            h = hc * (double)f;
-            if (++rejects > 200 || !(h > cfg.T * 1e-10)) { failed = true; break; }
-            continue;
-        }
-        if (s >= cfg.S_cap) { failed = true; break; }
-#ifdef GCDYN_TRAJ_TRACE
-        if (s == 0 && rejects == 0) TRACE_STAMP(12);
-        if (s > 0) { const long long t = clock64(); tr_b += t - tr_t; tr_t = t; }
-#endif
-        // accept: publish ĉ_0..ĉ_M, τ_s and h_s to the consumer warps (they build and store the table rows of F, which
-        // the integration itself never needs) and advance p to the next grid point
-        {
-            const int slot_i = s % CHEB_RING_SLOTS;
-            if (s >= CHEB_RING_SLOTS) mbar_wait(s_empty + slot_i, (uint32_t)(s / CHEB_RING_SLOTS - 1) & 1u);   // consumers left it
-            double* slot = cs.ring + (size_t)slot_i * K * L;
-#pragma unroll
-            for (int q = 0; q < KPL; ++q) {
-                if (own[q]) {
-                    double2* dst = reinterpret_cast<double2*>(slot + (size_t)(pt + NPROD * q) * L);
-#pragma unroll
-                    for (int n = 0; n < M; n += 2) dst[n >> 1] = make_double2(c[n][q], c[n + 1][q]);
-                    dst[M >> 1] = make_double2(c[M][q], 0.0);
+                for (int q = 0; q < KPL; ++q) {
+                    if (own[q]) slot[(size_t)n * ts.KS + pt + NPROD * q] = A[q][n];
+                    dnew[q] = d[q][0] + d[q][1];
                 }
             }
-            if (pt == 0) {
-                cs.sgrid[s] = tau; cs.sgrid[s + 1] = last ? cfg.T : tau + hc; cs.shc[s] = hc;
-                cs.sflag[s] = last ? CELL_LAST : 0;
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) {
+                // λ (n+1)! R_{n+1}: needs A_1..A_n only, i.e. nothing of this stage — it fills the broadcast's shadow
+                double add = 0.0;
+                if (n >= 1) {
+                    const int k = n + 1;
+                    double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+                    for (int m = 1; 2 * m < k; ++m) {
+                        if (m & 1) r1 = fma(A[q][m], A[q][k - m], r1);
+                        else r0 = fma(A[q][m], A[q][k - m], r0);
+                    }
+                    double R = 2.0 * (r0 + r1);
+                    if ((k & 1) == 0) R = fma(A[q][k / 2], A[q][k / 2], R);
+                    add = (lam[q] * factd(k)) * R;
+                }
+                dn[q] = dnew[q];
+                A[q][n + 1] = dnew[q] * (1.0 / factd(n + 1));
+                seed[q] = fma(kappa[q], dnew[q], add);
             }
-            prod_sync();
-            if (pt == 0) mbar_arrive(s_full + slot_i);
         }
+#pragma unroll
+        for (int q = 0; q < KPL; ++q)
+            if (own[q]) slot[(size_t)M * ts.KS + pt + NPROD * q] = A[q][M];
+        TRACE_ACC(tr_stage);
+        // ---- cell width from the last two coefficients
+        unsigned hiM = 0u, hiM1 = 0u;
 #pragma unroll
         for (int q = 0; q < KPL; ++q) {
-            double ps[4] = {0.0, 0.0, 0.0, 0.0};             // Σ_{n≥1} ĉ_n, smallest terms first, four partial sums
-#pragma unroll
-            for (int n = M; n >= 1; --n) ps[n & 3] += c[n][q];
-            pcur[q] = ((ps[0] + ps[1]) + (ps[2] + ps[3])) + c[0][q];
-            if (own[q] && !(pcur[q] >= -1e-9 && pcur[q] <= 1.0 + 1e-9)) bad = true;   // isoutofdomain, mbp.jl:146,204,231
+            if (own[q]) {
+                hiM = max(hiM, (unsigned)__double2hiint(fabs(A[q][M])));
+                hiM1 = max(hiM1, (unsigned)__double2hiint(fabs(A[q][M - 1])));
+            }
         }
-        if (ind_hi > errmax_hi) errmax_hi = ind_hi;
-#ifdef GCDYN_TRAJ_TRACE
-        if (s == 0 && rejects == 0) TRACE_STAMP(13);
-        { const long long t = clock64(); if (s > 0) tr_c += t - tr_t; tr_t = t; }
-#endif
-        ++s;
-        if (last) break;
-        tau += hc;
+        hiM = __reduce_max_sync(FULL, hiM);
+        hiM1 = __reduce_max_sync(FULL, hiM1);
+        prod_max2(hiM, hiM1);
+        double h;
+        bool last = false;
         if (adaptive) {
-            // next cell: aim a decade below tol; never more than double, never less than half
-            float f = 0.9f * decade * ratio;
-            if (!(f <= 2.0f)) f = 2.0f;            // also ind == 0 → +Inf, NaN
-            if (f < 0.5f) f = 0.5f;
-            h = hc * (double)f;
+            const float lM = (float)((int)hiM - 0x3ff00000) * (1.0f / 1048576.0f);
+            const float lM1 = (float)((int)hiM1 - 0x3ff00000) * (1.0f / 1048576.0f);
+            float lh = fminf((l2aim - lM) * (1.0f / (float)M), (l2aim - lM1) * (1.0f / (float)(M - 1)));
+            lh = fminf(lh, 100.0f);
+            h = (double)exp2f(lh);
+            if (!(h > cfg.T * 1e-10)) { failed = true; break; }          // non-finite coefficients land here too
+            if (!(h <= hcap)) h = hcap;
+            const double rem = cfg.T - tau;
+            if (h >= rem * (1.0 - 1e-3)) { h = rem; last = true; }
+            else if (h > 0.5 * rem) h = 0.5 * rem;                       // two even cells instead of a sliver at the end
+        } else {
+            last = s + 1 >= cfg.S_fixed;
+            h = last ? cfg.T - tau : cfg.T / (double)cfg.S_fixed;
         }
+        // ---- p(τ_s + h); outside [0, 1]: shrink the cell and re-evaluate (isoutofdomain, mbp.jl:146,204,231)
+        double pn[KPL];
+        for (int shrinks = 0;; ++shrinks) {
+            bool bad = false;
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) {
+                pn[q] = estrin<M>(A[q], h);
+                if (own[q] && !(pn[q] >= -1e-9 && pn[q] <= 1.0 + 1e-9)) bad = true;
+            }
+            unsigned anyb = __any_sync(FULL, bad) ? 1u : 0u, zero = 0u;
+            prod_max2(anyb, zero);
+            if (!anyb) break;
+            h *= 0.5;
+            last = false;
+            if (!adaptive || shrinks >= 60 || !(h > cfg.T * 1e-10)) { failed = true; break; }
+        }
+        if (failed) break;
+        // error indicator of the accepted cell (diagnostics; decides success on a fixed grid)
+        {
+            const double hM1 = powi<M - 1>(h), hM = hM1 * h;
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) {
+                const double ind = fma(fabs(A[q][M]), hM, fabs(A[q][M - 1]) * hM1);
+                if (own[q]) errmax_hi = max(errmax_hi, (unsigned)__double2hiint(ind));
+            }
+        }
+        // ---- publish the cell: A_n are in the slot already; τ_s, τ_{s+1}, h and the flags follow
+        if (pt == 0) {
+            double* meta = ts.meta + slot_i * 4;
+            meta[0] = tau; meta[1] = last ? cfg.T : tau + h; meta[2] = h; meta[3] = last ? (double)CELL_LAST : 0.0;
+        }
+        prod_sync();
+        if (pt == 0) mbar_arrive(s_full + slot_i);
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) pcur[q] = pn[q];
+        ++s;
+        TRACE_ACC(tr_epi);
+        if (last) break;
+        tau += h;
     }
+#ifdef GCDYN_TRAJ_TRACE
+    if (lane == 0) { g_trace[7] = tr_wait; g_trace[8] = tr_stage; g_trace[9] = tr_epi; }
+#endif
     if (failed) {                                       // tell the consumers to stop (the regular exit flagged its last cell)
-        const int slot_i = s % CHEB_RING_SLOTS;
-        if (s >= CHEB_RING_SLOTS) mbar_wait(s_empty + slot_i, (uint32_t)(s / CHEB_RING_SLOTS - 1) & 1u);
-        if (pt == 0) { cs.sflag[s] = CELL_FAIL; mbar_arrive(s_full + slot_i); }
+        const int slot_i = s % RING_SLOTS;
+        if (s >= RING_SLOTS) mbar_wait(s_empty + slot_i, (uint32_t)(s / RING_SLOTS - 1) & 1u);
+        if (pt == 0) { ts.meta[slot_i * 4 + 3] = (double)CELL_FAIL; }
+        prod_sync();
+        if (pt == 0) mbar_arrive(s_full + slot_i);
     }
     TRACE_STAMP(3);
-#ifdef GCDYN_TRAJ_TRACE
-    if (lane == 0) { g_attempts = s + rejects; g_trace[1] = tr_a; g_trace[5] = tr_b; g_trace[11] = tr_c; }
-#endif
     // conditioning term and diagnostics
 #pragma unroll
     for (int q = 0; q < KPL; ++q) {
         const int i = pt + NPROD * q;
-        if (own[q]) pk.logcond[(size_t)p * K + i] = log1p(-pcur[q]);   // log(1 − p_i(T)), mbp.jl:244-245
+        if (own[q]) {
+            const double lc = log1p(-pcur[q]);                         // log(1 − p_i(T)), mbp.jl:244-245
+            pk.logcond[(size_t)p * K + i] = lc;
+            if (cheb) {                                                // its column of the coefficient row
+                double v = -lc;
+                if (!isfinite(v)) {
+                    if (cc.mv.colsum[K + 2 + i] != 0.0) atomicOr(&s_flag, 2);
+                    v = 0.0;
+                }
+                cc.A[(size_t)p * cc.mv.Jst + K + 2 + i] = v;
+            }
+        }
     }
-    const bool unresolved = failed || !(errmax_hi < tol_hi);
-    const bool anybad = prod_max_u64(__any_sync(FULL, bad) ? 1ULL : 0ULL) != 0ULL || unresolved;
+    unsigned emax = __reduce_max_sync(FULL, errmax_hi), zero = 0u;
+    prod_max2(emax, zero);
+    const bool unresolved = failed || !(emax < tol_hi);
     if (pt == 0) {
-        pk.perr[p] = __hiloint2double((int)min(errmax_hi + 1u, 0x7ff00000u), 0);   // upper bound of the largest accepted indicator
+        pk.perr[p] = __hiloint2double((int)min(emax + 1u, 0x7ff00000u), 0);   // upper bound of the largest accepted indicator
         pk.S[p] = s > 0 ? s : 1;
-        pk.pstatus[p] = anybad ? ST_SOLVER : 0;
+        pk.pstatus[p] = unresolved ? ST_SOLVER : 0;
     }
     }   // integrating warps
+#ifdef GCDYN_EXP_LATE_PDL
+    pdl_launch_dependents();
+#endif
     if (!cheb) return;
     __syncthreads();                                    // node values, status of this pset are complete and visible
     TRACE_STAMP(4);
-    cheb_finish<M>(pv, pk, cc, p, cs TRACE_PASS);
+    nodal_finish(pk, cc, p, ts, &s_flag);
 #ifdef GCDYN_TRAJ_TRACE
     __syncthreads();
+    TRACE_STAMP(5);
     if (threadIdx.x == 0) { long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); g_trace[15] = gt; }
     if (threadIdx.x == 0 && p < 1024) {
         unsigned smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
         long long* o = g_trace_out + (size_t)p * 24;
         for (int i = 0; i < 16; ++i) o[i] = g_trace[i];
-        o[16] = smid; o[17] = pw; o[18] = pk.S[p]; o[19] = g_attempts; o[20] = s_wid[0]; o[21] = s_wid[1]; o[22] = s_wid[2]; o[23] = s_wid[3];
+        o[16] = smid; o[18] = pk.S[p];
     }
 #endif
 }

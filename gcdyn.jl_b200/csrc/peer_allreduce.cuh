@@ -10,6 +10,9 @@
 // The parity alternates per call: a rank can be at most one call ahead of its slowest peer (it needs that
 // peer's flag for the current call before it can start the next), so the slots of call n+2 never overwrite
 // slots of call n that are still being read.
+// The wait is BOUNDED: a peer that never arrives (it failed before enqueueing, or died) must not leave this GPU spinning
+// inside a stream synchronisation.  After `timeout_ns` of %globaltimer the kernel gives up, writes NaN to every output
+// and raises `*err` (pinned host memory; the host-buffer entry points turn it into an error code).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -38,8 +41,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 // One CTA.  `in` = this rank's [P] partial sums, `out` = the all-reduced sums (may alias `in`; may be pinned host memory).
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(1024) peer_allreduce_kernel(PeerView pv, const double* in, double* out, int P,
-                                                              unsigned long long seq) {
+                                                              unsigned long long seq, unsigned long long timeout_ns,
+                                                              int* err) {
+    __shared__ int s_timeout;
+    if (threadIdx.x == 0) s_timeout = 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");      // launched behind finish_kernel with programmatic serialization
     const int par = (int)(seq & 1ULL);
     const size_t slot = ((size_t)par * pv.world + pv.rank) * pv.cap;
@@ -52,9 +64,18 @@ __global__ void __launch_bounds__(1024) peer_allreduce_kernel(PeerView pv, const
     if (threadIdx.x < pv.world) st_release_sys(pv.win[threadIdx.x].flag + pv.rank, seq);
     if (threadIdx.x < pv.world) {
         const unsigned long long* f = pv.win[pv.rank].flag + threadIdx.x;
-        while (ld_acquire_sys(f) < seq) __nanosleep(100);
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(f) < seq) {
+            __nanosleep(100);
+            if (global_ns() - t0 > timeout_ns) { atomicExch(&s_timeout, 1); break; }
+        }
     }
     __syncthreads();
+    if (s_timeout) {                                        // CTA-uniform after the barrier
+        for (int p = threadIdx.x; p < P; p += blockDim.x) out[p] = __longlong_as_double(0x7ff8000000000000LL);
+        if (threadIdx.x == 0 && err) *err = 1;
+        return;
+    }
     const double* local = pv.win[pv.rank].data + (size_t)par * pv.world * pv.cap;
     for (int p = threadIdx.x; p < P; p += blockDim.x) {
         double s = 0.0;

@@ -24,21 +24,20 @@ g0 = t[:, 14].min()
 rows = []
 for p in range(P):
     r = t[p]
-    rows.append(dict(p=p, sm=int(r[16]), pw=int(r[17]), S=int(r[18]), att=int(r[19]), wid0=int(r[20]),
-                     start_ns=int(r[14] - g0), end_ns=int(r[15] - g0), setup=int(r[2] - r[0]), integ=int(r[3] - r[2]),
-                     per_cell=int((r[3] - r[2]) / max(1, r[19])), wait=int(r[4] - r[3]), fold=int(r[7] - r[6]), dct=int(r[8] - r[7]),
-                     deff=int(r[9] - r[8]), write=int(r[10] - r[9]), later_cells=(int(r[1] / max(1, r[18] - 1)), int(r[5] / max(1, r[18] - 1)), int(r[11] / max(1, r[18] - 1)))))
-import collections
-by_sm = collections.defaultdict(list)
-for r in rows: by_sm[r["sm"]].append(r)
-print("SMs used", len(by_sm), "CTAs/SM histogram", collections.Counter(len(v) for v in by_sm.values()))
-same = sum(1 for v in by_sm.values() if len(v) > 1 and len({(r["wid0"] + r["pw"]) & 3 for r in v}) < len(v))
-print("SMs whose CTAs integrate on the same sub-partition:", same)
+    rows.append(dict(p=p, sm=int(r[16]), S=int(r[18]), start_ns=int(r[14] - g0), end_ns=int(r[15] - g0), setup=int(r[2] - r[0]),
+                     integ=int(r[3] - r[2]), per_cell=int((r[3] - r[2]) / max(1, r[18])), cons_after=int(r[6] - r[3]),
+                     sync=int(r[4] - max(r[3], r[6])), finish=int(r[5] - r[4]), total=int(r[5] - r[0]),
+                     c_wait=int(r[7] / max(1, r[18])), c_stage=int(r[8] / max(1, r[18])), c_epi=int(r[9] / max(1, r[18]))))
 rows.sort(key=lambda r: -r["end_ns"])
 print("kernel span ns:", rows[0]["end_ns"], " start spread ns:", max(r["start_ns"] for r in rows))
 for r in rows[:6] + rows[-3:]:
     print(r)
-for key in ("setup", "integ", "per_cell", "wait", "fold", "dct", "deff", "write"):
-    v = np.array([r[key] for r in rows]); print(f"{key:9s} mean {v.mean():9.0f} min {v.min():8d} max {v.max():8d}")
-alone = [r["per_cell"] for r in rows if len(by_sm[r["sm"]]) == 1]; shared = [r["per_cell"] for r in rows if len(by_sm[r["sm"]]) > 1]
-print("per_cell alone", np.mean(alone) if alone else None, "shared", np.mean(shared) if shared else None)
+for key in ("setup", "integ", "per_cell", "cons_after", "sync", "finish", "total", "S", "c_wait", "c_stage", "c_epi"):
+    v = np.array([r[key] for r in rows]); print(f"{key:10s} mean {v.mean():9.0f} min {v.min():8d} max {v.max():8d}")
+print("cheb", ctx.last_cheb(), "diag", {k: v for k, v in ctx.last_diag(4).items() if k != "err_indicator"})
+import collections
+by_sm = collections.defaultdict(list)
+for r in rows: by_sm[r["sm"]].append(r)
+alone = [r["c_stage"] for r in rows if len(by_sm[r["sm"]]) == 1]; shared = [r["c_stage"] for r in rows if len(by_sm[r["sm"]]) > 1]
+print("c_stage alone on its SM: n=%d mean %.0f | sharing an SM: n=%d mean %.0f" % (len(alone), np.mean(alone) if alone else 0, len(shared), np.mean(shared) if shared else 0))
+print("CTAs per SM histogram", collections.Counter(len(v) for v in by_sm.values()))
