@@ -597,20 +597,6 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
     __shared__ __align__(8) uint64_t s_full[RING_SLOTS], s_empty[RING_SLOTS];   // ring of cells → consumer warps
     __shared__ int s_flag;                              // fallback reasons collected while the integration runs
     const bool cheb = cc.D > 0;                         // CTA-uniform
-    {   // pull this pset's parameters towards the SM before anything depends on them: one memory round trip instead of
-        // one per dependent group of loads (the caller's L2 may be cold)
-        auto pf = [](const void* a) { asm volatile("prefetch.global.L1 [%0];" ::"l"(a)); };
-        const int t = threadIdx.x;
-        if (t == 0) { pf(pv.mu + p); pf(pv.delta + p); pf(pv.rho + p); pf(pv.sigma + p); }
-        if (pv.response == 2) {
-            if (t == 1) { pf(pv.xscale + p); pf(pv.xshift + p); pf(pv.yscale + p); pf(pv.yshift + p); }
-            for (int i = t * 16; i < K; i += 16 * TRAJ_THREADS) pf(pv.type_space + i);
-        } else if (pv.response == 0) {
-            for (int i = t * 16; i < K; i += 16 * TRAJ_THREADS) pf(pv.lambda + (size_t)p * K + i);
-        } else if (t == 1) pf(pv.lambda + p);
-        const char* g0 = reinterpret_cast<const char*>(pv.Gamma + (size_t)p * pv.gamma_stride);
-        for (size_t off = (size_t)t * 128; off < (size_t)K * K * 8; off += (size_t)128 * TRAJ_THREADS) pf(g0 + off);
-    }
     const int KSB = KPL == 1 ? KP : ((K + 3) & ~3);     // broadcast buffer length (multiple of 4)
     const size_t traj_doubles = 2 * (size_t)KSB + (KPL == 1 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
     const TrajSmem ts(smem + traj_doubles, K, cheb ? cc.D : 0, M);
@@ -695,22 +681,46 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
     double* cb = smem;                                  // 2 × KSB
     double* GT = smem + 2 * KSB;                        // KPL > 1 only: GT[j*K + i] = δ Γ[i,j]
 
-    const double mu = pv.mu[p], delta = pv.delta[p], rho = pv.rho[p], sigma = pv.sigma[p];
+    // ---- set-up.  Every global load is issued before the first value is used, so that a cold cache costs ONE memory
+    //      round trip, not one per dependent group (scalars → birth rates → diagonal → row of δΓ).
     const double* G = pv.Gamma + (size_t)p * pv.gamma_stride;
-    const double b = mu * (1.0 - sigma);
-
-    double lam[KPL], a[KPL];
+    const double mu = pv.mu[p], delta = pv.delta[p], rho = pv.rho[p], sigma = pv.sigma[p];
     bool own[KPL];
-    double rate = 0.0;
+    double in0[KPL], gdiag[KPL];                        // birth-rate input (λ itself, or the type value) and Γ[i,i]
+    double rs0 = 0.0, rs1 = 0.0, rs2 = 0.0, rs3 = 0.0;  // sigmoid parameters
+    if (pv.response == 2) { rs0 = pv.xscale[p]; rs1 = pv.xshift[p]; rs2 = pv.yscale[p]; rs3 = pv.yshift[p]; }
 #pragma unroll
     for (int q = 0; q < KPL; ++q) {
         const int i = pt + NPROD * q;
         own[q] = i < K;
-        lam[q] = own[q] ? birth_rate(pv, p, i) : 0.0;
-        const double gam = own[q] ? delta * -G[i + (size_t)i * K] : 0.0;
+        const int ii = own[q] ? i : 0;
+        in0[q] = pv.response == 0 ? pv.lambda[(size_t)p * K + ii] : (pv.response == 1 ? pv.lambda[p] : pv.type_space[ii]);
+        gdiag[q] = G[ii + (size_t)ii * K];
+    }
+    double g[KPL == 1 ? KP : 1];
+    if constexpr (KPL == 1) {
+        const int ii = own[0] ? pt : 0;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) g[j] = G[ii + (size_t)(j < K ? j : 0) * K];
+    }
+    const double b = mu * (1.0 - sigma);
+    double lam[KPL], a[KPL];
+    double rate = 0.0;
+#pragma unroll
+    for (int q = 0; q < KPL; ++q) {
+        double l = in0[q];                              // λ(model, type), mbp.jl:27-43
+        if (pv.response == 2) l = rs2 * (1.0 / (1.0 + exp(-(rs0 * (in0[q] - rs1))))) + rs3;
+        lam[q] = own[q] ? l : 0.0;
+        const double gam = own[q] ? delta * -gdiag[q] : 0.0;
         a[q] = lam[q] + mu;
         const double r = own[q] ? fabs(lam[q]) + fabs(mu) + 2.0 * fabs(gam) : 0.0;
         if (!(r <= rate)) rate = r;
+    }
+    if constexpr (KPL == 1) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) g[j] = (own[0] && j < K) ? delta * g[j] : 0.0;
+    } else {
+        for (int e = lane; e < K * K; e += 32) GT[e] = delta * G[e];   // G[i + j*K] → GT[j*K + i]
     }
     rate = warp_max_nan(rate);
     if (NPW > 1) {                                      // non-negative doubles (and NaN) order like their bit patterns
@@ -722,14 +732,6 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
         dummy = 0u;
         prod_max2(l0, dummy);
         rate = __hiloint2double((int)h0, (int)l0);
-    }
-
-    double g[KPL == 1 ? KP : 1];
-    if constexpr (KPL == 1) {
-#pragma unroll
-        for (int j = 0; j < KP; ++j) g[j] = (own[0] && j < K) ? delta * G[pt + (size_t)j * K] : 0.0;
-    } else {
-        for (int e = lane; e < K * K; e += 32) GT[e] = delta * G[e];   // G[i + j*K] → GT[j*K + i]
     }
     for (int e = pt; e < 2 * KSB; e += NPROD) cb[e] = 0.0;
     prod_sync();
