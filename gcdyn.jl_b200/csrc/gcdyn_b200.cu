@@ -1118,6 +1118,18 @@ int gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_l
     GUARD_END(ctx)
 }
 
+int gcdyn_last_cells(gcdyn_ctx* ctx, int32_t* cells, int32_t n_psets) {
+    GUARD_BEGIN
+    if (!ctx || !cells || n_psets <= 0) return fail(ctx, GCDYN_EINVAL, "bad argument");
+    if (n_psets > ctx->last_P || !ctx->last_pack.S || ctx->last_order <= 0)
+        return fail(ctx, GCDYN_EINVAL, "no ODE evaluation with that many psets to report on");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaDeviceSynchronize());
+    CU_TRY(ctx, cudaMemcpy(cells, ctx->last_pack.S, (size_t)n_psets * 4, cudaMemcpyDeviceToHost));
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
 int gcdyn_last_cheb_degree(gcdyn_ctx* ctx, int32_t* interp_degree, int32_t* effective_degree, int32_t* n_fallback) {
     GUARD_BEGIN
     if (!ctx) return fail(ctx, GCDYN_EINVAL, "ctx is NULL");

@@ -115,6 +115,7 @@ def _lib():
         "gcdyn_loglik_batch_resident": (C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.POINTER(Opts),
                                                   vp, vp, vp, vp]),
         "gcdyn_last_diag": (C.c_int, [vp, _p_i32, _p_i32, _p_i32, _p_f64, C.c_int32]),
+        "gcdyn_last_cells": (C.c_int, [vp, _p_i32, C.c_int32]),
         "gcdyn_probe_fp64_peak": (C.c_int, [vp, _p_f64]),
         "gcdyn_last_cheb_degree": (C.c_int, [vp, _p_i32, _p_i32, _p_i32]),
         "gcdyn_sim_forest": (C.c_int, [C.POINTER(Params), C.c_double, C.c_int32, C.c_int64, C.c_uint64, C.c_int64,
@@ -195,7 +196,12 @@ class Context:
         err = np.zeros(max(n_psets, 1))
         _check(_lib().gcdyn_last_diag(self._h, C.byref(s), C.byref(o), C.byref(nl),
                                       _ptr(err, _p_f64) if n_psets else _p_f64(), int(n_psets)), self._h)
-        return dict(steps=s.value, order=o.value, n_launches=nl.value, err_indicator=err[:n_psets])
+        out = dict(steps=s.value, order=o.value, n_launches=nl.value, err_indicator=err[:n_psets])
+        if n_psets and o.value > 0:
+            cells = np.zeros(n_psets, dtype=np.int32)
+            _check(_lib().gcdyn_last_cells(self._h, _ptr(cells, _p_i32), int(n_psets)), self._h)
+            out["cells"] = cells
+        return out
 
     def last_cheb(self):
         """Chebyshev/GEMM stage of the last ODE evaluation (all zeros if it did not run)."""

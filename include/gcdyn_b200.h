@@ -166,6 +166,10 @@ int  gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* forest, con
  * steps and order used, number of kernels launched, and per-pset error indicators [P] (may be NULL). */
 int  gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_launches,
                      double* err_indicator, int32_t n_psets);
+/* Taylor cells each of the first n_psets parameter sets of the last ODE evaluation took (host copy; synchronises).
+ * The integrator has no counterpart of the reference's `maxiters`: the number of cells is bounded by the table capacity
+ * and a parameter set that would exceed it comes back as a solver failure (-Inf), as mbp.jl:154-158 does. */
+int  gcdyn_last_cells(gcdyn_ctx* ctx, int32_t* cells, int32_t n_psets);
 
 /* Native forward simulator (host code, OpenMP): draws n_trees trees from the law of the reference's
  * rand_tree(model, present_time, init_type, n; reject_stubs, min_leaves, max_rejections)
