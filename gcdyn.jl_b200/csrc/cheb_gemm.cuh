@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, ParamsView p
                                                      long long tab_stride, int S_cap, int grid_doubles, double Tpres,
                                                      const double* __restrict__ partial, int splits,
                                                      const double* __restrict__ tree_const,
-                                                     const int* __restrict__ need_sweep, int P, int D, int* __restrict__ nflag, int* __restrict__ feedback,
+                                                     const int* __restrict__ need_sweep, int P, int D, int* __restrict__ nflag, int* __restrict__ feedback, int totals_only,
                                                      double* __restrict__ out_tree, int32_t* __restrict__ status,
                                                      double* __restrict__ out_pset) {
     __shared__ double part[8];
@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, ParamsView p
     const int64_t T = fv.n_trees;
     pdl_wait();                                            // partial sums come from the contraction
     const int pst = pk.pstatus[p];
+    if (totals_only && !(need_sweep[p] && !(pst & ST_SOLVER))) return;   // traj_kernel already wrote this pset's sum
     // psets whose interpolant was not resolved on this grid are summed exactly below.  When they are a quarter of the
     // batch the grid no longer fits the parameters: tell the host (pinned word), the next call widens it.
     if (threadIdx.x == 0 && feedback && (need_sweep[p] & 1) && !(pst & ST_SOLVER)) {

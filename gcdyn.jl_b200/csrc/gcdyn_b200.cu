@@ -98,8 +98,9 @@ struct gcdyn_forest {
     mutable double D_T = -1.0;
     mutable int* h_feedback = nullptr;    // pinned, written by finish_kernel / degree_probe_kernel
     // shared-Γ constant Σ count·log Γ_xy per tree, cached for the last Γ seen
-    mutable double* d_tree_const = nullptr;
+    mutable double* d_tree_const = nullptr;   // [T] constants, then one more slot: their sum (GCDYN_FLAG_TOTALS)
     mutable std::vector<double> tc_gamma;
+    bool any_self_loop = false;
 };
 
 struct gcdyn_comm {
@@ -108,7 +109,6 @@ struct gcdyn_comm {
     void* window = nullptr;               // this rank's allocation: data then flags
     void* peer[gcdyn::PEER_MAX_WORLD] = {};   // peers' windows as mapped here (peer[rank] == window)
     bool connected = false;
-    unsigned long long seq = 0;
     unsigned long long timeout_ns = 20000000000ULL;   // bounded wait for the peers' flags ($GCDYN_PEER_TIMEOUT_MS)
     int* h_err = nullptr;                 // pinned: raised by the kernel when a peer did not arrive in time
 };
@@ -498,22 +498,22 @@ cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t s
 template <int M>
 int launch_finish_m(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, const PsetPack& pk, const double* tab, const TrajCfg& cfg, double T,
                     const double* partial, int splits, const double* tree_const, const int* need_sweep, int P,
-                    double* out_tree, int32_t* status, double* out_pset, cudaStream_t st) {
+                    double* out_tree, int32_t* status, double* out_pset, cudaStream_t st, int totals_only) {
     cudaLaunchConfig_t lc = pdl_config(dim3((unsigned)P), dim3(256), 0, st);
     CU_TRY(ctx, cudaLaunchKernelEx(&lc, finish_kernel<M>, f->v, pv, pk, tab, cfg.tab_stride, cfg.S_cap, cfg.grid_doubles, T, partial,
-                                   splits, tree_const, need_sweep, P, f->mom.D, const_cast<int*>(need_sweep) + P, f->h_feedback, out_tree, status, out_pset));
+                                   splits, tree_const, need_sweep, P, f->mom.D, const_cast<int*>(need_sweep) + P, f->h_feedback, totals_only, out_tree, status, out_pset));
     return GCDYN_OK;
 }
 
 int launch_finish(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const ParamsView& pv, const PsetPack& pk, const double* tab, const TrajCfg& cfg,
                   double T, const double* partial, int splits, const double* tree_const, const int* need_sweep, int P,
-                  double* out_tree, int32_t* status, double* out_pset, cudaStream_t st) {
+                  double* out_tree, int32_t* status, double* out_pset, cudaStream_t st, int totals_only = 0) {
     switch (M) {
-        case 8: return launch_finish_m<8>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
-        case 12: return launch_finish_m<12>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
-        case 16: return launch_finish_m<16>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
-        case 20: return launch_finish_m<20>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
-        case 24: return launch_finish_m<24>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st);
+        case 8: return launch_finish_m<8>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only);
+        case 12: return launch_finish_m<12>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only);
+        case 16: return launch_finish_m<16>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only);
+        case 20: return launch_finish_m<20>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only);
+        case 24: return launch_finish_m<24>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only);
     }
     return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
 }
@@ -586,29 +586,54 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             cc.need_sweep = need_sweep;
             cc.nflag = need_sweep + P;
         }
-        rc = launch_traj(ctx, M, pv, pk, cfg, cc, ctx->table.as<double>(), st);
-        if (rc) return rc;
-        ++launches;
-        if (prof) cudaEventRecord(ctx->ev[2], st);
+        const double* tree_const = nullptr;
+        // (the calibrating first call takes the full path once; its repetition on the adopted grid is the totals call)
+        const bool totals = use_gemm && (flags & GCDYN_FLAG_TOTALS) && !calibrating;
         if (use_gemm) {
-            const MomentView& mv = f->mom;
-            const double* tree_const = nullptr;
             if (cc.compact_tc) {
                 // shared Γ: Σ count·log Γ_xy is the same for every pset — one constant per tree, recomputed only
-                // when Γ (or the moments it is built from) changed since the last call on this forest
+                // when Γ (or the moments it is built from) changed since the last call on this forest; done BEFORE the
+                // trajectory kernel so that nothing stands between it and the contraction
                 const size_t kk = (size_t)K * K;
-                if (!f->d_tree_const) CU_TRY(ctx, cudaMalloc(&f->d_tree_const, std::max<size_t>((size_t)Tn * 8, 8)));
+                if (!f->d_tree_const) CU_TRY(ctx, cudaMalloc(&f->d_tree_const, ((size_t)Tn + 1) * 8));
                 const bool same = host_gamma_shared && f->tc_gamma.size() == kk &&
                                   std::memcmp(f->tc_gamma.data(), host_gamma_shared, kk * 8) == 0;
                 if (!same) {
-                    tc_const_kernel<<<(unsigned)((Tn + 7) / 8), 256, 0, st>>>(mv, Tn, pv.Gamma, f->d_tree_const);
+                    tc_const_kernel<<<(unsigned)((Tn + 7) / 8), 256, 0, st>>>(f->mom, Tn, pv.Gamma, f->d_tree_const);
                     CU_TRY(ctx, cudaGetLastError());
-                    ++launches;
+                    reduce_kernel<<<1, 256, 0, st>>>(f->d_tree_const, Tn, f->d_tree_const + Tn);   // their sum, for the totals path
+                    CU_TRY(ctx, cudaGetLastError());
+                    launches += 2;
                     if (host_gamma_shared) f->tc_gamma.assign(host_gamma_shared, host_gamma_shared + kk);
                     else f->tc_gamma.clear();
                 }
                 tree_const = f->d_tree_const;
             }
+            if (totals) {
+                cc.totals = d_out_pset;
+                cc.tc_total = tree_const ? tree_const + Tn : nullptr;
+                cc.any_self_loop = f->any_self_loop ? 1 : 0;
+            }
+        }
+        rc = launch_traj(ctx, M, pv, pk, cfg, cc, ctx->table.as<double>(), st);
+        if (rc) return rc;
+        ++launches;
+        if (prof) cudaEventRecord(ctx->ev[2], st);
+        if (totals) {
+            // the per-pset sums are already in d_out_pset; finish_kernel only redoes the psets the grid did not resolve
+            if (prof) { cudaEventRecord(ctx->ev[3], st); cudaEventRecord(ctx->ev[4], st); cudaEventRecord(ctx->ev[5], st); }
+            rc = launch_finish(ctx, M, f, pv, pk, ctx->table.as<double>(), cfg, T, nullptr, 0, nullptr, need_sweep, P,
+                               d_out_tree, d_status, d_out_pset, st, 1);
+            if (rc) return rc;
+            ++launches;
+            if (prof) { cudaEventRecord(ctx->ev[6], st); ctx->ev_valid = true; }
+            ctx->last_cheb_D = cc.D; ctx->last_feedback = f->h_feedback; ctx->last_steps = cfg.S_cap; ctx->last_order = M;
+            ctx->last_launches = launches; ctx->last_P = P; ctx->last_pack = pk;
+            if (pk_out) *pk_out = pk;
+            return GCDYN_OK;
+        }
+        if (use_gemm) {
+            const MomentView& mv = f->mom;
             if (prof) cudaEventRecord(ctx->ev[3], st);
             dim3 grid((unsigned)((Tn + GT_TILE - 1) / GT_TILE), (unsigned)((P + GT_TILE - 1) / GT_TILE));
             if (!ctx->gemm_attr_set) {
@@ -818,6 +843,7 @@ int forest_create_impl(gcdyn_ctx* ctx, const gcdyn_forest_desc* d, gcdyn_forest*
     if (!f) return fail(ctx, GCDYN_ENOMEM, "host allocation failed");
     f->device = ctx->device;
     f->max_tree_items = max_items;
+    if (d->self_loop) for (int64_t t = 0; t < T; ++t) if (d->self_loop[t]) { f->any_self_loop = true; break; }
     ForestView& v = f->v;
     v.n_trees = T; v.n_nodes = N; v.n_items = n_items; v.K = K;
     if (!d->live) live_all.assign((size_t)std::max<int64_t>(N, 1), 1);
@@ -880,6 +906,7 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
     const ParamsView pv = view_of(pr, L, ctx->params_blob.as<double>());
 
     const bool want_rows = out_tree_pset || status;
+    if ((o.flags & GCDYN_FLAG_TOTALS) && want_rows) return fail(ctx, GCDYN_EINVAL, "GCDYN_FLAG_TOTALS produces no per-tree values: out_tree_pset and status must be NULL");
     if (status) CU_TRY(ctx, ctx->status.ensure((size_t)P * Tn * 4));
     if (comm) CU_TRY(ctx, ctx->out_pset.ensure((size_t)P * 8));
     // the per-pset sums are written by the last kernel straight into pinned host memory (device-accessible under
@@ -1084,6 +1111,8 @@ int gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcd
     const int M = normalise_order(o.order);
     if (M < 0) return fail(ctx, GCDYN_EINVAL, "order must be 0, 8, 12, 16, 20 or 24");
     if (o.steps < 0 || o.steps > S_CAP) return fail(ctx, GCDYN_EINVAL, "steps out of range");
+    if ((o.flags & GCDYN_FLAG_TOTALS) && (d_out_tree_pset || d_status))
+        return fail(ctx, GCDYN_EINVAL, "GCDYN_FLAG_TOTALS produces no per-tree values: d_out_tree_pset and d_status must be NULL");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
     return enqueue_eval(ctx, f, dp->v, dp->rate_max, present_time, method, M, o.steps, o.tol > 0.0 ? o.tol : 1e-11,
@@ -1319,7 +1348,7 @@ extern "C" int gcdyn_comm_create(gcdyn_ctx* ctx, int32_t rank, int32_t world, in
     }
     if (cudaHostAlloc(&c->h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); c->h_err = nullptr; }
     else *c->h_err = 0;
-    const size_t bytes = comm_data_bytes(world, c->cap) + (size_t)world * sizeof(unsigned long long);
+    const size_t bytes = comm_data_bytes(world, c->cap) + ((size_t)world + 1) * sizeof(unsigned long long);   // data | flags | call counter
     cudaError_t e = cudaMalloc(&c->window, bytes);
     if (e == cudaSuccess) e = cudaMemset(c->window, 0, bytes);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -1365,9 +1394,9 @@ int comm_enqueue(gcdyn_comm* c, const double* d_in, double* out, int n_psets, cu
         pv.win[r].data = static_cast<double*>(c->peer[r]);
         pv.win[r].flag = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->peer[r]) + comm_data_bytes(c->world, c->cap));
     }
-    ++c->seq;
+    pv.seq_dev = pv.win[c->rank].flag + c->world;
     cudaLaunchConfig_t lc = pdl_config(dim3(1), dim3(1024), 0, st);
-    CU_TRY(ctx, cudaLaunchKernelEx(&lc, gcdyn::peer_allreduce_kernel, pv, d_in, out, n_psets, c->seq, c->timeout_ns, c->h_err));
+    CU_TRY(ctx, cudaLaunchKernelEx(&lc, gcdyn::peer_allreduce_kernel, pv, d_in, out, n_psets, c->timeout_ns, c->h_err));
     return GCDYN_OK;
 }
 }  // namespace
@@ -1421,6 +1450,10 @@ struct gcdyn_mh {
     bool have_ll = false;
     void* hist = nullptr;              // device history buffer (grow-only)
     size_t hist_cap = 0;
+    // one Metropolis iteration (propose → trajectory → finish → [all-reduce] → accept → tick) captured as a CUDA graph
+    cudaGraphExec_t graph = nullptr;
+    int graph_D = 0;                   // nodal grid degree the captured iteration was built for
+    int64_t uncaptured_iters = 0;      // iterations run launch by launch (diagnostics)
 };
 
 extern "C" int gcdyn_mh_create(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_mh_desc* d, double present_time,
@@ -1454,7 +1487,7 @@ extern "C" int gcdyn_mh_create(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdy
     }
     // blob: xscale xshift yscale yshift mu delta rho sigma [C each] | type_space [K] | Gamma [K*K] | theta prop [6C each]
     //       | ll ll_prop [C each] | accepted [C i64] | inside [C i32]
-    const size_t nd = (size_t)8 * C + K + (size_t)K * K + (size_t)2 * gcdyn::MH_DIM * C + 2 * (size_t)C + C + (C + 1) / 2 + 8;
+    const size_t nd = (size_t)8 * C + K + (size_t)K * K + (size_t)2 * gcdyn::MH_DIM * C + 2 * (size_t)C + C + (C + 1) / 2 + 8 + 8;
     cudaError_t e = cudaMalloc(&m->blob, nd * 8);
     if (e != cudaSuccess) { delete m; return fail(ctx, GCDYN_ECUDA, cudaGetErrorString(e)); }
     std::vector<double> h(nd, 0.0);
@@ -1464,7 +1497,8 @@ extern "C" int gcdyn_mh_create(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdy
     const size_t o_xs = take(C), o_xsh = take(C), o_ys = take(C), o_ysh = take(C), o_mu = take(C), o_de = take(C);
     const size_t o_rho = take(C), o_sig = take(C), o_ts = take(K), o_G = take((size_t)K * K);
     const size_t o_th = take((size_t)gcdyn::MH_DIM * C), o_pr = take((size_t)gcdyn::MH_DIM * C);
-    const size_t o_ll = take(C), o_llp = take(C), o_acc = take(C), o_in = take((C + 1) / 2);
+    const size_t o_ll = take(C), o_llp = take(C), o_acc = take(C), o_in = take((C + 1) / 2 + 1);
+    const size_t o_it = take(1), o_hist = take(4);
     for (int c = 0; c < C; ++c) { h[o_rho + c] = d->rho; h[o_sig + c] = d->sigma; }
     std::memcpy(&h[o_ts], d->type_space, (size_t)K * 8);
     std::memcpy(&h[o_G], d->Gamma, (size_t)K * K * 8);
@@ -1484,6 +1518,8 @@ extern "C" int gcdyn_mh_create(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdy
     v.mu = base + o_mu; v.delta = base + o_de;
     for (int j = 0; j < gcdyn::MH_DIM; ++j) { v.lower[j] = d->lower[j]; v.upper[j] = d->upper[j]; }
     v.step = d->step; v.seed = d->seed;
+    v.it_dev = reinterpret_cast<unsigned long long*>(base + o_it);
+    v.hist = reinterpret_cast<gcdyn::MhView::Hist*>(base + o_hist);
     *out = m;
     return GCDYN_OK;
     GUARD_END(ctx)
@@ -1493,7 +1529,7 @@ namespace {
 // one batched likelihood of the C parameter sets currently in the blob → dst[C] (all-reduced when sharded)
 int mh_loglik(gcdyn_mh* m, double* dst, cudaStream_t st) {
     gcdyn_ctx* ctx = m->ctx;
-    int rc = enqueue_eval(ctx, m->forest, m->pv, m->rate_bound, m->T, GCDYN_METHOD_ODE, 16, 0, 1e-11, 0, m->host_gamma.data(),
+    int rc = enqueue_eval(ctx, m->forest, m->pv, m->rate_bound, m->T, GCDYN_METHOD_ODE, 16, 0, 1e-11, GCDYN_FLAG_TOTALS, m->host_gamma.data(),
                           dst, nullptr, nullptr, st, nullptr, m->rate_typical);
     if (rc && m->comm) {              // release the peers with NaN sums (see batch_impl), then report the local error
         const std::string why = ctx->err;
@@ -1527,21 +1563,66 @@ extern "C" int gcdyn_mh_run(gcdyn_mh* m, int64_t iterations, double* theta_hist,
         d_ht = static_cast<double*>(m->hist);
         d_hl = d_ht + (size_t)iterations * C * gcdyn::MH_DIM;
     }
+    // where this run's history rows go (read by mh_accept_kernel through device memory, so the captured graph is
+    // the same for every run) and the iteration the device counter stands at
+    {
+        gcdyn::MhView::Hist h{d_ht, d_hl, (long long)m->iteration, (long long)iterations};
+        const unsigned long long it0 = (unsigned long long)m->iteration;
+        CU_TRY(ctx, cudaMemcpyAsync(m->v.hist, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+        CU_TRY(ctx, cudaMemcpyAsync(m->v.it_dev, &it0, sizeof(it0), cudaMemcpyHostToDevice, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));            // h, it0 are stack variables
+    }
     if (!m->have_ll) {
         gcdyn::mh_state_params_kernel<<<blocks, threads, 0, st>>>(m->v);
         CU_TRY(ctx, cudaGetLastError());
-        int rc = mh_loglik(m, m->v.ll, st);
+        int rc = mh_loglik(m, m->v.ll, st);                 // also calibrates the forest's nodal grid (synchronises once)
         if (rc) return rc;
         m->have_ll = true;
     }
-    for (int64_t i = 0; i < iterations; ++i) {
-        const uint64_t it = (uint64_t)(m->iteration + 1);
-        gcdyn::mh_propose_kernel<<<blocks, threads, 0, st>>>(m->v, it);
+    auto enqueue_iteration = [&]() -> int {
+        gcdyn::mh_propose_kernel<<<blocks, threads, 0, st>>>(m->v);
         CU_TRY(ctx, cudaGetLastError());
         int rc = mh_loglik(m, m->v.ll_prop, st);
         if (rc) return rc;
-        gcdyn::mh_accept_kernel<<<blocks, threads, 0, st>>>(m->v, it, d_ht, d_hl, (long long)i);
+        gcdyn::mh_accept_kernel<<<blocks, threads, 0, st>>>(m->v);
         CU_TRY(ctx, cudaGetLastError());
+        gcdyn::mh_tick_kernel<<<1, 1, 0, st>>>(m->v);
+        CU_TRY(ctx, cudaGetLastError());
+        return GCDYN_OK;
+    };
+    const bool use_graph = std::getenv("GCDYN_MH_NO_GRAPH") == nullptr;
+    const gcdyn_forest* f = m->forest;
+    for (int64_t i = 0; i < iterations; ++i) {
+        // the captured iteration is valid as long as the forest's grid degree stands; a pending widening request (a
+        // quarter of a batch unresolved) is served by one launch-by-launch iteration, then the graph is re-captured
+        const bool widen_pending = f->h_feedback && f->D_cur > 0 && f->h_feedback[0] == f->D_cur && f->D_cur < 128;
+        if (use_graph && m->graph && (m->graph_D != f->D_cur || widen_pending)) {
+            cudaGraphExecDestroy(m->graph);
+            m->graph = nullptr;
+        }
+        if (use_graph && !m->graph && !widen_pending && m->uncaptured_iters > 0) {
+            // capture ONE iteration: every workspace already has its size (an uncaptured iteration ran before)
+            cudaGraph_t g = nullptr;
+            CU_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueue_iteration();
+            const cudaError_t ce = cudaStreamEndCapture(st, &g);
+            if (rc || ce != cudaSuccess || !g) {
+                if (g) cudaGraphDestroy(g);
+                cudaGetLastError();
+                return rc ? rc : fail(ctx, GCDYN_ECUDA, std::string("graph capture of a Metropolis iteration failed: ") + cudaGetErrorString(ce));
+            }
+            const cudaError_t ie = cudaGraphInstantiate(&m->graph, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { m->graph = nullptr; return fail(ctx, GCDYN_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+            m->graph_D = f->D_cur;
+        }
+        if (use_graph && m->graph) {
+            CU_TRY(ctx, cudaGraphLaunch(m->graph, st));
+        } else {
+            const int rc = enqueue_iteration();
+            if (rc) return rc;
+            ++m->uncaptured_iters;
+        }
         ++m->iteration;
     }
     if (d_ht) {
@@ -1596,6 +1677,7 @@ extern "C" void gcdyn_mh_destroy(gcdyn_mh* m) {
     cudaGetDevice(&prev);
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
+    if (m->graph) cudaGraphExecDestroy(m->graph);
     if (m->blob) cudaFree(m->blob);
     if (m->hist) cudaFree(m->hist);
     cudaSetDevice(prev);

@@ -199,6 +199,10 @@ struct ChebCfg {
     double* A;             // [P][Jst] coefficient rows of the GEMM: count columns | F_x(τ_k), node-major | K² block
     int* need_sweep;       // [P] fallback flags: 1 = interpolant unresolved, 2 = non-finite node-term logs
     int* nflag;            // [1] psets of this batch that were unresolved (reset by traj_kernel, counted by finish_kernel)
+    // GCDYN_FLAG_TOTALS: out_pset[p] = Σ_j A[p][j]·colsum[j] + tc_total straight from traj_kernel (nullptr = off)
+    double* totals;        // [P]
+    const double* tc_total;   // [1] Σ_t tree_const[t] (shared Γ), or nullptr
+    int any_self_loop;     // the forest holds a tree the reference gives -Inf for
 };
 
 // Cell containing τ on a pset's (non-uniform) grid: largest s < S with grid[s] ≤ τ.
@@ -542,7 +546,7 @@ __device__ __forceinline__ void nodal_finish(const PsetPack& pk, const ChebCfg& 
     const int pst = pk.pstatus[p];
     if (pst & ST_SOLVER) {                               // CTA-uniform: a failed trajectory has no usable nodes; it is
         for (int idx = threadIdx.x; idx < NV; idx += blockDim.x) Arow[C1 + idx] = 0.0;   // -Inf through its status
-        if (threadIdx.x == 0) cfg.need_sweep[p] = 0;
+        if (threadIdx.x == 0) { cfg.need_sweep[p] = 0; if (cfg.totals) cfg.totals[p] = -CUDART_INF; }
         return;
     }
     // a_{D−j} = (2/D) Σ''_k V_k (−1)^k cos(π k j / D) for j = 0, 1, 2 (a_D halved).  NSEG threads per type share the
@@ -576,7 +580,27 @@ __device__ __forceinline__ void nodal_finish(const PsetPack& pk, const ChebCfg& 
         if (!(last3 <= cfg.tol)) unresolved = true;
     }
     const int any_unres = __syncthreads_or(unresolved ? 1 : 0);
-    if (threadIdx.x == 0) cfg.need_sweep[p] = *s_flag | (any_unres ? 1 : 0);
+    const int flag = *s_flag | (any_unres ? 1 : 0);
+    if (threadIdx.x == 0) cfg.need_sweep[p] = flag;
+    if (cfg.totals && !flag) {
+        // Σ_j A[p][j]·colsum[j]: the count columns (read back: other threads of this CTA wrote them before the barrier),
+        // the node values still in shared memory, the K² block when every pset has its own Γ.  Fixed order.
+        __shared__ double tpart[TRAJ_THREADS / 32];
+        double acc = 0.0;
+        for (int c = threadIdx.x; c < C1; c += blockDim.x) acc = fma(__ldcg(Arow + c), mv.colsum[c], acc);
+        for (int idx = threadIdx.x; idx < NV; idx += blockDim.x) acc = fma(V[idx], mv.colsum[C1 + idx], acc);
+        if (!cfg.compact_tc)
+            for (int e = threadIdx.x; e < K * K; e += blockDim.x) acc = fma(__ldcg(Arow + mv.Jtc + e), mv.colsum[mv.Jtc + e], acc);
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) tpart[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sum = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += tpart[w];
+            if (cfg.tc_total) sum += *cfg.tc_total;
+            cfg.totals[p] = cfg.any_self_loop ? -CUDART_INF : sum;
+        }
+    }
 }
 
 template <int M, int KP, int KPL, int NPW>

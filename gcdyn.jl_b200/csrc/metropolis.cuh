@@ -39,13 +39,18 @@ struct MhView {
     double lower[MH_DIM], upper[MH_DIM];
     double step;
     uint64_t seed;
+    // device-side bookkeeping, so that ONE captured CUDA graph serves every iteration: the number of completed
+    // iterations (the kernels derive their random-number counter from it) and where history rows go
+    unsigned long long* it_dev;     // [1]
+    struct Hist { double* theta; double* ll; long long base; long long rows; }* hist;   // [1]
 };
 
 // One thread per chain: Gaussian random-walk proposal (Box–Muller on slots 2j, 2j+1), box test, and the
 // canonical parameters of the (clipped) proposal written straight into the likelihood's parameter blob.
-__global__ void mh_propose_kernel(MhView v, uint64_t it) {
+__global__ void mh_propose_kernel(MhView v) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= v.C) return;
+    const uint64_t it = *v.it_dev + 1;
     bool in = true;
     double q[MH_DIM];
 #pragma unroll
@@ -69,10 +74,13 @@ __global__ void mh_propose_kernel(MhView v, uint64_t it) {
 }
 
 // Metropolis accept/reject (flat prior: the ratio is the likelihood ratio); history rows are optional.
-__global__ void mh_accept_kernel(MhView v, uint64_t it, double* __restrict__ hist_theta, double* __restrict__ hist_ll,
-                                 long long hist_row) {
+__global__ void mh_accept_kernel(MhView v) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= v.C) return;
+    const uint64_t it = *v.it_dev + 1;
+    const long long hist_row = (long long)(it - 1) - v.hist->base;
+    double* __restrict__ hist_theta = (hist_row >= 0 && hist_row < v.hist->rows) ? v.hist->theta : nullptr;
+    double* __restrict__ hist_ll = v.hist->ll;
     const double logu = log(mh_uniform(v.seed, it, c, 2 * MH_DIM));
     const double llp = v.ll_prop[c], llc = v.ll[c];
     const bool acc = v.inside[c] && (logu < llp - llc);        // NaN compares false: never accepted
@@ -88,6 +96,9 @@ __global__ void mh_accept_kernel(MhView v, uint64_t it, double* __restrict__ his
         hist_ll[(size_t)hist_row * v.C + c] = v.ll[c];
     }
 }
+
+// one iteration completed (its own launch: every block of mh_accept_kernel has read the counter by then)
+__global__ void mh_tick_kernel(MhView v) { *v.it_dev += 1; }
 
 // parameters of the CURRENT state into the blob (initial likelihood)
 __global__ void mh_state_params_kernel(MhView v) {

@@ -29,6 +29,8 @@ constexpr int PEER_MAX_WORLD = 16;
 struct PeerView {
     PeerWindow win[PEER_MAX_WORLD];    // win[r] = rank r's window as mapped in this process (win[rank] is local)
     int rank, world, cap;
+    unsigned long long* seq_dev;       // this rank's call counter, in device memory: the kernel takes the next sequence
+                                       // number from it, so a captured CUDA graph can replay the all-reduce unchanged
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -48,11 +50,11 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 
 __global__ void __launch_bounds__(1024) peer_allreduce_kernel(PeerView pv, const double* in, double* out, int P,
-                                                              unsigned long long seq, unsigned long long timeout_ns,
-                                                              int* err) {
+                                                              unsigned long long timeout_ns, int* err) {
     __shared__ int s_timeout;
     if (threadIdx.x == 0) s_timeout = 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");      // launched behind finish_kernel with programmatic serialization
+    const unsigned long long seq = *pv.seq_dev + 1;         // every rank makes the same number of calls
     const int par = (int)(seq & 1ULL);
     const size_t slot = ((size_t)par * pv.world + pv.rank) * pv.cap;
     for (int i = threadIdx.x; i < P * pv.world; i += blockDim.x) {
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(1024) peer_allreduce_kernel(PeerView pv, const
     if (s_timeout) {                                        // CTA-uniform after the barrier
         for (int p = threadIdx.x; p < P; p += blockDim.x) out[p] = __longlong_as_double(0x7ff8000000000000LL);
         if (threadIdx.x == 0 && err) *err = 1;
+        if (threadIdx.x == 0) *pv.seq_dev = seq;
         return;
     }
     const double* local = pv.win[pv.rank].data + (size_t)par * pv.world * pv.cap;
@@ -82,6 +85,8 @@ __global__ void __launch_bounds__(1024) peer_allreduce_kernel(PeerView pv, const
         for (int r = 0; r < pv.world; ++r) s += __ldcg(local + (size_t)r * pv.cap + p);
         out[p] = s;
     }
+    __syncthreads();                                        // everybody has read seq
+    if (threadIdx.x == 0) *pv.seq_dev = seq;
 }
 
 }  // namespace gcdyn

@@ -26,6 +26,7 @@ __all__ = ["loglikelihood", "naive_loglikelihood", "stadler_appx_loglikelihood",
 METHOD_CODE = {"ode": 0, "naive": 1, "stadler": 2, "stadler_unconditioned": 3}
 STATUS_SELF_LOOP, STATUS_SOLVER, STATUS_DOMAIN = 1, 2, 4
 FLAG_SWEEP_ONLY = 4
+FLAG_TOTALS = 8
 
 _ERRNAMES = {-1: "EINVAL", -2: "ECUDA", -3: "ENOMEM", -4: "EUNSUPPORTED", -5: "ENODEVICE"}
 

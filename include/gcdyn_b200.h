@@ -125,6 +125,12 @@ typedef struct {
 } gcdyn_opts;
 
 #define GCDYN_FLAG_SWEEP_ONLY 4 /* per-tree sums by the item sweep only (skip the Chebyshev-moment GEMM) */
+#define GCDYN_FLAG_TOTALS     8 /* only out_pset is wanted (what loglikelihood(model, trees, T) returns, mbp.jl:250-259):
+                                   the per-pset sums come straight from the trajectory kernel as the product of the pset's
+                                   coefficient row with the forest's COLUMN SUMS of the moment matrix - no per-tree values are
+                                   formed, out_tree_pset and status must be NULL.  Same value as the sum of the per-tree
+                                   path up to the order of summation (~1e-14 relative).  A forest containing a self-loop
+                                   gives -Inf, as the plain sum would. */
 
 int  gcdyn_version(void);
 int  gcdyn_device_count(void);

@@ -399,3 +399,37 @@ def test_per_pset_gamma_and_device_sigmoid_across_kernel_layouts(ctx, K):
     for i in (0, 8):
         want = oracle.loglikelihood_shared(models[i], trees, 2.5)
         assert abs(out[i] - want) <= SUM_RTOL * abs(want), i
+
+
+def test_totals_path_equals_the_sum_of_the_per_tree_path(ctx):
+    """GCDYN_FLAG_TOTALS: per-pset sums from the coefficient rows and the forest's column sums, no contraction and no
+    per-tree values.  Same numbers as summing the per-tree path (to the order of summation), −Inf for a failed pset and
+    for a forest with a self-loop, EINVAL when per-tree outputs are requested with it."""
+    from gcdyn.likelihood import FLAG_TOTALS, GcdynError
+    flat, params, T, exp, _ = load_golden("g2_config2")
+    forest = gcdyn.Forest(flat, None, T, ctx=ctx)
+    big = _tile(params, 12)
+    big.mu = big.mu.copy()
+    big.mu[5] *= 1.3
+    big.mu[7] = np.nan                                           # a failed trajectory
+    full, tp, st = evaluate(forest, big, T, per_tree=True)
+    tot, _, _ = evaluate(forest, big, T, want_status=False, flags=FLAG_TOTALS)
+    keep = np.arange(12) != 7
+    assert np.isneginf(tot[7]) and np.isneginf(full[7])
+    assert rel(tot[keep], full[keep]) <= 1e-12
+    assert abs(tot[0] - exp["ode_branch"].sum()) <= SUM_RTOL * abs(exp["ode_branch"].sum())
+    with pytest.raises(GcdynError):
+        evaluate(forest, big, T, per_tree=True, flags=FLAG_TOTALS)
+    # psets the grid cannot take are still summed exactly (finish_kernel runs for them alone)
+    ts = np.linspace(-2, 2, 6)
+    rng = np.random.default_rng(16)
+    mk = lambda ys, mu, sig: gcdyn.SigmoidalBranchingProcess(1.5, 0.0, ys, 0.5, mu, 1.0, 0.5, sig, ts)
+    trees = gcdyn.rand_tree(mk(2.5, 1.0, 0.1), 3.0, ts[2], 12, rng=rng)
+    models = [mk(2.5 * f, 1.0, 0.1) for f in np.linspace(0.8, 1.2, 8)]
+    models[3] = mk(2.5, 1.0, 0.0)                                # log σ = −Inf where the forest has sampled deaths
+    f2 = gcdyn.Forest(trees, ts, 3.0, ctx=ctx)
+    full2, _, _ = evaluate(f2, pack_params(models), 3.0)
+    tot2, _, _ = evaluate(f2, pack_params(models), 3.0, want_status=False, flags=FLAG_TOTALS)
+    fin = np.isfinite(full2)
+    assert ctx.last_cheb()["n_fallback"] >= 1 and not fin[3] and np.isneginf(tot2[3])
+    assert np.array_equal(fin, np.isfinite(tot2)) and rel(tot2[fin], full2[fin]) <= 1e-12
