@@ -269,14 +269,13 @@ def run_gpu(args):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
             peer = None
-        allreduce_kind = "peer-memory kernel (gcdyn_comm_allreduce)" if peer else "nccl"
+        allreduce_kind = "peer memory, fused into finish_kernel (gcdyn_loglik_batch_resident_sharded)" if peer else "nccl"
 
     def step_resident():
+        # N > 1: gcdyn_loglik_batch_resident_sharded — the all-reduce of the [P] sums is fused into finish_kernel
         evaluate_resident(forest, dpar, T, out.data_ptr(), out_tree.data_ptr(), 0, stream.cuda_stream,
-                          steps=args.taylor_steps, order=args.order)
-        if peer is not None:
-            peer.allreduce(out.data_ptr(), P, stream.cuda_stream)
-        elif world > 1:
+                          steps=args.taylor_steps, order=args.order, comm=peer)
+        if peer is None and world > 1:
             dist.all_reduce(out)
 
     def barrier():
@@ -450,7 +449,7 @@ def run_gpu(args):
                 "taylor_order": M, "max_err_indicator": float(np.max(diag["err_indicator"])),
                 "allreduce": allreduce_kind}),
             "clocks": clocks, "e2e": e2e, "cold": cold,
-            "gpu_launches": (launches_per_step + (1 if peer is not None else 0)) * args.steps,
+            "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "parity": parity}
     if cpu:
         line["cpu_baseline"] = cpu

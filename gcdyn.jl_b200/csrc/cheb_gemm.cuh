@@ -21,6 +21,7 @@
 // are re-done exactly (item sums from the Taylor table) inside finish_kernel.
 #pragma once
 #include "kernels.cuh"
+#include "peer_allreduce.cuh"
 
 namespace gcdyn {
 
@@ -389,14 +390,20 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, ParamsView p
                                                      const double* __restrict__ tree_const,
                                                      const int* __restrict__ need_sweep, int P, int D, int* __restrict__ nflag, int* __restrict__ feedback, int totals_only,
                                                      double* __restrict__ out_tree, int32_t* __restrict__ status,
-                                                     double* __restrict__ out_pset) {
+                                                     double* __restrict__ out_pset, FusedAllReduce fc) {
     __shared__ double part[8];
+    __shared__ double s_total;
     const int p = blockIdx.x;
     const int K = fv.K;
     const int64_t T = fv.n_trees;
     pdl_wait();                                            // partial sums come from the contraction
     const int pst = pk.pstatus[p];
-    if (totals_only && !(need_sweep[p] && !(pst & ST_SOLVER))) return;   // traj_kernel already wrote this pset's sum
+    const bool redo = need_sweep[p] && !(pst & ST_SOLVER);
+    const bool sharded = fc.pv.world > 1;
+    if (totals_only && !redo) {                            // traj_kernel already formed this pset's sum
+        if (!sharded) return;
+        if (threadIdx.x == 0) s_total = fc.totals_in[p];
+    } else {
     // psets whose interpolant was not resolved on this grid are summed exactly below.  When they are a quarter of the
     // batch the grid no longer fits the parameters: tell the host (pinned word), the next call widens it.
     if (threadIdx.x == 0 && feedback && (need_sweep[p] & 1) && !(pst & ST_SOLVER)) {
@@ -472,7 +479,55 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, ParamsView p
     if (threadIdx.x == 0) {
         double s = 0.0;
         for (int w = 0; w < nwarps; ++w) s += part[w];
-        out_pset[p] = s;
+        s_total = s;
+    }
+    }
+    if (!sharded) {
+        if (threadIdx.x == 0) out_pset[p] = s_total;
+        return;
+    }
+    // ---- trees sharded over ranks: the all-reduce of the [P] sums is part of this kernel.  Every CTA stores its pset's
+    //      sum as a self-validating entry straight into slot `rank` of EVERY rank's window (P2P stores over NVLink, no
+    //      fence); the CTA that arrives last polls the entries of all ranks (bounded) and adds them in rank order, so every
+    //      rank ends with bit-identical sums and no collective is launched.
+    __shared__ int s_last, s_timeout;
+    __shared__ unsigned long long s_seq;
+    const PeerView& pr = fc.pv;
+    if (threadIdx.x == 0) {
+        const unsigned long long seq = *pr.seq_dev + 1;     // read before this CTA counts itself: the last CTA bumps it
+        s_seq = seq;
+        s_timeout = 0;
+        const size_t slot = ((size_t)(seq & 1ULL) * pr.world + pr.rank) * pr.cap + p;
+        for (int r = 0; r < pr.world; ++r) ll_store(pr.win[r].ll + slot, s_total, (unsigned)seq);
+        s_last = atomicAdd(fc.done, 1) == P - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+#ifdef GCDYN_COMM_TRACE
+    unsigned long long tr0 = global_ns();
+#endif
+    const unsigned long long seq = s_seq;
+    if (threadIdx.x == 0) *fc.done = 0;
+    const uint4* local = pr.win[pr.rank].ll + (size_t)(seq & 1ULL) * pr.world * pr.cap;
+    const unsigned long long t0 = global_ns();
+    for (int q = threadIdx.x; q < P; q += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < pr.world; ++r) {
+            double v;
+            while (!ll_load(local + (size_t)r * pr.cap + q, (unsigned)seq, v)) {
+                if (global_ns() - t0 > fc.timeout_ns) { s_timeout = 1; v = __longlong_as_double(0x7ff8000000000000LL); break; }
+            }
+            s += v;
+        }
+        out_pset[q] = s;
+    }
+    __syncthreads();
+#ifdef GCDYN_COMM_TRACE
+    if (threadIdx.x == 0) printf("rank %d seq %llu: last CTA arrived, then %llu ns until every entry was in and summed\n", pr.rank, seq, global_ns() - tr0);
+#endif
+    if (threadIdx.x == 0) {
+        if (s_timeout && fc.err) *fc.err = 1;
+        *pr.seq_dev = seq;
     }
 }
 

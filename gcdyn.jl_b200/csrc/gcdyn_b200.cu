@@ -498,35 +498,45 @@ cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t s
 template <int M>
 int launch_finish_m(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, const PsetPack& pk, const double* tab, const TrajCfg& cfg, double T,
                     const double* partial, int splits, const double* tree_const, const int* need_sweep, int P,
-                    double* out_tree, int32_t* status, double* out_pset, cudaStream_t st, int totals_only) {
+                    double* out_tree, int32_t* status, double* out_pset, cudaStream_t st, int totals_only,
+                    const gcdyn::FusedAllReduce& fc) {
     cudaLaunchConfig_t lc = pdl_config(dim3((unsigned)P), dim3(256), 0, st);
     CU_TRY(ctx, cudaLaunchKernelEx(&lc, finish_kernel<M>, f->v, pv, pk, tab, cfg.tab_stride, cfg.S_cap, cfg.grid_doubles, T, partial,
-                                   splits, tree_const, need_sweep, P, f->mom.D, const_cast<int*>(need_sweep) + P, f->h_feedback, totals_only, out_tree, status, out_pset));
+                                   splits, tree_const, need_sweep, P, f->mom.D, const_cast<int*>(need_sweep) + P, f->h_feedback, totals_only, out_tree, status, out_pset, fc));
     return GCDYN_OK;
 }
 
 int launch_finish(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const ParamsView& pv, const PsetPack& pk, const double* tab, const TrajCfg& cfg,
                   double T, const double* partial, int splits, const double* tree_const, const int* need_sweep, int P,
-                  double* out_tree, int32_t* status, double* out_pset, cudaStream_t st, int totals_only = 0) {
+                  double* out_tree, int32_t* status, double* out_pset, cudaStream_t st, int totals_only,
+                  const gcdyn::FusedAllReduce& fc) {
     switch (M) {
-        case 8: return launch_finish_m<8>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only);
-        case 12: return launch_finish_m<12>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only);
-        case 16: return launch_finish_m<16>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only);
-        case 20: return launch_finish_m<20>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only);
-        case 24: return launch_finish_m<24>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only);
+        case 8: return launch_finish_m<8>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc);
+        case 12: return launch_finish_m<12>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc);
+        case 16: return launch_finish_m<16>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc);
+        case 20: return launch_finish_m<20>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc);
+        case 24: return launch_finish_m<24>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc);
     }
     return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
 }
 
+int comm_enqueue(gcdyn_comm* c, const double* d_in, double* out, int n_psets, cudaStream_t st);   // peer all-reduce (below)
+int comm_fused_view(gcdyn_comm* c, int n_psets, gcdyn::FusedAllReduce* out);                      // its form fused into finish_kernel
+void comm_poison(gcdyn_comm* c, int n_psets, cudaStream_t st);                                     // NaN contribution of a rank that failed
+
 // Enqueue one evaluation on `st`.  All pointers are device pointers; d_out_tree/d_status may be null.
+// `comm`: the forest is this rank's shard — d_out_pset receives the sums over all ranks (fused into finish_kernel on the
+// contraction / totals paths, a separate one-CTA kernel behind the other paths).
 // S_fixed > 0 pins the number of Taylor cells; otherwise every pset adapts it inside traj_kernel.
 int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, double rate_max, double T, int method,
                  int M, int S_fixed, double tol, int flags, const double* host_gamma_shared, double* d_out_pset,
-                 double* d_out_tree, int32_t* d_status, cudaStream_t st, PsetPack* pk_out, double rate_typical = 0.0) {
+                 double* d_out_tree, int32_t* d_status, cudaStream_t st, PsetPack* pk_out, double rate_typical = 0.0,
+                 gcdyn_comm* comm = nullptr) {
     // rate_max bounds every pset's rates (table capacity); rate_typical (> 0: the sampler's current rates) only picks
     // the Chebyshev interpolation degree — a pset it is too small for is flagged and summed exactly
     const int P = pv.P, K = pv.K;
     if (P > 65535) return fail(ctx, GCDYN_EUNSUPPORTED, "more than 65535 parameter sets per call");
+    if (comm && comm->world <= 1) comm = nullptr;         // a world of one rank: nothing to combine
     PsetPack pk{};
     int rc = carve_pack(ctx, P, K, &pk);
     if (rc) return rc;
@@ -587,6 +597,8 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             cc.nflag = need_sweep + P;
         }
         const double* tree_const = nullptr;
+        gcdyn::FusedAllReduce fc{};
+        fc.pv.world = 1;
         // (the calibrating first call takes the full path once; its repetition on the adopted grid is the totals call)
         const bool totals = use_gemm && (flags & GCDYN_FLAG_TOTALS) && !calibrating;
         if (use_gemm) {
@@ -609,8 +621,16 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
                 }
                 tree_const = f->d_tree_const;
             }
+            if (comm) {                                    // fused all-reduce: this rank's sums never leave the kernel chain
+                rc = comm_fused_view(comm, P, &fc);
+                if (rc) return rc;
+                if (totals) {
+                    CU_TRY(ctx, ctx->out_pset.ensure((size_t)P * 8));
+                    fc.totals_in = ctx->out_pset.as<double>();
+                }
+            }
             if (totals) {
-                cc.totals = d_out_pset;
+                cc.totals = comm ? ctx->out_pset.as<double>() : d_out_pset;
                 cc.tc_total = tree_const ? tree_const + Tn : nullptr;
                 cc.any_self_loop = f->any_self_loop ? 1 : 0;
             }
@@ -623,7 +643,7 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             // the per-pset sums are already in d_out_pset; finish_kernel only redoes the psets the grid did not resolve
             if (prof) { cudaEventRecord(ctx->ev[3], st); cudaEventRecord(ctx->ev[4], st); cudaEventRecord(ctx->ev[5], st); }
             rc = launch_finish(ctx, M, f, pv, pk, ctx->table.as<double>(), cfg, T, nullptr, 0, nullptr, need_sweep, P,
-                               d_out_tree, d_status, d_out_pset, st, 1);
+                               d_out_tree, d_status, d_out_pset, st, 1, fc);
             if (rc) return rc;
             ++launches;
             if (prof) { cudaEventRecord(ctx->ev[6], st); ctx->ev_valid = true; }
@@ -654,7 +674,7 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             ++launches;
             if (prof) { cudaEventRecord(ctx->ev[4], st); cudaEventRecord(ctx->ev[5], st); }
             rc = launch_finish(ctx, M, f, pv, pk, ctx->table.as<double>(), cfg, T, ctx->partial.as<double>(), splits, tree_const,
-                               need_sweep, P, d_out_tree, d_status, d_out_pset, st);
+                               need_sweep, P, d_out_tree, d_status, d_out_pset, st, 0, fc);
             if (rc) return rc;
             ++launches;
             if (prof) { cudaEventRecord(ctx->ev[6], st); ctx->ev_valid = true; }
@@ -674,9 +694,10 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
                 }
                 f->D_cur = adopt;
                 f->D_T = T;
-                if (adopt != cc.D)
+                // (sharded: every rank repeats, whatever it adopted — the ranks must make the same number of collective calls)
+                if (adopt != cc.D || comm)
                     return enqueue_eval(ctx, f, pv, rate_max, T, method, M, S_fixed, tol, flags, host_gamma_shared, d_out_pset,
-                                        d_out_tree == ctx->out_tree.as<double>() ? nullptr : d_out_tree, d_status, st, pk_out, rate_typical);
+                                        d_out_tree == ctx->out_tree.as<double>() ? nullptr : d_out_tree, d_status, st, pk_out, rate_typical, comm);
             }
             ctx->last_cheb_D = cc.D;
             ctx->last_feedback = f->h_feedback;
@@ -717,8 +738,17 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         ctx->last_steps = 0;
     }
     if (prof) cudaEventRecord(ctx->ev[5], st);
-    reduce_kernel<<<P, 256, 0, st>>>(d_out_tree, Tn, d_out_pset);
-    CU_TRY(ctx, cudaGetLastError());
+    if (comm) {                                            // sweep / alternate paths: partial sums, then the one-CTA all-reduce
+        CU_TRY(ctx, ctx->out_pset.ensure((size_t)P * 8));
+        reduce_kernel<<<P, 256, 0, st>>>(d_out_tree, Tn, ctx->out_pset.as<double>());
+        CU_TRY(ctx, cudaGetLastError());
+        rc = comm_enqueue(comm, ctx->out_pset.as<double>(), d_out_pset, P, st);
+        if (rc) return rc;
+        ++launches;
+    } else {
+        reduce_kernel<<<P, 256, 0, st>>>(d_out_tree, Tn, d_out_pset);
+        CU_TRY(ctx, cudaGetLastError());
+    }
     ++launches;
     if (prof) { cudaEventRecord(ctx->ev[6], st); ctx->ev_valid = true; }
     ctx->last_order = method == GCDYN_METHOD_ODE ? M : 0;
@@ -875,7 +905,6 @@ int forest_create_impl(gcdyn_ctx* ctx, const gcdyn_forest_desc* d, gcdyn_forest*
     return GCDYN_OK;
 }
 
-int comm_enqueue(gcdyn_comm* c, const double* d_in, double* out, int n_psets, cudaStream_t st);   // peer all-reduce (below)
 
 int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, double T, int method,
                const gcdyn_opts* opts, double* out_pset, double* out_tree_pset, int32_t* status, gcdyn_comm* comm = nullptr) {
@@ -917,23 +946,18 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
     // one pass: every pset adapts its own step count inside traj_kernel (or uses opts->steps as given);
     // a pset that cannot be resolved within the table capacity comes back as a solver failure (-Inf)
     rc = enqueue_eval(ctx, f, pv, rate_max_of(pr), T, method, M, o.steps, tol, o.flags,
-                      pr->gamma_pset_stride == 0 ? pr->Gamma : nullptr, comm ? ctx->out_pset.as<double>() : h_out, nullptr,
-                      status ? ctx->status.as<int32_t>() : nullptr, st, nullptr);
+                      pr->gamma_pset_stride == 0 ? pr->Gamma : nullptr, h_out, nullptr,
+                      status ? ctx->status.as<int32_t>() : nullptr, st, nullptr, 0.0, comm);
     if (rc && comm) {
         // a rank-local failure must still release the peers: contribute NaN (every rank then sees NaN sums, and this rank
         // returns its error) instead of leaving them to wait for a flag that never comes
         const std::string why = ctx->err;
         cudaGetLastError();
-        if (ctx->out_pset.p && cudaMemsetAsync(ctx->out_pset.p, 0xFF, (size_t)P * 8, st) == cudaSuccess &&
-            comm_enqueue(comm, ctx->out_pset.as<double>(), h_out, P, st) == GCDYN_OK)
-            cudaStreamSynchronize(st);
+        comm_poison(comm, P, st);
+        cudaStreamSynchronize(st);
         return fail(ctx, rc, why);
     }
     if (rc) return rc;
-    if (comm) {                       // trees sharded over ranks: sum the partial [P] over the peers, result → pinned host
-        rc = comm_enqueue(comm, ctx->out_pset.as<double>(), h_out, P, st);
-        if (rc) return rc;
-    }
     if (want_rows) {
         if (out_tree_pset)
             CU_TRY(ctx, cudaMemcpyAsync(out_tree_pset, ctx->out_tree.p, (size_t)P * Tn * 8, cudaMemcpyDeviceToHost, st));
@@ -1118,6 +1142,31 @@ int gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcd
     return enqueue_eval(ctx, f, dp->v, dp->rate_max, present_time, method, M, o.steps, o.tol > 0.0 ? o.tol : 1e-11,
                         o.flags, dp->host_gamma.empty() ? nullptr : dp->host_gamma.data(), d_out_pset, d_out_tree_pset,
                         d_status, st, nullptr);
+    GUARD_END(ctx)
+}
+
+int gcdyn_loglik_batch_resident_sharded(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_dparams* dp, double present_time,
+                                        int method, const gcdyn_opts* opts, gcdyn_comm* comm, double* d_out_pset,
+                                        double* d_out_tree_pset, int32_t* d_status, void* stream) {
+    GUARD_BEGIN
+    if (!ctx || !f || !dp || !d_out_pset || !comm) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    if (comm->ctx != ctx) return fail(ctx, GCDYN_EINVAL, "comm belongs to another context");
+    if (method < 0 || method > 3) return fail(ctx, GCDYN_EINVAL, "unknown method");
+    if (dp->v.K != f->v.K) return fail(ctx, GCDYN_EINVAL, "params and forest disagree on n_types");
+    if (f->device != ctx->device || dp->device != ctx->device) return fail(ctx, GCDYN_EINVAL, "handles live on another device");
+    if (method != GCDYN_METHOD_NAIVE && !(present_time > 0.0)) return fail(ctx, GCDYN_EINVAL, "present_time must be positive");
+    gcdyn_opts o{};
+    if (opts) o = *opts;
+    const int M = normalise_order(o.order);
+    if (M < 0) return fail(ctx, GCDYN_EINVAL, "order must be 0, 8, 12, 16, 20 or 24");
+    if (o.steps < 0 || o.steps > S_CAP) return fail(ctx, GCDYN_EINVAL, "steps out of range");
+    if ((o.flags & GCDYN_FLAG_TOTALS) && (d_out_tree_pset || d_status))
+        return fail(ctx, GCDYN_EINVAL, "GCDYN_FLAG_TOTALS produces no per-tree values: d_out_tree_pset and d_status must be NULL");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
+    return enqueue_eval(ctx, f, dp->v, dp->rate_max, present_time, method, M, o.steps, o.tol > 0.0 ? o.tol : 1e-11,
+                        o.flags, dp->host_gamma.empty() ? nullptr : dp->host_gamma.data(), d_out_pset, d_out_tree_pset,
+                        d_status, st, nullptr, 0.0, comm);
     GUARD_END(ctx)
 }
 
@@ -1330,6 +1379,8 @@ int gcdyn_probe_fp64_peak(gcdyn_ctx* ctx, double* tflops) {
 // ---- peer all-reduce (multi-GPU) ---------------------------------------------------------------------------
 namespace {
 size_t comm_data_bytes(int world, int cap) { return (size_t)2 * world * cap * sizeof(double); }
+// byte offset of the 16-byte entries of the fused form: behind data | flags | call counter | CTA counter, 16-byte aligned
+size_t comm_ll_offset(int world, int cap) { return (comm_data_bytes(world, cap) + ((size_t)world + 2) * 8 + 15) & ~(size_t)15; }
 }
 
 extern "C" int gcdyn_comm_create(gcdyn_ctx* ctx, int32_t rank, int32_t world, int32_t max_psets, void* handle_out,
@@ -1348,7 +1399,8 @@ extern "C" int gcdyn_comm_create(gcdyn_ctx* ctx, int32_t rank, int32_t world, in
     }
     if (cudaHostAlloc(&c->h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); c->h_err = nullptr; }
     else *c->h_err = 0;
-    const size_t bytes = comm_data_bytes(world, c->cap) + ((size_t)world + 1) * sizeof(unsigned long long);   // data | flags | call counter
+    // data | flags | call counter | fused-kernel CTA counter | self-validating entries of the fused form (16 B each)
+    const size_t bytes = comm_ll_offset(world, c->cap) + comm_data_bytes(world, c->cap) * 2;
     cudaError_t e = cudaMalloc(&c->window, bytes);
     if (e == cudaSuccess) e = cudaMemset(c->window, 0, bytes);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -1398,6 +1450,34 @@ int comm_enqueue(gcdyn_comm* c, const double* d_in, double* out, int n_psets, cu
     cudaLaunchConfig_t lc = pdl_config(dim3(1), dim3(1024), 0, st);
     CU_TRY(ctx, cudaLaunchKernelEx(&lc, gcdyn::peer_allreduce_kernel, pv, d_in, out, n_psets, c->timeout_ns, c->h_err));
     return GCDYN_OK;
+}
+}  // namespace
+
+namespace {
+int comm_fused_view(gcdyn_comm* c, int n_psets, gcdyn::FusedAllReduce* out) {
+    gcdyn_ctx* ctx = c->ctx;
+    if (!c->connected && c->world > 1) return fail(ctx, GCDYN_EINVAL, "gcdyn_comm_connect has not been called");
+    if (n_psets < 1 || n_psets > c->cap) return fail(ctx, GCDYN_EINVAL, "n_psets exceeds the window capacity");
+    gcdyn::FusedAllReduce fc{};
+    fc.pv.rank = c->rank; fc.pv.world = c->world; fc.pv.cap = c->cap;
+    for (int r = 0; r < c->world; ++r) {
+        fc.pv.win[r].data = static_cast<double*>(c->peer[r]);
+        fc.pv.win[r].flag = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->peer[r]) + comm_data_bytes(c->world, c->cap));
+        fc.pv.win[r].ll = reinterpret_cast<uint4*>(static_cast<char*>(c->peer[r]) + comm_ll_offset(c->world, c->cap));
+    }
+    fc.pv.seq_dev = fc.pv.win[c->rank].flag + c->world;
+    fc.done = reinterpret_cast<int*>(fc.pv.win[c->rank].flag + c->world + 1);
+    fc.timeout_ns = c->timeout_ns;
+    fc.err = c->h_err;
+    fc.totals_in = nullptr;
+    *out = fc;
+    return GCDYN_OK;
+}
+void comm_poison(gcdyn_comm* c, int n_psets, cudaStream_t st) {
+    gcdyn::FusedAllReduce fc{};
+    if (c->world <= 1 || n_psets < 1 || n_psets > c->cap || comm_fused_view(c, n_psets, &fc) != GCDYN_OK) return;
+    gcdyn::peer_poison_kernel<<<1, 256, 0, st>>>(fc.pv, n_psets);
+    cudaGetLastError();
 }
 }  // namespace
 
@@ -1530,16 +1610,14 @@ namespace {
 int mh_loglik(gcdyn_mh* m, double* dst, cudaStream_t st) {
     gcdyn_ctx* ctx = m->ctx;
     int rc = enqueue_eval(ctx, m->forest, m->pv, m->rate_bound, m->T, GCDYN_METHOD_ODE, 16, 0, 1e-11, GCDYN_FLAG_TOTALS, m->host_gamma.data(),
-                          dst, nullptr, nullptr, st, nullptr, m->rate_typical);
+                          dst, nullptr, nullptr, st, nullptr, m->rate_typical, m->comm);
     if (rc && m->comm) {              // release the peers with NaN sums (see batch_impl), then report the local error
         const std::string why = ctx->err;
         cudaGetLastError();
-        if (cudaMemsetAsync(dst, 0xFF, (size_t)m->C * 8, st) == cudaSuccess) comm_enqueue(m->comm, dst, dst, m->C, st);
+        comm_poison(m->comm, m->C, st);
         return fail(ctx, rc, why);
     }
-    if (rc) return rc;
-    if (m->comm) return comm_enqueue(m->comm, dst, dst, m->C, st);
-    return GCDYN_OK;
+    return rc;
 }
 }  // namespace
 

@@ -22,6 +22,7 @@ namespace gcdyn {
 struct PeerWindow {
     double* data;                  // [2][world][cap]
     unsigned long long* flag;      // [world]
+    uint4* ll;                     // [2][world][cap] self-validating entries {lo32, seq, hi32, seq} of the fused form
 };
 
 constexpr int PEER_MAX_WORLD = 16;
@@ -32,6 +33,33 @@ struct PeerView {
     unsigned long long* seq_dev;       // this rank's call counter, in device memory: the kernel takes the next sequence
                                        // number from it, so a captured CUDA graph can replay the all-reduce unchanged
 };
+
+// The same all-reduce fused into the kernel that produces the sums (finish_kernel, cheb_gemm.cuh): world == 1 = off.
+// Its entries are SELF-VALIDATING (the low-latency protocol of collective libraries): a double travels as two aligned
+// 8-byte words {low half, seq} and {high half, seq}; an 8-byte store is single-copy atomic, so a reader that finds the
+// call's sequence number in both words has the value — no fence, no separate flag, no ordering between stores is needed,
+// and the cost of the collective is one NVLink store latency.  Parities alternate per call as above.
+struct FusedAllReduce {
+    PeerView pv;
+    unsigned long long timeout_ns;
+    int* err;                          // pinned host word raised on a timeout
+    int* done;                         // device counter of the CTAs that have stored their sum (reset by the last one)
+    const double* totals_in;           // GCDYN_FLAG_TOTALS: this rank's sums as traj_kernel wrote them
+};
+
+__device__ __forceinline__ void ll_store(uint4* slot, double v, unsigned seq) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const uint2 w0 = make_uint2((unsigned)bits, seq), w1 = make_uint2((unsigned)(bits >> 32), seq);
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot), "r"(w0.x), "r"(w0.y) : "memory");
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<char*>(slot) + 8), "r"(w1.x), "r"(w1.y) : "memory");
+}
+__device__ __forceinline__ bool ll_load(const uint4* slot, unsigned seq, double& v) {
+    uint4 w;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(slot) : "memory");
+    if (w.y != seq || w.w != seq) return false;
+    v = __longlong_as_double((long long)(((unsigned long long)w.z << 32) | (unsigned long long)w.x));
+    return true;
+}
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -86,6 +114,23 @@ __global__ void __launch_bounds__(1024) peer_allreduce_kernel(PeerView pv, const
         out[p] = s;
     }
     __syncthreads();                                        // everybody has read seq
+    if (threadIdx.x == 0) *pv.seq_dev = seq;
+}
+
+// A rank whose evaluation failed locally still owes its peers a contribution, or they would wait for the timeout: NaN
+// in both forms (slots + flag, self-validating entries) for the next sequence number, without waiting for anybody.
+__global__ void __launch_bounds__(256) peer_poison_kernel(PeerView pv, int P) {
+    const unsigned long long seq = *pv.seq_dev + 1;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const size_t base = ((size_t)(seq & 1ULL) * pv.world + pv.rank) * pv.cap;
+    for (int i = threadIdx.x; i < P * pv.world; i += blockDim.x) {
+        const int r = i / P, p = i - r * P;
+        pv.win[r].data[base + p] = nan;
+        ll_store(pv.win[r].ll + base + p, nan, (unsigned)seq);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < pv.world) st_release_sys(pv.win[threadIdx.x].flag + pv.rank, seq);
     if (threadIdx.x == 0) *pv.seq_dev = seq;
 }
 

@@ -115,6 +115,8 @@ def _lib():
         "gcdyn_dparams_destroy": (None, [vp]),
         "gcdyn_loglik_batch_resident": (C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.POINTER(Opts),
                                                   vp, vp, vp, vp]),
+        "gcdyn_loglik_batch_resident_sharded": (C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.POINTER(Opts), vp,
+                                                          vp, vp, vp, vp]),
         "gcdyn_last_diag": (C.c_int, [vp, _p_i32, _p_i32, _p_i32, _p_f64, C.c_int32]),
         "gcdyn_last_cells": (C.c_int, [vp, _p_i32, C.c_int32]),
         "gcdyn_probe_fp64_peak": (C.c_int, [vp, _p_f64]),
@@ -373,11 +375,17 @@ class DeviceParams:
 
 
 def evaluate_resident(forest, dparams, present_time, d_out_pset, d_out_tree_pset=0, d_status=0, stream=0,
-                      method="ode", steps=0, order=0, flags=0):
+                      method="ode", steps=0, order=0, flags=0, comm=None):
     """`gcdyn_loglik_batch_resident`: everything already in HBM; `d_*` are raw device addresses
     (e.g. `tensor.data_ptr()`), `stream` a raw cudaStream_t (e.g. `torch.cuda.current_stream().cuda_stream`).
     Enqueues and returns without synchronising."""
     op = Opts(steps=int(steps), order=int(order), tol=0.0, flags=int(flags), reserved=0)
+    if comm is not None:            # the forest is this rank's shard: d_out_pset receives the sums over all ranks
+        _check(_lib().gcdyn_loglik_batch_resident_sharded(
+            forest.ctx._h, forest._h, dparams._h, float(present_time if present_time is not None else 0.0),
+            METHOD_CODE[method], C.byref(op), comm._h, C.c_void_p(d_out_pset), C.c_void_p(d_out_tree_pset or None),
+            C.c_void_p(d_status or None), C.c_void_p(stream or None)), forest.ctx._h)
+        return
     _check(_lib().gcdyn_loglik_batch_resident(
         forest.ctx._h, forest._h, dparams._h, float(present_time if present_time is not None else 0.0),
         METHOD_CODE[method], C.byref(op), C.c_void_p(d_out_pset), C.c_void_p(d_out_tree_pset or None),

@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define GCDYN_B200_VERSION 110  /* major*100 + minor; 1.10 adds gcdyn_comm_*, gcdyn_loglik_batch_sharded, gcdyn_mh_* */
+#define GCDYN_B200_VERSION 120  /* major*100 + minor; 1.10 adds gcdyn_comm_*, gcdyn_loglik_batch_sharded, gcdyn_mh_*;
+                                   1.20 adds GCDYN_FLAG_TOTALS, gcdyn_last_cells, gcdyn_loglik_batch_resident_sharded */
 
 /* return codes */
 #define GCDYN_OK            0
@@ -232,6 +233,14 @@ int  gcdyn_comm_allreduce(gcdyn_comm* comm, double* d_inout, int32_t n_psets, vo
 int  gcdyn_loglik_batch_sharded(gcdyn_ctx* ctx, const gcdyn_forest* forest, const gcdyn_params* params,
                                 double present_time, int method, const gcdyn_opts* opts, gcdyn_comm* comm,
                                 double* out_pset, double* out_tree_pset, int32_t* status);
+/* The device-resident form: like gcdyn_loglik_batch_resident (device outputs, caller's stream, no synchronisation), with
+ * d_out_pset receiving the sums over all ranks' trees.  On the contraction / totals paths the all-reduce is FUSED into the
+ * kernel that produces the sums: every CTA stores its parameter set's sum into every rank's window over NVLink, the last
+ * one publishes the flags, waits (bounded) for the peers and adds the ranks in order - no collective is launched.
+ * Collective: every rank must make the same sequence of sharded calls. */
+int  gcdyn_loglik_batch_resident_sharded(gcdyn_ctx* ctx, const gcdyn_forest* forest, const gcdyn_dparams* dparams,
+                                         double present_time, int method, const gcdyn_opts* opts, gcdyn_comm* comm,
+                                         double* d_out_pset, double* d_out_tree_pset, int32_t* d_status, void* stream);
 void gcdyn_comm_destroy(gcdyn_comm* comm);
 
 /* ---- device-resident random-walk Metropolis (BASELINE config 4) --------------------------

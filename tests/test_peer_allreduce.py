@@ -51,16 +51,62 @@ for _ in range(3):
     gathered = [None] * world
     dist.all_gather_object(gathered, got.tobytes())
     assert all(g == gathered[0] for g in gathered)
+# sharded device-resident Metropolis (proposal, likelihood, peer all-reduce, accept/reject inside one captured CUDA graph per
+# iteration): every rank walks the chain of the unsharded sampler
+from gcdyn.mcmc import device_metropolis, theta_of
+tpl = models[0]
+th = theta_of(tpl)
+th0 = th + 0.03 * np.random.default_rng(7).standard_normal((6, 6))
+kw = dict(step=0.04, seed=11, lower=th - 0.6, upper=th + 0.6)
+ref = device_metropolis(whole, tpl, 2.5, th0, 15, **kw)
+sh = device_metropolis(shard, tpl, 2.5, th0, 15, comm=peer, **kw)
+assert np.array_equal(sh.accepted, ref.accepted), (rank, sh.accepted, ref.accepted)
+assert np.max(np.abs(sh.chain - ref.chain)) <= 1e-12 and np.max(np.abs(sh.loglik - ref.loglik) / np.abs(ref.loglik)) <= 1e-12
+gathered = [None] * world
+dist.all_gather_object(gathered, sh.chain.tobytes() + sh.loglik.tobytes())
+assert all(g == gathered[0] for g in gathered)       # bit-identical chains on every rank
 peer.close()
 dist.barrier()
 sys.stdout.write("rank%d-ok\n" % rank)
 """
 
+# A peer that never arrives: the waiting rank's kernel gives up after GCDYN_PEER_TIMEOUT_MS, the call returns an error
+# and NaN sums instead of hanging inside cudaStreamSynchronize (ADVICE round 1).
+TIMEOUT_WORKER = r"""
+import os, sys, time
+os.environ["GCDYN_PEER_TIMEOUT_MS"] = "400"
+sys.path[:0] = [os.path.join("@ROOT@", "gcdyn.jl_b200")]
+import numpy as np, torch, torch.distributed as dist
+import gcdyn
+from gcdyn.sharding import PeerAllReduce
+from gcdyn.likelihood import evaluate, pack_params, GcdynError
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("gloo")
+ctx = gcdyn.Context(local)
+peer = PeerAllReduce(ctx, 16)
+ts = np.linspace(-1.0, 1.0, 5)
+models = [gcdyn.SigmoidalBranchingProcess(1.2, 0.0, 2.0 + 0.1 * i, 0.5, 1.0, 1.0, 0.6, 0.2, ts) for i in range(9)]
+trees = gcdyn.rand_tree(models[0], 2.5, ts[2], 8, rng=np.random.default_rng(3))
+shard = gcdyn.Forest(trees[rank::world], ts, 2.5, ctx=ctx)
+if rank == 0:
+    t0 = time.time()
+    try:
+        evaluate(shard, pack_params(models), 2.5, comm=peer)
+        raise SystemExit("the call returned although rank 1 never arrived")
+    except GcdynError as e:
+        assert "timed out" in str(e), str(e)
+    assert time.time() - t0 < 30.0
+dist.barrier()
+sys.stdout.write("rank%d-ok\n" % rank)
+os._exit(0)                                          # the windows are out of step now: skip the orderly teardown
+"""
 
-def _run(world):
+
+def _run(world, worker=None):
     import tempfile
     with tempfile.NamedTemporaryFile("w", suffix=".py", delete=False) as f:
-        f.write(WORKER.replace("@ROOT@", ROOT))
+        f.write((worker or WORKER).replace("@ROOT@", ROOT))
         path = f.name
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + world), path]
@@ -84,3 +130,11 @@ def test_peer_allreduce_two_ranks_bit_identical():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     _run(2)
+
+
+@pytest.mark.gpu
+def test_peer_allreduce_wait_is_bounded():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run(2, TIMEOUT_WORKER)
