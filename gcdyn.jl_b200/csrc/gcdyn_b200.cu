@@ -7,6 +7,7 @@
 #include "simulator.h"
 #include "peer_allreduce.cuh"
 #include "metropolis.cuh"
+#include "grad.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -63,7 +64,7 @@ struct gcdyn_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     // workspace (grow-only)
-    DevBuf params_blob, pack, table, out_tree, out_pset, status, probe, gemm_a, flags, partial;
+    DevBuf params_blob, pack, table, out_tree, out_pset, status, probe, gemm_a, flags, partial, grad_out;
     PinBuf pin_in, pin_out;
     // diagnostics of the last evaluation
     int last_steps = 0, last_order = 0, last_launches = 0, last_P = 0;
@@ -243,6 +244,7 @@ double rate_max_of(const gcdyn_params* pr) {
 // step-count rule: h·rate_max ≤ target(M), from the numerical study in tests/algo_model.py
 // ---------------------------------------------------------------------------------------------
 constexpr int S_CAP = 8192;
+constexpr int FLAG_FORCE_MOMENTS = 0x100;   // internal: take the moment path whatever the batch size (gradients need it)
 
 int normalise_order(int order) {
     if (order == 0) return 16;
@@ -564,7 +566,7 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         // ---- per-tree sums: Chebyshev-moment GEMM (DMMA), with the item sweep as exact fallback.  The Chebyshev
         //      stage (node values = coefficient row, resolution check, fallback flag) runs inside traj_kernel.
         bool use_gemm = !(flags & GCDYN_FLAG_SWEEP_ONLY) && Tn > 0 && !f->mom_refused &&
-                        (P >= 8 || (f->mom.Mt && f->mom_T == T));
+                        (P >= 8 || (f->mom.Mt && f->mom_T == T) || (flags & FLAG_FORCE_MOMENTS));
         const int* only_flagged = nullptr;
         ChebCfg cc{};
         int* need_sweep = nullptr;
@@ -984,6 +986,32 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
     catch (const std::exception& e) { return fail(ctx, GCDYN_EINVAL, e.what()); }             \
     catch (...) { return fail(ctx, GCDYN_EINVAL, "unknown C++ exception"); }
 
+namespace {
+template <int M, int KP>
+int launch_grad_inst(gcdyn_ctx* ctx, const ParamsView& pv, const gcdyn::GradCfg& gc, cudaStream_t st) {
+    constexpr int NV = 1 + gcdyn::GRAD_MAX_DIRS;
+    const size_t doubles = (size_t)2 * NV * KP + (size_t)NV * (M + 1) * KP + (((size_t)gc.D + 3) & ~(size_t)1) + (size_t)NV * KP;
+    const size_t smem = doubles * 8;
+    if (smem > 48 * 1024)
+        CU_TRY(ctx, cudaFuncSetAttribute(gcdyn::traj_grad_kernel<M, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gcdyn::traj_grad_kernel<M, KP><<<pv.P, gcdyn::GRAD_THREADS, smem, st>>>(pv, gc);
+    CU_TRY(ctx, cudaGetLastError());
+    return GCDYN_OK;
+}
+template <int M>
+int launch_grad_m(gcdyn_ctx* ctx, const ParamsView& pv, const gcdyn::GradCfg& gc, cudaStream_t st) {
+    const int K = pv.K;
+    if (K <= 4) return launch_grad_inst<M, 4>(ctx, pv, gc, st);
+    if (K <= 8) return launch_grad_inst<M, 8>(ctx, pv, gc, st);
+    if (K <= 12) return launch_grad_inst<M, 12>(ctx, pv, gc, st);
+    if (K <= 16) return launch_grad_inst<M, 16>(ctx, pv, gc, st);
+    if (K <= 20) return launch_grad_inst<M, 20>(ctx, pv, gc, st);
+    if (K <= 24) return launch_grad_inst<M, 24>(ctx, pv, gc, st);
+    if (K <= 28) return launch_grad_inst<M, 28>(ctx, pv, gc, st);
+    return launch_grad_inst<M, 32>(ctx, pv, gc, st);
+}
+}  // namespace
+
 extern "C" {
 
 int gcdyn_version(void) { return GCDYN_B200_VERSION; }
@@ -1035,7 +1063,7 @@ void gcdyn_ctx_destroy(gcdyn_ctx* ctx) {
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     ctx->params_blob.release(); ctx->pack.release(); ctx->table.release(); ctx->out_tree.release();
-    ctx->out_pset.release(); ctx->status.release(); ctx->probe.release(); ctx->gemm_a.release(); ctx->flags.release(); ctx->partial.release();
+    ctx->out_pset.release(); ctx->status.release(); ctx->probe.release(); ctx->gemm_a.release(); ctx->flags.release(); ctx->partial.release(); ctx->grad_out.release();
     ctx->pin_in.release(); ctx->pin_out.release();
     cudaSetDevice(prev);
     delete ctx;
@@ -1191,6 +1219,79 @@ int gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_l
         CU_TRY(ctx, cudaSetDevice(ctx->device));
         CU_TRY(ctx, cudaDeviceSynchronize());
         CU_TRY(ctx, cudaMemcpy(err_indicator, ctx->last_pack.perr, (size_t)n_psets * 8, cudaMemcpyDeviceToHost));
+    }
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+int gcdyn_loglik_grad_batch(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, double T, const gcdyn_opts* opts,
+                            double* out_pset, double* out_grad, int32_t* n_dirs) {
+    GUARD_BEGIN
+    if (!ctx || !f || !out_pset || !out_grad) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    int rc = check_params(ctx, pr);
+    if (rc) return rc;
+    if (pr->n_types != f->v.K) return fail(ctx, GCDYN_EINVAL, "params and forest disagree on n_types");
+    if (f->device != ctx->device) return fail(ctx, GCDYN_EINVAL, "forest lives on another device");
+    if (!(T > 0.0)) return fail(ctx, GCDYN_EINVAL, "present_time must be positive");
+    if (pr->response == GCDYN_LAMBDA_TABLE)
+        return fail(ctx, GCDYN_EUNSUPPORTED, "gradients need a parametric birth response (sigmoid or constant): a table has K + 2 directions");
+    if (pr->n_types > 32) return fail(ctx, GCDYN_EUNSUPPORTED, "gradients are built for n_types <= 32");
+    gcdyn_opts o{};
+    if (opts) o = *opts;
+    const int M = normalise_order(o.order);
+    if (M < 0 || M > 16) return fail(ctx, GCDYN_EINVAL, "gradient order must be 0, 8, 12 or 16");
+    const double tol = o.tol > 0.0 ? o.tol : 1e-11;
+    const int NS = pr->response == GCDYN_LAMBDA_SIGMOID ? 6 : 3;
+    if (n_dirs) *n_dirs = NS;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int P = pr->n_psets;
+    // parameters → device; a plain totals evaluation first: it builds and calibrates the forest's nodal moments, gives the
+    // exact value of parameter sets the grid does not resolve, and tells us which those are
+    const ParamLayout L = layout_of(pr);
+    CU_TRY(ctx, ctx->pin_in.ensure(L.n_doubles * 8));
+    pack_host(pr, L, reinterpret_cast<double*>(ctx->pin_in.p));
+    CU_TRY(ctx, ctx->params_blob.ensure(L.n_doubles * 8));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->params_blob.p, ctx->pin_in.p, L.n_doubles * 8, cudaMemcpyHostToDevice, st));
+    const ParamsView pv = view_of(pr, L, ctx->params_blob.as<double>());
+    CU_TRY(ctx, ctx->grad_out.ensure(((size_t)P * (NS + 2)) * 8 + (size_t)P * 4));
+    double* d_tot = ctx->grad_out.as<double>();
+    double* d_ll = d_tot + P;
+    double* d_grad = d_ll + P;
+    int* d_st = reinterpret_cast<int*>(d_grad + (size_t)P * NS);
+    rc = enqueue_eval(ctx, f, pv, rate_max_of(pr), T, GCDYN_METHOD_ODE, M, 0, tol, GCDYN_FLAG_TOTALS | FLAG_FORCE_MOMENTS,
+                      pr->gamma_pset_stride == 0 ? pr->Gamma : nullptr, d_tot, nullptr, nullptr, st, nullptr);
+    if (rc) return rc;
+    if (!f->mom.Mt || f->mom_T != T)
+        return fail(ctx, GCDYN_EUNSUPPORTED, "gradients need the forest's moment matrix (refused for this forest: too large or too few items per tree)");
+    gcdyn::GradCfg gc{};
+    gc.T = T; gc.tol = tol; gc.D = f->mom.D; gc.NS = NS; gc.compact_tc = pr->gamma_pset_stride == 0 ? 1 : 0;
+    gc.any_self_loop = f->any_self_loop ? 1 : 0;
+    gc.mv = f->mom;
+    gc.tc_total = gc.compact_tc && f->d_tree_const ? f->d_tree_const + f->v.n_trees : nullptr;
+    gc.out_ll = d_ll; gc.out_grad = d_grad; gc.out_status = d_st;
+    switch (M) {
+        case 8: rc = launch_grad_m<8>(ctx, pv, gc, st); break;
+        case 12: rc = launch_grad_m<12>(ctx, pv, gc, st); break;
+        default: rc = launch_grad_m<16>(ctx, pv, gc, st); break;
+    }
+    if (rc) return rc;
+    std::vector<double> h_tot(P), h_ll(P);
+    std::vector<int> h_flag(P);
+    CU_TRY(ctx, cudaMemcpyAsync(h_tot.data(), d_tot, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(h_ll.data(), d_ll, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(out_grad, d_grad, (size_t)P * NS * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaMemcpyAsync(h_flag.data(), ctx->flags.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    const double nan = std::nan("");
+    for (int p = 0; p < P; ++p) {
+        if (h_flag[p]) {                                   // summed exactly by the plain path; no gradient on this grid
+            out_pset[p] = h_tot[p];
+            for (int j = 0; j < NS; ++j) out_grad[(size_t)p * NS + j] = nan;
+        } else {
+            out_pset[p] = h_ll[p];
+            if (!std::isfinite(h_ll[p])) for (int j = 0; j < NS; ++j) out_grad[(size_t)p * NS + j] = nan;
+        }
     }
     return GCDYN_OK;
     GUARD_END(ctx)

@@ -14,8 +14,9 @@ from .flatten import FlatForest, flatten, map_types_flat
 from .likelihood import (loglikelihood, naive_loglikelihood, stadler_appx_loglikelihood,
                          stadler_appx_unconditioned_loglikelihood, Forest, Context,
                          pack_params, DeviceParams, evaluate, evaluate_resident,
-                         GcdynError, library_path)
-from .mcmc import random_walk_metropolis, device_metropolis, loglikelihood_gradient, MetropolisResult
+                         GcdynError, library_path, loglikelihood_and_gradient)
+from .mcmc import (random_walk_metropolis, device_metropolis, loglikelihood_gradient, loglikelihood_gradient_exact,
+                   MetropolisResult)
 from .native_sim import simulate_flat
 
 __all__ = [

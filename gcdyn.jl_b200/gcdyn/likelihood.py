@@ -19,7 +19,7 @@ from .types import (AbstractBranchingProcess, ArgumentError, ConstantBranchingPr
                     DiscreteBranchingProcess, DomainError, SigmoidalBranchingProcess, TreeNode)
 from .flatten import FlatForest, flatten
 
-__all__ = ["loglikelihood", "naive_loglikelihood", "stadler_appx_loglikelihood",
+__all__ = ["loglikelihood_and_gradient", "loglikelihood", "naive_loglikelihood", "stadler_appx_loglikelihood",
            "stadler_appx_unconditioned_loglikelihood", "Forest", "Context", "pack_params",
            "DeviceParams", "evaluate", "evaluate_resident", "GcdynError", "library_path"]
 
@@ -117,6 +117,7 @@ def _lib():
                                                   vp, vp, vp, vp]),
         "gcdyn_loglik_batch_resident_sharded": (C.c_int, [vp, vp, vp, C.c_double, C.c_int, C.POINTER(Opts), vp,
                                                           vp, vp, vp, vp]),
+        "gcdyn_loglik_grad_batch": (C.c_int, [vp, vp, C.POINTER(Params), C.c_double, C.POINTER(Opts), _p_f64, _p_f64, _p_i32]),
         "gcdyn_last_diag": (C.c_int, [vp, _p_i32, _p_i32, _p_i32, _p_f64, C.c_int32]),
         "gcdyn_last_cells": (C.c_int, [vp, _p_i32, C.c_int32]),
         "gcdyn_probe_fp64_peak": (C.c_int, [vp, _p_f64]),
@@ -424,6 +425,25 @@ def evaluate(forest: Forest, params: PackedParams, present_time, method="ode", *
         _check(lib.gcdyn_loglik_batch(forest.ctx._h, forest._h, C.byref(ps), T, METHOD_CODE[method], C.byref(op),
                                       _ptr(out, _p_f64), _ptr(tp, _p_f64), _ptr(st, _p_i32)), forest.ctx._h)
     return out, tp, st
+
+
+def loglikelihood_and_gradient(forest: Forest, params: PackedParams, present_time, *, order=0):
+    """`gcdyn_loglik_grad_batch`: per-parameter-set log-likelihood [P] and its exact gradient [P, n_dirs] by forward
+    sensitivities of the trajectory — the derivatives the reference gets from ForwardDiff through its `T<:Real` structs
+    (types.jl:92, mbp.jl:118-122).  Directions: (xscale, xshift, yscale, yshift, μ, δ) for `pack_params(..., "sigmoid")`,
+    (λ, μ, δ) for constant-rate models."""
+    lib = _lib()
+    P = params.n_psets
+    if params.n_types != forest.flat.n_types:
+        raise ArgumentError("model type_space and forest disagree on the number of types")
+    out = np.empty(P, dtype=np.float64)
+    grad = np.empty(P * 6, dtype=np.float64)
+    nd = C.c_int32()
+    ps = params.struct()
+    op = _opts(None, None, 0, order, 0)
+    _check(lib.gcdyn_loglik_grad_batch(forest.ctx._h, forest._h, C.byref(ps), float(present_time), C.byref(op),
+                                       _ptr(out, _p_f64), _ptr(grad, _p_f64), C.byref(nd)), forest.ctx._h)
+    return out, grad[:P * nd.value].reshape(P, nd.value).copy()
 
 
 def _report(status, method):

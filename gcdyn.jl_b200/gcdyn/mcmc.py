@@ -18,7 +18,7 @@ import numpy as np
 from .types import SigmoidalBranchingProcess
 from .likelihood import DeviceParams, Forest, evaluate, pack_params
 
-__all__ = ["MetropolisResult", "random_walk_metropolis", "device_metropolis", "CounterRNG", "loglikelihood_gradient", "theta_of", "model_of"]
+__all__ = ["MetropolisResult", "random_walk_metropolis", "device_metropolis", "CounterRNG", "loglikelihood_gradient", "loglikelihood_gradient_exact", "theta_of", "model_of"]
 
 NAMES = ("log_xscale", "xshift", "log_yscale", "log_yshift", "log_mu", "log_delta")
 
@@ -186,6 +186,28 @@ def random_walk_metropolis(forest: Forest, template: SigmoidalBranchingProcess, 
         accepted += accept
         chain[it], lls[it] = theta, ll
     return MetropolisResult(chain=chain, loglik=lls, accepted=accepted)
+
+
+def loglikelihood_gradient_exact(forest: Forest, template: SigmoidalBranchingProcess, present_time, thetas):
+    """Log-likelihoods [C] and EXACT gradients [C, 6] w.r.t. θ = (log xscale, xshift, log yscale, log yshift, log μ, log δ)
+    for a batch of C points: `gcdyn_loglik_grad_batch` integrates the forward sensitivities of the trajectory for the raw
+    parameters (xscale, xshift, yscale, yshift, μ, δ) — what ForwardDiff does for the reference through its `T<:Real`
+    structs (types.jl:92, mbp.jl:118-122) — and the chain rule through exp() maps them to θ."""
+    from .likelihood import PackedParams, loglikelihood_and_gradient
+    th = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+    n = len(th)
+    ts = np.ascontiguousarray(template.type_space)
+    raw = np.stack([np.exp(th[:, 0]), th[:, 1], np.exp(th[:, 2]), np.exp(th[:, 3]), np.exp(th[:, 4]), np.exp(th[:, 5])], axis=1)
+    c = lambda k: np.ascontiguousarray(raw[:, k])
+    params = PackedParams(n_psets=n, n_types=len(ts), response=2, gamma_pset_stride=0, lam=None, xscale=c(0), xshift=c(1),
+                          yscale=c(2), yshift=c(3), type_space=ts, mu=c(4), delta=c(5), rho=np.full(n, float(template.ρ)),
+                          sigma=np.full(n, float(template.σ)),
+                          Gamma=np.ascontiguousarray(np.asarray(template.Γ, dtype=np.float64).ravel(order="F")))
+    ll, g = loglikelihood_and_gradient(forest, params, present_time)
+    scale = np.ones_like(raw)
+    for k in (0, 2, 3, 4, 5):
+        scale[:, k] = raw[:, k]                  # d/d log x = x d/dx
+    return ll, g * scale
 
 
 def loglikelihood_gradient(forest: Forest, template: SigmoidalBranchingProcess, present_time, theta, *, rel_step=1e-4,

@@ -169,6 +169,20 @@ int  gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* forest, con
                                  double present_time, int method, const gcdyn_opts* opts,
                                  double* d_out_pset, double* d_out_tree_pset, int32_t* d_status,
                                  void* stream);
+/* Exact gradient of the per-parameter-set log-likelihood (ODE method) by forward sensitivities of the trajectory: what
+ * the reference obtains by pushing ForwardDiff dual numbers through loglikelihood - its model structs are parametric in
+ * T<:Real for exactly that (src/types.jl:92, src/multitype_branching_process.jl:118-122).  Directions = the autodiff-able
+ * fields of the model:
+ *     GCDYN_LAMBDA_SIGMOID   (xscale, xshift, yscale, yshift, mu, delta)    n_dirs = 6
+ *     GCDYN_LAMBDA_CONSTANT  (lambda, mu, delta)                            n_dirs = 3
+ * (GCDYN_LAMBDA_TABLE has K + 2 directions and n_types > 32 two integrating warps per vector: GCDYN_EUNSUPPORTED.)
+ *   out_pset [P]          sum over trees of the log-likelihood (same value as gcdyn_loglik_batch with GCDYN_FLAG_TOTALS)
+ *   out_grad [P*n_dirs]   d out_pset[p] / d direction j at out_grad[p*n_dirs + j]; NaN for a parameter set whose value is
+ *                         -Inf or that the forest's Chebyshev grid does not resolve (its out_pset is still exact)
+ * Cost: about one plain evaluation plus one sensitivity integration (all directions advance in lockstep with p). */
+int  gcdyn_loglik_grad_batch(gcdyn_ctx* ctx, const gcdyn_forest* forest, const gcdyn_params* params, double present_time,
+                             const gcdyn_opts* opts, double* out_pset, double* out_grad, int32_t* n_dirs);
+
 /* Diagnostics of the last ODE evaluation on this ctx (host copies; synchronises the stream):
  * steps and order used, number of kernels launched, and per-pset error indicators [P] (may be NULL). */
 int  gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_launches,

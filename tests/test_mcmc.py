@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import gcdyn
+from gcdyn.likelihood import pack_params
 from gcdyn.mcmc import model_of, random_walk_metropolis, theta_of
 
 
@@ -146,3 +147,50 @@ def test_counter_rng_mirror_is_bit_identical_to_the_library():
             want = lib.gcdyn_mh_uniform(int(seed) & (2**64 - 1), int(it), int(c), int(s))
             got = float(r.uniform(int(it), np.array([c]), np.array([s]))[0])
             assert got == want and 0.0 < got < 1.0
+
+
+@pytest.mark.gpu
+def test_exact_gradient_by_forward_sensitivities(ctx):
+    """`gcdyn_loglik_grad_batch`: log-likelihood and its gradient with respect to the autodiff-able fields
+    of the model, from the sensitivity trajectories.  Checked against Richardson-extrapolated central differences of the
+    ORACLE (O(h⁴) truncation; its own DOP853 noise at 1e-13 of |LL| limits the reference to ≈1e-8 relative), against the
+    finite differences of the GPU path, and the value against the plain evaluation."""
+    import oracle
+    from gcdyn.mcmc import loglikelihood_gradient, loglikelihood_gradient_exact
+    from gcdyn.likelihood import FLAG_TOTALS
+    rng = np.random.default_rng(41)
+    tpl = _template()
+    T = 3.0
+    trees = gcdyn.rand_tree(tpl, T, tpl.type_space[2], 10, rng=rng)
+    forest = gcdyn.Forest(trees, tpl.type_space, T, ctx=ctx)
+    th = theta_of(tpl)
+    pts = np.stack([th, th + 0.1 * rng.standard_normal(6), th - 0.1 * rng.standard_normal(6)])
+    ll, grad = loglikelihood_gradient_exact(forest, tpl, T, pts)
+    assert ll.shape == (3,) and grad.shape == (3, 6) and np.all(np.isfinite(grad))
+    f = lambda t: oracle.loglikelihood_shared(model_of(t, tpl), trees, T)
+    for i, t0 in enumerate(pts):
+        assert abs(ll[i] - f(t0)) <= 1e-10 * abs(ll[i])
+        for k in range(6):
+            e = np.zeros(6); e[k] = 1.0
+            d = lambda h: (f(t0 + h * e) - f(t0 - h * e)) / (2 * h)
+            want = (4.0 * d(1e-3) - d(2e-3)) / 3.0                    # O(h^4)
+            assert abs(grad[i, k] - want) <= 2e-7 * max(1.0, abs(want)), (i, k, grad[i, k], want)
+    # consistency with the batched central differences of the GPU path (≈1e-7) and with the constant-rate directions
+    _, fd = loglikelihood_gradient(forest, tpl, T, th)
+    assert np.max(np.abs(fd - grad[0]) / np.maximum(1.0, np.abs(grad[0]))) <= 2e-6
+    cm = gcdyn.ConstantBranchingProcess(1.7, 0.9, 1.1, 0.6, 0.3, tpl.type_space)
+    ctrees = gcdyn.rand_tree(cm, T, tpl.type_space[1], 8, rng=rng)
+    cf = gcdyn.Forest(ctrees, tpl.type_space, T, ctx=ctx)
+    from gcdyn.likelihood import loglikelihood_and_gradient
+    llc, gc = loglikelihood_and_gradient(cf, pack_params([cm] * 2), T)
+    assert gc.shape == (2, 3)
+    fc = lambda lam, mu, de: oracle.loglikelihood_shared(
+        gcdyn.ConstantBranchingProcess(lam, mu, de, cm.Γ, cm.ρ, cm.σ, cm.type_space), ctrees, T)
+    base = (1.7, 0.9, 1.0)
+    assert abs(llc[0] - fc(*base)) <= 1e-10 * abs(llc[0])
+    for k in range(3):
+        def d(h):
+            a = list(base); b = list(base); a[k] += h; b[k] -= h
+            return (fc(*a) - fc(*b)) / (2 * h)
+        want = (4.0 * d(1e-3) - d(2e-3)) / 3.0
+        assert abs(gc[0, k] - want) <= 2e-7 * max(1.0, abs(want)), (k, gc[0, k], want)
