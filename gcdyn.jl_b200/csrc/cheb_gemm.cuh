@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(128) counts_kernel(ForestView fv, int Dcap, lo
     const int64_t t = blockIdx.x;
     for (int i = threadIdx.x; i < NC; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
-    for (int64_t i = fv.tree_off[t] + threadIdx.x; i < fv.tree_off[t + 1]; i += blockDim.x) {
+    // (a tree with a self-loop is -Inf through its status; its records may hold placeholder indices: leave its row zero)
+    const int64_t i_end = fv.self_loop[t] ? fv.tree_off[t] : fv.tree_off[t + 1];
+    for (int64_t i = fv.tree_off[t] + threadIdx.x; i < i_end; i += blockDim.x) {
         if (!fv.live[i]) continue;
         const int ev = fv.event[i], x = fv.btype_idx[i], y = fv.type_idx[i];
         if (ev == EV_BIRTH) atomicAdd(&cnt[x], 1);
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(128) counts_kernel(ForestView fv, int Dcap, lo
     }
     if (threadIdx.x == 0) {
         const int rt = fv.root_type[t];
-        if (rt >= 0) cnt[K + 2 + rt] = 1;
+        if (rt >= 0 && !fv.self_loop[t]) cnt[K + 2 + rt] = 1;
     }
     __syncthreads();
     double* row = Mt + (size_t)t * Jst;

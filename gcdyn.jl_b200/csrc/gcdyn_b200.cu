@@ -799,12 +799,19 @@ int forest_create_impl(gcdyn_ctx* ctx, const gcdyn_forest_desc* d, gcdyn_forest*
     if (d->tree_off[0] != 0 || d->tree_off[T] != N) return fail(ctx, GCDYN_EINVAL, "tree_off must start at 0 and end at n_nodes");
     for (int64_t t = 0; t < T; ++t)
         if (d->tree_off[t + 1] < d->tree_off[t]) return fail(ctx, GCDYN_EINVAL, "tree_off must be non-decreasing");
-    for (int64_t i = 0; i < N; ++i) {
-        if (d->event[i] > 6) return fail(ctx, GCDYN_EINVAL, "event code out of range");
-        if (d->btype_idx[i] < 0 || d->btype_idx[i] >= K) return fail(ctx, GCDYN_EINVAL, "btype_idx out of range");
-        if (d->type_idx[i] < -1 || d->type_idx[i] >= K) return fail(ctx, GCDYN_EINVAL, "type_idx out of range");
-        if (d->event[i] == EV_TC && d->type_idx[i] < 0) return fail(ctx, GCDYN_EINVAL, "type_change to a type outside the type space");
-        if (!(d->t_start[i] == d->t_start[i]) || !(d->t_end[i] == d->t_end[i])) return fail(ctx, GCDYN_EINVAL, "NaN node time");
+    // A tree the reference gives -Inf for (self-loop, mbp.jl:181-185) was not examined past the offending node by the
+    // flattener either: its remaining records may carry placeholder indices.  Such trees are never looked at by the
+    // kernels beyond their self_loop flag, so their records are exempt from the index checks (and yield no lookup items).
+    for (int64_t t = 0; t < T; ++t) {
+        const bool looped = d->self_loop && d->self_loop[t];
+        for (int64_t i = d->tree_off[t]; i < d->tree_off[t + 1]; ++i) {
+            if (d->event[i] > 6) return fail(ctx, GCDYN_EINVAL, "event code out of range");
+            if (!(d->t_start[i] == d->t_start[i]) || !(d->t_end[i] == d->t_end[i])) return fail(ctx, GCDYN_EINVAL, "NaN node time");
+            if (looped) continue;
+            if (d->btype_idx[i] < 0 || d->btype_idx[i] >= K) return fail(ctx, GCDYN_EINVAL, "btype_idx out of range");
+            if (d->type_idx[i] < -1 || d->type_idx[i] >= K) return fail(ctx, GCDYN_EINVAL, "type_idx out of range");
+            if (d->event[i] == EV_TC && d->type_idx[i] < 0) return fail(ctx, GCDYN_EINVAL, "type_change to a type outside the type space");
+        }
     }
     for (int64_t t = 0; t < T; ++t)
         if (d->root_type_idx[t] < -1 || d->root_type_idx[t] >= K) return fail(ctx, GCDYN_EINVAL, "root_type_idx out of range");
@@ -835,7 +842,8 @@ int forest_create_impl(gcdyn_ctx* ctx, const gcdyn_forest_desc* d, gcdyn_forest*
     };
     int64_t max_items = 0;
     for (int64_t t = 0; t < T; ++t) {
-        for (int64_t i = d->tree_off[t]; i < d->tree_off[t + 1]; ++i) {
+        const bool looped = d->self_loop && d->self_loop[t];
+        for (int64_t i = d->tree_off[t]; i < d->tree_off[t + 1] && !looped; ++i) {
             if (d->live && !d->live[i]) continue;
             const int ev = d->event[i], x = d->btype_idx[i], y = d->type_idx[i];
             const double te = d->t_end[i];

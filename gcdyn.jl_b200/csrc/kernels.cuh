@@ -1140,6 +1140,13 @@ __global__ void __launch_bounds__(256) alt_kernel(ForestView fv, ParamsView pv, 
     for (int64_t t = t_lo + warp; t < t_hi; t += nwarps) {
         const int64_t i0 = fv.tree_off[t], i1 = fv.tree_off[t + 1];
         double acc = 0.0;
+        if (fv.self_loop[t]) {                  // log γ(x→x) = log 0 (extra_likelihoods.jl:21-23 with mbp.jl:84-97): −Inf, and the
+            if (lane == 0) {                    // records behind the self-loop may hold placeholder indices
+                out_tree[(size_t)p * fv.n_trees + t] = -CUDART_INF;
+                if (status) status[(size_t)p * fv.n_trees + t] = 0;
+            }
+            continue;
+        }
         for (int64_t i = i0 + lane; i < i1; i += 32) {
             const int ev = fv.event[i];
             const int x = fv.btype_idx[i];

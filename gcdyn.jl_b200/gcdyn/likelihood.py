@@ -412,6 +412,7 @@ def evaluate(forest: Forest, params: PackedParams, present_time, method="ode", *
     P, T = params.n_psets, forest.flat.n_trees
     if params.n_types != forest.flat.n_types:
         raise ArgumentError("model type_space and forest disagree on the number of types")
+    _check_present_time(forest, present_time, method)
     out = np.empty(P, dtype=np.float64)
     tp = np.empty((P, T), dtype=np.float64) if per_tree else None
     st = np.zeros((P, T), dtype=np.int32) if (want_status or per_tree) else None
@@ -436,6 +437,7 @@ def loglikelihood_and_gradient(forest: Forest, params: PackedParams, present_tim
     P = params.n_psets
     if params.n_types != forest.flat.n_types:
         raise ArgumentError("model type_space and forest disagree on the number of types")
+    _check_present_time(forest, present_time, "ode")
     out = np.empty(P, dtype=np.float64)
     grad = np.empty(P * 6, dtype=np.float64)
     nd = C.c_int32()
@@ -444,6 +446,16 @@ def loglikelihood_and_gradient(forest: Forest, params: PackedParams, present_tim
     _check(lib.gcdyn_loglik_grad_batch(forest.ctx._h, forest._h, C.byref(ps), float(present_time), C.byref(op),
                                        _ptr(out, _p_f64), _ptr(grad, _p_f64), C.byref(nd)), forest.ctx._h)
     return out, grad[:P * nd.value].reshape(P, nd.value).copy()
+
+
+def _check_present_time(forest, present_time, method):
+    """The flattener validated leaf times against the forest's own present_time (survivors must sit exactly there,
+    mbp.jl:125-130); evaluating at another one would extrapolate silently where the reference raises."""
+    if method == "naive" or forest.present_time is None or present_time is None:
+        return
+    if float(present_time) != float(forest.present_time):
+        raise ArgumentError(f"present_time {present_time} differs from the {forest.present_time} this forest was flattened for: "
+                            "Sampled survival leaf must be at present time")
 
 
 def _report(status, method):

@@ -100,6 +100,7 @@ struct FlatForest
     root_type_idx::Vector{Int32}
     root_time::Vector{Float64}
     self_loop::Vector{UInt8}
+    present_time::Float64          # the present time the leaves were validated against (NaN: not an ODE/Stadler flattening)
 end
 
 const EVENT_CODE = Dict(e => UInt8(i - 1) for (i, e) in enumerate(EVENTS))     # types.jl:6, 0-based codes
@@ -109,7 +110,7 @@ index_of(type_space, t) = (i = findfirst(==(t), type_space); isnothing(i) ? Int3
 function flatten(trees::Vector{<:TreeNode}, model::AbstractBranchingProcess, present_time; method = :ode)
     ts = model.type_space
     f = FlatForest(length(ts), Int64[0], UInt8[], Int32[], Int32[], Float64[], Float64[], Int32[], Int64[0], Int32[],
-                   UInt8[], Int32[], Float64[], UInt8[])
+                   UInt8[], Int32[], Float64[], UInt8[], method == :naive ? NaN : Float64(present_time))
     for tree in trees
         if method == :ode                                   # pass A of the reference, mbp.jl:124-164
             for leaf in LeafTraversal(tree)
@@ -218,6 +219,10 @@ end
 
 function b200_evaluate(models::Vector{<:AbstractBranchingProcess}, forest::B200Forest, present_time, method::Cint;
                        per_tree = false, tol = 0.0)
+    # the leaves were validated against the forest's own present time (mbp.jl:125-134): another one would extrapolate silently
+    if method != GCDYN_METHOD_NAIVE && !isnan(forest.flat.present_time) && Float64(present_time) != forest.flat.present_time
+        throw(ArgumentError("Sampled survival events must all be at the present time."))
+    end
     pp = pack_params(models)
     T = length(forest.flat.tree_off) - 1
     out = Vector{Float64}(undef, pp.P)
@@ -256,6 +261,49 @@ StatsAPI.loglikelihood(models::Vector{<:AbstractBranchingProcess}, forest::B200F
     b200_evaluate(models, forest, present_time, GCDYN_METHOD_ODE)[1]
 StatsAPI.loglikelihood(models::Vector{<:AbstractBranchingProcess}, trees::Vector{<:TreeNode}, present_time) =
     StatsAPI.loglikelihood(models, B200Forest(flatten(trees, models[1], present_time)), present_time)
+
+"""
+    loglikelihood_and_gradient(models::Vector{<:SigmoidalBranchingProcess}, forest, present_time) -> (ll[P], grad[6, P])
+
+Exact derivatives of every model's log-likelihood with respect to its autodiff-able fields
+`(λ_xscale, λ_xshift, λ_yscale, λ_yshift, μ, δ)` — the quantities the reference lets ForwardDiff differentiate through its
+`T<:Real` structs (src/types.jl:92, src/multitype_branching_process.jl:118-122) — from `gcdyn_loglik_grad_batch`
+(forward sensitivities of the trajectory on the GPU).  An `rrule`/`frule` for `loglikelihood` is one line on top of this.
+`ConstantBranchingProcess` models give `(λ, μ, δ)` (3 rows).
+"""
+function loglikelihood_and_gradient(models::Vector{<:AbstractBranchingProcess}, forest::B200Forest, present_time)
+    m1 = models[1]
+    sigmoid_resp = m1 isa SigmoidalBranchingProcess
+    (sigmoid_resp || m1 isa ConstantBranchingProcess) || throw(ArgumentError("gradients need a parametric birth response"))
+    all(m -> typeof(m) == typeof(m1), models) || throw(ArgumentError("all models of a batch must be of one type"))
+    P, K = length(models), length(m1.type_space)
+    mu, delta = Float64[m.μ for m in models], Float64[m.δ for m in models]
+    rho, sigma = Float64[m.ρ for m in models], Float64[m.σ for m in models]
+    shared = all(m -> m.Γ == m1.Γ, models)
+    Gamma = shared ? vec(copy(m1.Γ)) : reduce(vcat, (vec(m.Γ) for m in models))
+    ts = Vector{Float64}(m1.type_space)
+    xs = sigmoid_resp ? Float64[m.λ_xscale for m in models] : Float64[]
+    xsh = sigmoid_resp ? Float64[m.λ_xshift for m in models] : Float64[]
+    ys = sigmoid_resp ? Float64[m.λ_yscale for m in models] : Float64[]
+    ysh = sigmoid_resp ? Float64[m.λ_yshift for m in models] : Float64[]
+    lam = sigmoid_resp ? Float64[] : Float64[m.λ for m in models]
+    out = Vector{Float64}(undef, P)
+    grad = Matrix{Float64}(undef, 6, P)
+    ndirs = Ref{Int32}(0)
+    GC.@preserve mu delta rho sigma Gamma ts xs xsh ys ysh lam out grad begin
+        par = sigmoid_resp ?
+            GcdynParams(P, K, 2, shared ? 0 : K * K, C_NULL, pointer(xs), pointer(xsh), pointer(ys), pointer(ysh), pointer(ts),
+                        pointer(mu), pointer(delta), pointer(rho), pointer(sigma), pointer(Gamma)) :
+            GcdynParams(P, K, 1, shared ? 0 : K * K, pointer(lam), C_NULL, C_NULL, C_NULL, C_NULL, pointer(ts),
+                        pointer(mu), pointer(delta), pointer(rho), pointer(sigma), pointer(Gamma))
+        opts = GcdynOpts(0, 0, 0.0, 0, 0)
+        b200_check(forest.ctx, ccall((:gcdyn_loglik_grad_batch, LIBGCDYN), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Ref{GcdynParams}, Cdouble, Ref{GcdynOpts}, Ptr{Float64}, Ptr{Float64}, Ref{Int32}),
+            forest.ctx.handle, forest.handle, par, Float64(present_time), opts, out, grad, ndirs))
+    end
+    n = Int(ndirs[])
+    return out, reshape(vec(grad)[1:n * P], n, P)
+end
 
 naive_loglikelihood(model::AbstractBranchingProcess, tree::TreeNode) =
     b200_evaluate([model], B200Forest(flatten([tree], model, 0.0; method = :naive)), 0.0, GCDYN_METHOD_NAIVE)[1][1]

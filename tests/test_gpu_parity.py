@@ -433,3 +433,32 @@ def test_totals_path_equals_the_sum_of_the_per_tree_path(ctx):
     fin = np.isfinite(full2)
     assert ctx.last_cheb()["n_fallback"] >= 1 and not fin[3] and np.isneginf(tot2[3])
     assert np.array_equal(fin, np.isfinite(tot2)) and rel(tot2[fin], full2[fin]) <= 1e-12
+
+
+def test_self_loop_followed_by_an_out_of_space_type_and_present_time_mismatch(ctx):
+    """The reference returns -Inf at the self-loop (mbp.jl:181-185) and never looks at the nodes that follow it in
+    post-order — which may carry a type outside the type space.  The forest must be accepted (that tree is -Inf, its
+    neighbours are untouched).  Evaluating a forest at another present_time than it was flattened for is the reference's
+    ArgumentError (mbp.jl:125-130), not a silent extrapolation."""
+    import oracle
+    T = 2.0
+    ts = np.array([1.0, 2.0])
+    model = gcdyn.ConstantBranchingProcess(1.5, 0.7, 0.9, 0.8, 0.4, ts)
+    N = gcdyn.TreeNode
+    r = N("root", 0, 1.0)
+    b = N("birth", 0.4, 1.0); gcdyn.attach(r, b)
+    tc1 = N("type_change", 0.8, 1.0); gcdyn.attach(b, tc1); gcdyn.attach(tc1, N("sampled_survival", T, 1.0))     # self-loop
+    tc2 = N("type_change", 0.9, 9.0); gcdyn.attach(b, tc2); gcdyn.attach(tc2, N("sampled_survival", T, 9.0))     # type ∉ type_space
+    good = gcdyn.rand_tree(model, T, 1.0, rng=np.random.default_rng(3))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert gcdyn.loglikelihood(model, r, T) == -math.inf
+        assert any("Self-loop" in str(x.message) for x in w)
+    forest = gcdyn.Forest([good, r, good], ts, T, ctx=ctx)
+    for reps in (1, 9):                                     # item sweep and contraction paths
+        out, tp, st = evaluate(forest, pack_params([model] * reps), T, per_tree=True)
+        want = oracle.loglikelihood_shared(model, good, T)
+        assert np.all(np.isneginf(tp[:, 1])) and np.all(st[:, 1] & 1) and np.all(np.isneginf(out))
+        assert rel(tp[:, 0], np.full(reps, want)) <= TREE_RTOL and np.array_equal(tp[:, 0], tp[:, 2])
+    with pytest.raises(gcdyn.ArgumentError):
+        evaluate(forest, pack_params(model), T + 0.5)
