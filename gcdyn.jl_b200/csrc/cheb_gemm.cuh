@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, ParamsView p
                                                      const double* __restrict__ tree_const,
                                                      const int* __restrict__ need_sweep, int P, int D, int* __restrict__ nflag, int* __restrict__ feedback, int totals_only,
                                                      double* __restrict__ out_tree, int32_t* __restrict__ status,
-                                                     double* __restrict__ out_pset, FusedAllReduce fc) {
+                                                     double* __restrict__ out_pset, FusedAllReduce fc, int mh_on, MhView mh) {
     __shared__ double part[8];
     __shared__ double s_total;
     const int p = blockIdx.x;
@@ -402,8 +402,14 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, ParamsView p
     const int pst = pk.pstatus[p];
     const bool redo = need_sweep[p] && !(pst & ST_SOLVER);
     const bool sharded = fc.pv.world > 1;
-    if (totals_only && !redo) {                            // traj_kernel already formed this pset's sum
-        if (!sharded) return;
+    // fused Metropolis iteration: accept/reject of the chains this kernel closes, and the iteration counter — bumped by
+    // whichever CTA finishes last (every CTA has read the counter before it counts itself)
+    const unsigned long long mh_it = mh_on ? *mh.it_dev + 1 : 0;
+    auto mh_tick = [&]() {
+        if (mh_on && threadIdx.x == 0 && atomicAdd(mh.tick_count, 1) == P - 1) { *mh.tick_count = 0; *mh.it_dev = mh_it; }
+    };
+    if (totals_only && !redo) {                            // traj_kernel already formed this pset's sum (and decided its chain)
+        if (!sharded) { mh_tick(); return; }
         if (threadIdx.x == 0) s_total = fc.totals_in[p];
     } else {
     // psets whose interpolant was not resolved on this grid are summed exactly below.  When they are a quarter of the
@@ -485,7 +491,11 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, ParamsView p
     }
     }
     if (!sharded) {
-        if (threadIdx.x == 0) out_pset[p] = s_total;
+        if (threadIdx.x == 0) {
+            out_pset[p] = s_total;
+            if (mh_on) mh_accept_chain(mh, mh_it, p);
+        }
+        mh_tick();
         return;
     }
     // ---- trees sharded over ranks: the all-reduce of the [P] sums is part of this kernel.  Every CTA stores its pset's
@@ -522,6 +532,7 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, ParamsView p
             s += v;
         }
         out_pset[q] = s;
+        if (mh_on && !s_timeout) mh_accept_chain(mh, mh_it, q);
     }
     __syncthreads();
 #ifdef GCDYN_COMM_TRACE
@@ -530,6 +541,7 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, ParamsView p
     if (threadIdx.x == 0) {
         if (s_timeout && fc.err) *fc.err = 1;
         *pr.seq_dev = seq;
+        if (mh_on) *mh.it_dev = mh_it;
     }
 }
 

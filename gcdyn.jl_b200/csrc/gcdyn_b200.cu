@@ -501,23 +501,23 @@ template <int M>
 int launch_finish_m(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, const PsetPack& pk, const double* tab, const TrajCfg& cfg, double T,
                     const double* partial, int splits, const double* tree_const, const int* need_sweep, int P,
                     double* out_tree, int32_t* status, double* out_pset, cudaStream_t st, int totals_only,
-                    const gcdyn::FusedAllReduce& fc) {
+                    const gcdyn::FusedAllReduce& fc, int mh_on, const gcdyn::MhView& mh) {
     cudaLaunchConfig_t lc = pdl_config(dim3((unsigned)P), dim3(256), 0, st);
     CU_TRY(ctx, cudaLaunchKernelEx(&lc, finish_kernel<M>, f->v, pv, pk, tab, cfg.tab_stride, cfg.S_cap, cfg.grid_doubles, T, partial,
-                                   splits, tree_const, need_sweep, P, f->mom.D, const_cast<int*>(need_sweep) + P, f->h_feedback, totals_only, out_tree, status, out_pset, fc));
+                                   splits, tree_const, need_sweep, P, f->mom.D, const_cast<int*>(need_sweep) + P, f->h_feedback, totals_only, out_tree, status, out_pset, fc, mh_on, mh));
     return GCDYN_OK;
 }
 
 int launch_finish(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const ParamsView& pv, const PsetPack& pk, const double* tab, const TrajCfg& cfg,
                   double T, const double* partial, int splits, const double* tree_const, const int* need_sweep, int P,
                   double* out_tree, int32_t* status, double* out_pset, cudaStream_t st, int totals_only,
-                  const gcdyn::FusedAllReduce& fc) {
+                  const gcdyn::FusedAllReduce& fc, int mh_on = 0, const gcdyn::MhView& mh = gcdyn::MhView{}) {
     switch (M) {
-        case 8: return launch_finish_m<8>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc);
-        case 12: return launch_finish_m<12>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc);
-        case 16: return launch_finish_m<16>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc);
-        case 20: return launch_finish_m<20>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc);
-        case 24: return launch_finish_m<24>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc);
+        case 8: return launch_finish_m<8>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc, mh_on, mh);
+        case 12: return launch_finish_m<12>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc, mh_on, mh);
+        case 16: return launch_finish_m<16>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc, mh_on, mh);
+        case 20: return launch_finish_m<20>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc, mh_on, mh);
+        case 24: return launch_finish_m<24>(ctx, f, pv, pk, tab, cfg, T, partial, splits, tree_const, need_sweep, P, out_tree, status, out_pset, st, totals_only, fc, mh_on, mh);
     }
     return fail(ctx, GCDYN_EINVAL, "unsupported Taylor order");
 }
@@ -533,12 +533,13 @@ void comm_poison(gcdyn_comm* c, int n_psets, cudaStream_t st);                  
 int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, double rate_max, double T, int method,
                  int M, int S_fixed, double tol, int flags, const double* host_gamma_shared, double* d_out_pset,
                  double* d_out_tree, int32_t* d_status, cudaStream_t st, PsetPack* pk_out, double rate_typical = 0.0,
-                 gcdyn_comm* comm = nullptr) {
+                 gcdyn_comm* comm = nullptr, const gcdyn::MhView* mh = nullptr, bool* mh_fused = nullptr) {
     // rate_max bounds every pset's rates (table capacity); rate_typical (> 0: the sampler's current rates) only picks
     // the Chebyshev interpolation degree — a pset it is too small for is flagged and summed exactly
     const int P = pv.P, K = pv.K;
     if (P > 65535) return fail(ctx, GCDYN_EUNSUPPORTED, "more than 65535 parameter sets per call");
     if (comm && comm->world <= 1) comm = nullptr;         // a world of one rank: nothing to combine
+    if (mh_fused) *mh_fused = false;
     PsetPack pk{};
     int rc = carve_pack(ctx, P, K, &pk);
     if (rc) return rc;
@@ -631,6 +632,12 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
                     fc.totals_in = ctx->out_pset.as<double>();
                 }
             }
+            if (totals && mh) {                            // fused Metropolis iteration (see traj_kernel / finish_kernel)
+                cc.mh_on = 1;
+                cc.mh_sharded = comm ? 1 : 0;
+                cc.mh = *mh;
+                if (mh_fused) *mh_fused = true;
+            }
             if (totals) {
                 cc.totals = comm ? ctx->out_pset.as<double>() : d_out_pset;
                 cc.tc_total = tree_const ? tree_const + Tn : nullptr;
@@ -645,7 +652,7 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             // the per-pset sums are already in d_out_pset; finish_kernel only redoes the psets the grid did not resolve
             if (prof) { cudaEventRecord(ctx->ev[3], st); cudaEventRecord(ctx->ev[4], st); cudaEventRecord(ctx->ev[5], st); }
             rc = launch_finish(ctx, M, f, pv, pk, ctx->table.as<double>(), cfg, T, nullptr, 0, nullptr, need_sweep, P,
-                               d_out_tree, d_status, d_out_pset, st, 1, fc);
+                               d_out_tree, d_status, d_out_pset, st, 1, fc, cc.mh_on, cc.mh);
             if (rc) return rc;
             ++launches;
             if (prof) { cudaEventRecord(ctx->ev[6], st); ctx->ev_valid = true; }
@@ -699,7 +706,7 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
                 // (sharded: every rank repeats, whatever it adopted — the ranks must make the same number of collective calls)
                 if (adopt != cc.D || comm)
                     return enqueue_eval(ctx, f, pv, rate_max, T, method, M, S_fixed, tol, flags, host_gamma_shared, d_out_pset,
-                                        d_out_tree == ctx->out_tree.as<double>() ? nullptr : d_out_tree, d_status, st, pk_out, rate_typical, comm);
+                                        d_out_tree == ctx->out_tree.as<double>() ? nullptr : d_out_tree, d_status, st, pk_out, rate_typical, comm, mh, mh_fused);
             }
             ctx->last_cheb_D = cc.D;
             ctx->last_feedback = f->h_feedback;
@@ -1640,7 +1647,7 @@ struct gcdyn_mh {
     void* hist = nullptr;              // device history buffer (grow-only)
     size_t hist_cap = 0;
     // one Metropolis iteration (propose → trajectory → finish → [all-reduce] → accept → tick) captured as a CUDA graph
-    cudaGraphExec_t graph = nullptr;
+    cudaGraphExec_t graph = nullptr, graph_many = nullptr;   // one iteration / MH_UNROLL iterations
     int graph_D = 0;                   // nodal grid degree the captured iteration was built for
     int64_t uncaptured_iters = 0;      // iterations run launch by launch (diagnostics)
 };
@@ -1676,7 +1683,7 @@ extern "C" int gcdyn_mh_create(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdy
     }
     // blob: xscale xshift yscale yshift mu delta rho sigma [C each] | type_space [K] | Gamma [K*K] | theta prop [6C each]
     //       | ll ll_prop [C each] | accepted [C i64] | inside [C i32]
-    const size_t nd = (size_t)8 * C + K + (size_t)K * K + (size_t)2 * gcdyn::MH_DIM * C + 2 * (size_t)C + C + (C + 1) / 2 + 8 + 8;
+    const size_t nd = (size_t)8 * C + K + (size_t)K * K + (size_t)2 * gcdyn::MH_DIM * C + 2 * (size_t)C + C + (C + 1) / 2 + 8 + 8 + 2;
     cudaError_t e = cudaMalloc(&m->blob, nd * 8);
     if (e != cudaSuccess) { delete m; return fail(ctx, GCDYN_ECUDA, cudaGetErrorString(e)); }
     std::vector<double> h(nd, 0.0);
@@ -1687,7 +1694,7 @@ extern "C" int gcdyn_mh_create(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdy
     const size_t o_rho = take(C), o_sig = take(C), o_ts = take(K), o_G = take((size_t)K * K);
     const size_t o_th = take((size_t)gcdyn::MH_DIM * C), o_pr = take((size_t)gcdyn::MH_DIM * C);
     const size_t o_ll = take(C), o_llp = take(C), o_acc = take(C), o_in = take((C + 1) / 2 + 1);
-    const size_t o_it = take(1), o_hist = take(4);
+    const size_t o_it = take(1), o_hist = take(4), o_tick = take(1);
     for (int c = 0; c < C; ++c) { h[o_rho + c] = d->rho; h[o_sig + c] = d->sigma; }
     std::memcpy(&h[o_ts], d->type_space, (size_t)K * 8);
     std::memcpy(&h[o_G], d->Gamma, (size_t)K * K * 8);
@@ -1709,6 +1716,7 @@ extern "C" int gcdyn_mh_create(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdy
     v.step = d->step; v.seed = d->seed;
     v.it_dev = reinterpret_cast<unsigned long long*>(base + o_it);
     v.hist = reinterpret_cast<gcdyn::MhView::Hist*>(base + o_hist);
+    v.tick_count = reinterpret_cast<int*>(base + o_tick);
     *out = m;
     return GCDYN_OK;
     GUARD_END(ctx)
@@ -1716,10 +1724,13 @@ extern "C" int gcdyn_mh_create(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdy
 
 namespace {
 // one batched likelihood of the C parameter sets currently in the blob → dst[C] (all-reduced when sharded)
-int mh_loglik(gcdyn_mh* m, double* dst, cudaStream_t st) {
+// `hook`: fuse this iteration's proposal, accept/reject and counter into the likelihood's kernels; *fused tells whether that
+// happened (it cannot when the forest takes the item sweep)
+int mh_loglik(gcdyn_mh* m, double* dst, cudaStream_t st, bool hook = false, bool* fused = nullptr) {
     gcdyn_ctx* ctx = m->ctx;
-    int rc = enqueue_eval(ctx, m->forest, m->pv, m->rate_bound, m->T, GCDYN_METHOD_ODE, 16, 0, 1e-11, GCDYN_FLAG_TOTALS, m->host_gamma.data(),
-                          dst, nullptr, nullptr, st, nullptr, m->rate_typical, m->comm);
+    int rc = enqueue_eval(ctx, m->forest, m->pv, m->rate_bound, m->T, GCDYN_METHOD_ODE, 16, 0, 1e-11,
+                          GCDYN_FLAG_TOTALS | FLAG_FORCE_MOMENTS, m->host_gamma.data(),
+                          dst, nullptr, nullptr, st, nullptr, m->rate_typical, m->comm, hook ? &m->v : nullptr, fused);
     if (rc && m->comm) {              // release the peers with NaN sums (see batch_impl), then report the local error
         const std::string why = ctx->err;
         cudaGetLastError();
@@ -1766,7 +1777,17 @@ extern "C" int gcdyn_mh_run(gcdyn_mh* m, int64_t iterations, double* theta_hist,
         if (rc) return rc;
         m->have_ll = true;
     }
+    const gcdyn_forest* f = m->forest;
     auto enqueue_iteration = [&]() -> int {
+        // fused form: the likelihood's own kernels draw the proposals, decide accept/reject and bump the counter — an
+        // iteration is traj_kernel + finish_kernel.  Forests that take the item sweep use the stand-alone kernels.
+        if (!f->mom_refused && f->v.n_trees > 0 && std::getenv("GCDYN_MH_UNFUSED") == nullptr) {
+            bool fused = false;
+            const int rc = mh_loglik(m, m->v.ll_prop, st, true, &fused);
+            if (rc) return rc;
+            if (fused) return GCDYN_OK;
+            return fail(ctx, GCDYN_ECUDA, "internal: the fused Metropolis iteration was not taken");
+        }
         gcdyn::mh_propose_kernel<<<blocks, threads, 0, st>>>(m->v);
         CU_TRY(ctx, cudaGetLastError());
         int rc = mh_loglik(m, m->v.ll_prop, st);
@@ -1778,39 +1799,51 @@ extern "C" int gcdyn_mh_run(gcdyn_mh* m, int64_t iterations, double* theta_hist,
         return GCDYN_OK;
     };
     const bool use_graph = std::getenv("GCDYN_MH_NO_GRAPH") == nullptr;
-    const gcdyn_forest* f = m->forest;
-    for (int64_t i = 0; i < iterations; ++i) {
-        // the captured iteration is valid as long as the forest's grid degree stands; a pending widening request (a
-        // quarter of a batch unresolved) is served by one launch-by-launch iteration, then the graph is re-captured
+    // Iterations are replayed from CUDA graphs: one holding MH_UNROLL consecutive iterations (the kernels take the iteration
+    // number, the history row and the all-reduce sequence from device memory, so every replay is the same graph) and one
+    // holding a single iteration for the remainder.  A graph is valid as long as the forest's grid degree stands; a pending
+    // widening request (a quarter of a batch unresolved) is served by launch-by-launch iterations, then re-captured.
+    constexpr int MH_UNROLL = 16;
+    auto capture = [&](int n, cudaGraphExec_t* out) -> int {
+        cudaGraph_t g = nullptr;
+        CU_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = GCDYN_OK;
+        for (int k = 0; k < n && !rc; ++k) rc = enqueue_iteration();
+        const cudaError_t ce = cudaStreamEndCapture(st, &g);
+        if (rc || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            return rc ? rc : fail(ctx, GCDYN_ECUDA, std::string("graph capture of a Metropolis iteration failed: ") + cudaGetErrorString(ce));
+        }
+        const cudaError_t ie = cudaGraphInstantiate(out, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) { *out = nullptr; return fail(ctx, GCDYN_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+        return GCDYN_OK;
+    };
+    for (int64_t i = 0; i < iterations;) {
         const bool widen_pending = f->h_feedback && f->D_cur > 0 && f->h_feedback[0] == f->D_cur && f->D_cur < 128;
-        if (use_graph && m->graph && (m->graph_D != f->D_cur || widen_pending)) {
+        if (m->graph && (m->graph_D != f->D_cur || widen_pending || !use_graph)) {
             cudaGraphExecDestroy(m->graph);
-            m->graph = nullptr;
+            if (m->graph_many) cudaGraphExecDestroy(m->graph_many);
+            m->graph = m->graph_many = nullptr;
         }
         if (use_graph && !m->graph && !widen_pending && m->uncaptured_iters > 0) {
-            // capture ONE iteration: every workspace already has its size (an uncaptured iteration ran before)
-            cudaGraph_t g = nullptr;
-            CU_TRY(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int rc = enqueue_iteration();
-            const cudaError_t ce = cudaStreamEndCapture(st, &g);
-            if (rc || ce != cudaSuccess || !g) {
-                if (g) cudaGraphDestroy(g);
-                cudaGetLastError();
-                return rc ? rc : fail(ctx, GCDYN_ECUDA, std::string("graph capture of a Metropolis iteration failed: ") + cudaGetErrorString(ce));
-            }
-            const cudaError_t ie = cudaGraphInstantiate(&m->graph, g, 0);
-            cudaGraphDestroy(g);
-            if (ie != cudaSuccess) { m->graph = nullptr; return fail(ctx, GCDYN_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+            // every workspace already has its size (an uncaptured iteration ran before)
+            int rc = capture(1, &m->graph);
+            if (!rc) rc = capture(MH_UNROLL, &m->graph_many);
+            if (rc) return rc;
             m->graph_D = f->D_cur;
         }
         if (use_graph && m->graph) {
-            CU_TRY(ctx, cudaGraphLaunch(m->graph, st));
+            if (iterations - i >= MH_UNROLL) { CU_TRY(ctx, cudaGraphLaunch(m->graph_many, st)); i += MH_UNROLL; m->iteration += MH_UNROLL; }
+            else { CU_TRY(ctx, cudaGraphLaunch(m->graph, st)); ++i; ++m->iteration; }
         } else {
             const int rc = enqueue_iteration();
             if (rc) return rc;
             ++m->uncaptured_iters;
+            ++i;
+            ++m->iteration;
         }
-        ++m->iteration;
     }
     if (d_ht) {
         CU_TRY(ctx, cudaMemcpyAsync(theta_hist, d_ht, (size_t)iterations * C * gcdyn::MH_DIM * 8, cudaMemcpyDeviceToHost, st));
@@ -1865,6 +1898,7 @@ extern "C" void gcdyn_mh_destroy(gcdyn_mh* m) {
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     if (m->graph) cudaGraphExecDestroy(m->graph);
+    if (m->graph_many) cudaGraphExecDestroy(m->graph_many);
     if (m->blob) cudaFree(m->blob);
     if (m->hist) cudaFree(m->hist);
     cudaSetDevice(prev);

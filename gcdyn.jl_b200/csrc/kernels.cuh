@@ -24,6 +24,7 @@
 #include <math_constants.h>
 
 #include "common.h"
+#include "metropolis.cuh"
 
 namespace gcdyn {
 
@@ -203,6 +204,10 @@ struct ChebCfg {
     double* totals;        // [P]
     const double* tc_total;   // [1] Σ_t tree_const[t] (shared Γ), or nullptr
     int any_self_loop;     // the forest holds a tree the reference gives -Inf for
+    // fused Metropolis iteration (metropolis.cuh): the CTA of pset p draws chain p's proposal before it integrates and,
+    // when nothing is left to combine (one rank, pset resolved), decides accept/reject right after its sum
+    int mh_on, mh_sharded;
+    MhView mh;
 };
 
 // Cell containing τ on a pset's (non-uniform) grid: largest s < S with grid[s] ≤ τ.
@@ -538,30 +543,41 @@ __device__ __forceinline__ void cell_consume(const ParamsView& pv, const TrajCfg
 // After the last cell, all threads: resolution check of the degree-D interpolant (its last three Chebyshev coefficients
 // must be below tol — otherwise the pset is flagged and finish_kernel sums its items exactly from the table) and the
 // fallback flag.
-__device__ __forceinline__ void nodal_finish(const PsetPack& pk, const ChebCfg& cfg, int p, const TrajSmem& ts, int* s_flag) {
+__device__ __forceinline__ void nodal_finish(const ChebCfg& cfg, int p, const TrajSmem& ts, int* s_flag, int pst,
+                                             unsigned long long mh_it) {
     const MomentView& mv = cfg.mv;
     const int K = mv.K, C1 = mv.C1, D = cfg.D, NV = (D + 1) * K;
     double* V = ts.V;
     double* Arow = cfg.A + (size_t)p * mv.Jst;
-    const int pst = pk.pstatus[p];
     if (pst & ST_SOLVER) {                               // CTA-uniform: a failed trajectory has no usable nodes; it is
         for (int idx = threadIdx.x; idx < NV; idx += blockDim.x) Arow[C1 + idx] = 0.0;   // -Inf through its status
-        if (threadIdx.x == 0) { cfg.need_sweep[p] = 0; if (cfg.totals) cfg.totals[p] = -CUDART_INF; }
+        if (threadIdx.x == 0) {
+            cfg.need_sweep[p] = 0;
+            if (cfg.totals) {
+                cfg.totals[p] = -CUDART_INF;
+                if (cfg.mh_on && !cfg.mh_sharded) mh_accept_chain(cfg.mh, mh_it, p);
+            }
+        }
         return;
     }
     // a_{D−j} = (2/D) Σ''_k V_k (−1)^k cos(π k j / D) for j = 0, 1, 2 (a_D halved).  NSEG threads per type share the
     // node range; the partial sums are combined in segment order.
     const int NSEG = min(8, max(1, (int)blockDim.x / K));
+    const int per = (D + NSEG) / NSEG;                   // nodes per segment (32-bit arithmetic only: this is the tail)
     for (int w = threadIdx.x; w < NSEG * K; w += blockDim.x) {
         const int seg = w / K, x = w - seg * K;
-        const int k0 = (int)((long long)(D + 1) * seg / NSEG), k1 = (int)((long long)(D + 1) * (seg + 1) / NSEG);
+        const int k0 = seg * per, k1 = min(D + 1, k0 + per);
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        int i2 = 2 * k0;                                 // (2k) mod 2D
+        if (i2 >= 2 * D) i2 -= 2 * D;
         for (int k = k0; k < k1; ++k) {
             const double wk = (k == 0 || k == D) ? 0.5 : 1.0;
             const double v = (k & 1) ? -wk * V[k * K + x] : wk * V[k * K + x];
             s0 += v;
             s1 = fma(v, ts.costab[k], s1);
-            s2 = fma(v, ts.costab[(2 * k) % (2 * D)], s2);
+            s2 = fma(v, ts.costab[i2], s2);
+            i2 += 2;
+            if (i2 >= 2 * D) i2 -= 2 * D;
         }
         ts.chk[(seg * 3 + 0) * K + x] = s0;
         ts.chk[(seg * 3 + 1) * K + x] = s1;
@@ -599,6 +615,7 @@ __device__ __forceinline__ void nodal_finish(const PsetPack& pk, const ChebCfg& 
             for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += tpart[w];
             if (cfg.tc_total) sum += *cfg.tc_total;
             cfg.totals[p] = cfg.any_self_loop ? -CUDART_INF : sum;
+            if (cfg.mh_on && !cfg.mh_sharded) mh_accept_chain(cfg.mh, mh_it, p);   // totals IS the sampler's ll_prop
         }
     }
 }
@@ -620,6 +637,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
 #endif
     __shared__ __align__(8) uint64_t s_full[RING_SLOTS], s_empty[RING_SLOTS];   // ring of cells → consumer warps
     __shared__ int s_flag;                              // fallback reasons collected while the integration runs
+    __shared__ int s_pst;                               // the pset's status, for the tail (no trip through global memory)
     const bool cheb = cc.D > 0;                         // CTA-uniform
     const int KSB = KPL == 1 ? KP : ((K + 3) & ~3);     // broadcast buffer length (multiple of 4)
     const size_t traj_doubles = 2 * (size_t)KSB + (KPL == 1 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
@@ -640,7 +658,18 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
 #pragma unroll
         for (int i = 0; i < RING_SLOTS; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, NCONS); }
     }
-    __syncthreads();
+    // fused Metropolis iteration: six threads draw the six coordinates of chain p's proposal and write its parameters,
+    // which everybody reads behind the barrier
+    unsigned long long mh_it = 0;
+    if (cc.mh_on) {
+        mh_it = *cc.mh.it_dev + 1;
+        int in = 1;
+        if (threadIdx.x < MH_DIM) in = mh_propose_coord(cc.mh, mh_it, p, threadIdx.x) ? 1 : 0;
+        const int all_in = __syncthreads_and(in);
+        if (threadIdx.x == 0) cc.mh.inside[p] = all_in;
+    } else {
+        __syncthreads();
+    }
 #ifndef GCDYN_EXP_LATE_PDL
     pdl_launch_dependents();                            // the contraction's CTAs may become resident behind this grid
 #endif
@@ -978,6 +1007,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
         pk.perr[p] = __hiloint2double((int)min(emax + 1u, 0x7ff00000u), 0);   // upper bound of the largest accepted indicator
         pk.S[p] = s > 0 ? s : 1;
         pk.pstatus[p] = unresolved ? ST_SOLVER : 0;
+        s_pst = unresolved ? ST_SOLVER : 0;
     }
     }   // integrating warps
 #ifdef GCDYN_EXP_LATE_PDL
@@ -986,7 +1016,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
     if (!cheb) return;
     __syncthreads();                                    // node values, status of this pset are complete and visible
     TRACE_STAMP(4);
-    nodal_finish(pk, cc, p, ts, &s_flag);
+    nodal_finish(cc, p, ts, &s_flag, s_pst, mh_it);
 #ifdef GCDYN_TRAJ_TRACE
     __syncthreads();
     TRACE_STAMP(5);

@@ -42,42 +42,27 @@ struct MhView {
     // device-side bookkeeping, so that ONE captured CUDA graph serves every iteration: the number of completed
     // iterations (the kernels derive their random-number counter from it) and where history rows go
     unsigned long long* it_dev;     // [1]
+    int* tick_count;                // [1] CTAs of the closing kernel that are done with this iteration (fused form)
     struct Hist { double* theta; double* ll; long long base; long long rows; }* hist;   // [1]
 };
 
-// One thread per chain: Gaussian random-walk proposal (Box–Muller on slots 2j, 2j+1), box test, and the
-// canonical parameters of the (clipped) proposal written straight into the likelihood's parameter blob.
-__global__ void mh_propose_kernel(MhView v) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= v.C) return;
-    const uint64_t it = *v.it_dev + 1;
-    bool in = true;
-    double q[MH_DIM];
-#pragma unroll
-    for (int j = 0; j < MH_DIM; ++j) {
-        const double u1 = mh_uniform(v.seed, it, c, 2 * j), u2 = mh_uniform(v.seed, it, c, 2 * j + 1);
-        const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-        const double x = v.theta[c * MH_DIM + j] + v.step * z;
-        v.prop[c * MH_DIM + j] = x;
-        in = in && (x >= v.lower[j]) && (x <= v.upper[j]);
-        // proposals outside the box are rejected without looking at their likelihood, but still evaluated
-        // (clipped), so that every iteration is one batch of exactly C parameter sets
-        q[j] = fmin(fmax(x, fmax(v.lower[j], -50.0)), fmin(v.upper[j], 50.0));
-    }
-    v.inside[c] = in ? 1 : 0;
-    v.xscale[c] = exp(q[0]);
-    v.xshift[c] = q[1];
-    v.yscale[c] = exp(q[2]);
-    v.yshift[c] = exp(q[3]);
-    v.mu[c] = exp(q[4]);
-    v.delta[c] = exp(q[5]);
+// Coordinate j of chain c's Gaussian random-walk proposal (Box–Muller on slots 2j, 2j+1): writes the proposal and the
+// canonical parameter of the (clipped) proposal into the likelihood's parameter blob; returns whether it lies in the box.
+__device__ __forceinline__ bool mh_propose_coord(const MhView& v, uint64_t it, int c, int j) {
+    const double u1 = mh_uniform(v.seed, it, c, 2 * j), u2 = mh_uniform(v.seed, it, c, 2 * j + 1);
+    const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    const double x = v.theta[c * MH_DIM + j] + v.step * z;
+    v.prop[c * MH_DIM + j] = x;
+    // proposals outside the box are rejected without looking at their likelihood, but still evaluated
+    // (clipped), so that every iteration is one batch of exactly C parameter sets
+    const double q = fmin(fmax(x, fmax(v.lower[j], -50.0)), fmin(v.upper[j], 50.0));
+    double* dst = j == 0 ? v.xscale : j == 1 ? v.xshift : j == 2 ? v.yscale : j == 3 ? v.yshift : j == 4 ? v.mu : v.delta;
+    dst[c] = j == 1 ? q : exp(q);
+    return (x >= v.lower[j]) && (x <= v.upper[j]);
 }
 
-// Metropolis accept/reject (flat prior: the ratio is the likelihood ratio); history rows are optional.
-__global__ void mh_accept_kernel(MhView v) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= v.C) return;
-    const uint64_t it = *v.it_dev + 1;
+// Metropolis accept/reject of chain c (flat prior: the ratio is the likelihood ratio); history rows are optional.
+__device__ __forceinline__ void mh_accept_chain(const MhView& v, uint64_t it, int c) {
     const long long hist_row = (long long)(it - 1) - v.hist->base;
     double* __restrict__ hist_theta = (hist_row >= 0 && hist_row < v.hist->rows) ? v.hist->theta : nullptr;
     double* __restrict__ hist_ll = v.hist->ll;
@@ -95,6 +80,23 @@ __global__ void mh_accept_kernel(MhView v) {
         for (int j = 0; j < MH_DIM; ++j) hist_theta[((size_t)hist_row * v.C + c) * MH_DIM + j] = v.theta[c * MH_DIM + j];
         hist_ll[(size_t)hist_row * v.C + c] = v.ll[c];
     }
+}
+
+// The same steps as stand-alone kernels (one thread per chain), for forests that take the item sweep.
+__global__ void mh_propose_kernel(MhView v) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.C) return;
+    const uint64_t it = *v.it_dev + 1;
+    bool in = true;
+#pragma unroll
+    for (int j = 0; j < MH_DIM; ++j) in = mh_propose_coord(v, it, c, j) && in;
+    v.inside[c] = in ? 1 : 0;
+}
+
+__global__ void mh_accept_kernel(MhView v) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= v.C) return;
+    mh_accept_chain(v, *v.it_dev + 1, c);
 }
 
 // one iteration completed (its own launch: every block of mh_accept_kernel has read the counter by then)

@@ -3,7 +3,7 @@
        -DGCDYN_TRAJ_TRACE -o tools/_trace/libgcdyn_trace.so gcdyn.jl_b200/csrc/gcdyn_b200.cu
   GCDYN_B200_LIB=tools/_trace/libgcdyn_trace.so python tools/trace_probe.py
 The stamps perturb the kernel (≈1.5× slower); use the numbers relative to each other."""
-import sys, ctypes as C
+import os, sys, ctypes as C
 sys.path[:0] = ["/root/repo", "/root/repo/gcdyn.jl_b200"]
 import numpy as np, torch, gcdyn, workloads
 from gcdyn.likelihood import evaluate, pack_params, _lib
@@ -12,7 +12,7 @@ flat = workloads.flat_forest("C3"); models = workloads.jittered_models("C3", P)
 params = pack_params(models); ctx = gcdyn.Context(0); forest = gcdyn.Forest(flat, None, 4.0, ctx=ctx)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for _ in range(5):
-    flush.zero_()
+    if not os.environ.get("NOFLUSH"): flush.zero_()
     evaluate(forest, params, 4.0, want_status=False)
     torch.cuda.synchronize()
 lib = _lib()

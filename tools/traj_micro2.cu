@@ -157,12 +157,12 @@ __global__ void cell_loop(double* out, long long* cyc, int cells, double hfix, d
     out[blockIdx.x * blockDim.x + threadIdx.x] = pcur + 1e-30 * (hsum + slot[lane]);
 }
 
-template <int M, int V, int W = 0>
+template <int M, int V, int W = 0, int KPX = 20>
 void run(const char* name, double* out, long long* cyc, int nblocks, int nthreads) {
     const int cells = 2000;
     long long h;
     double res[32];
-    cell_loop<M, 20, V, W><<<nblocks, nthreads>>>(out, cyc, cells, 0.05, 1.3, 1.8, 0.4, 0.02);
+    cell_loop<M, KPX, V, W><<<nblocks, nthreads>>>(out, cyc, cells, 0.05, 1.3, 1.8, 0.4, 0.02);
     cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
     cudaMemcpy(res, out, 32 * 8, cudaMemcpyDeviceToHost);
     printf("%-52s M=%d: %.0f cycles per cell, %.1f per order   p[0]=%.15f p[19]=%.15f\n", name, M, (double)h / cells,
@@ -188,6 +188,13 @@ int main() {
         run<16, 1, 1>("V1 + spin, 256 CTAs", out, cyc, 256, 128);
         run<16, 1, 4>("V1 + nanosleep, 256 CTAs", out, cyc, 256, 128);
     }
+    run<16, 2, 0, 4>("V2 K=4", out, cyc, 1, 32);
+    run<16, 2, 0, 8>("V2 K=8", out, cyc, 1, 32);
+    run<16, 2, 0, 12>("V2 K=12", out, cyc, 1, 32);
+    run<16, 2, 0, 16>("V2 K=16", out, cyc, 1, 32);
+    run<16, 2, 0, 20>("V2 K=20", out, cyc, 1, 32);
+    run<16, 2, 0, 24>("V2 K=24", out, cyc, 1, 32);
+    run<16, 2, 0, 32>("V2 K=32", out, cyc, 1, 32);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
