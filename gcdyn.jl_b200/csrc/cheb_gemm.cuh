@@ -191,54 +191,50 @@ __global__ void __launch_bounds__(256) colsum_kernel(const double* __restrict__ 
     }
 }
 
-// degree_probe_kernel (one CTA, off the critical path, run now and then): full Chebyshev coefficients of a few psets'
-// interpolants from their node values → the smallest degree whose tail Σ_{k>d}|a_k| is below tol for every sampled pset
-// and type.  The host reads the result (pinned memory) at a later call and re-sizes the nodal grid when a smaller one
-// suffices.  out[0] = that degree, out[1] = the grid degree it was measured on.
-__global__ void __launch_bounds__(512) degree_probe_kernel(const double* __restrict__ A, MomentView mv, const int* __restrict__ need_sweep,
-                                                           int P, double tol, int* __restrict__ out) {
+// degree_probe_kernel (calibration of a forest's grid, once): one CTA per parameter set computes the full Chebyshev
+// spectrum of its interpolants from the node values and the smallest degree whose tail Σ_{k>d}|a_k| is below tol for every
+// type; the maximum over the batch lands in out[0] (atomicMax; the host zeroes it first), the grid degree it was measured
+// on in out[1].  Parameter sets that are flagged already (or failed) do not vote.
+__global__ void __launch_bounds__(256) degree_probe_kernel(const double* __restrict__ A, MomentView mv, const int* __restrict__ need_sweep,
+                                                           const int* __restrict__ pstatus, double tol, int* __restrict__ out) {
     extern __shared__ __align__(16) double psm[];          // [2D] cos | [(D+1)*K] values | [(D+1)*K] |a_d|
     const int K = mv.K, D = mv.D, NV = (D + 1) * K;
+    const int p = blockIdx.x;
+    if (need_sweep[p] || (pstatus[p] & ST_SOLVER)) return;   // CTA-uniform
     double* ctab = psm;
     double* V = psm + 2 * D;
     double* Ac = V + NV;
     __shared__ int s_deff;
     if (threadIdx.x == 0) s_deff = 4;
     for (int m = threadIdx.x; m < 2 * D; m += blockDim.x) ctab[m] = cospi((double)m / (double)D);
-    const int nsample = P < 16 ? P : 16;
-    for (int si = 0; si < nsample; ++si) {
-        const int p = (int)((long long)si * P / nsample);
-        __syncthreads();
-        if (need_sweep[p]) continue;                       // CTA-uniform
-        const double* row = A + (size_t)p * mv.Jst + mv.C1;
-        for (int i = threadIdx.x; i < NV; i += blockDim.x) V[i] = row[i];
-        __syncthreads();
-        for (int i = threadIdx.x; i < NV; i += blockDim.x) {
-            const int d = i / K, x = i - d * K;
-            double s0 = 0.0, s1 = 0.0;
-            int idx = 0;
-            for (int k = 0; k <= D; ++k) {
-                const double wk = (k == 0 || k == D) ? 0.5 : 1.0;
-                const double t = wk * V[k * K + x] * ctab[idx];
-                if (k & 1) s1 += t; else s0 += t;
-                idx += d;
-                if (idx >= 2 * D) idx -= 2 * D;
-            }
-            Ac[i] = fabs((2.0 / (double)D) * (s0 + s1)) * ((d == 0 || d == D) ? 0.5 : 1.0);
+    const double* row = A + (size_t)p * mv.Jst + mv.C1;
+    for (int i = threadIdx.x; i < NV; i += blockDim.x) V[i] = row[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < NV; i += blockDim.x) {
+        const int d = i / K, x = i - d * K;
+        double s0 = 0.0, s1 = 0.0;
+        int idx = 0;
+        for (int k = 0; k <= D; ++k) {
+            const double wk = (k == 0 || k == D) ? 0.5 : 1.0;
+            const double t = wk * V[k * K + x] * ctab[idx];
+            if (k & 1) s1 += t; else s0 += t;
+            idx += d;
+            if (idx >= 2 * D) idx -= 2 * D;
         }
-        __syncthreads();
-        for (int x = threadIdx.x; x < K; x += blockDim.x) {
-            double tail = 0.0;
-            int found = 4;
-            for (int d = D; d > 4; --d) {
-                tail += Ac[d * K + x];
-                if (!(tail <= tol)) { found = d; break; }
-            }
-            atomicMax(&s_deff, found);
-        }
+        Ac[i] = fabs((2.0 / (double)D) * (s0 + s1)) * ((d == 0 || d == D) ? 0.5 : 1.0);
     }
     __syncthreads();
-    if (threadIdx.x == 0) { out[0] = s_deff; out[1] = D; }
+    for (int x = threadIdx.x; x < K; x += blockDim.x) {
+        double tail = 0.0;
+        int found = 4;
+        for (int d = D; d > 4; --d) {
+            tail += Ac[d * K + x];
+            if (!(tail <= tol)) { found = d; break; }
+        }
+        atomicMax(&s_deff, found);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { atomicMax(out, s_deff); out[1] = D; }
 }
 
 // Shared Γ: per-tree constant Σ_{x→y} count · log Γ_xy (the pset-independent part of Σ log δΓ_xy), one warp per tree.

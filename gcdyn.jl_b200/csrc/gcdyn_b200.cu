@@ -388,9 +388,12 @@ int launch_sweep(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const PsetPack& p
 }
 
 // Degrees the nodal Chebyshev grid may take.
-const int D_LADDER[] = {8, 12, 16, 20, 24, 28, 32, 36, 40, 48, 56, 64, 80, 96, 112, 128};
+// every even degree up to 64 (a column block of K doubles per degree: no reason to round further), then coarser rungs
 int degree_ladder_ceil(int d) {
-    for (int v : D_LADDER) if (v >= d) return v;
+    if (d <= 8) return 8;
+    if (d <= 64) return (d + 1) & ~1;
+    const int coarse[] = {72, 80, 96, 112, 128};
+    for (int v : coarse) if (v >= d) return v;
     return 128;
 }
 
@@ -403,7 +406,7 @@ int degree_ladder_ceil(int d) {
 // pinned word, and the next call takes the next rung.
 size_t fit_degree_smem(int K, int D) { return (2 * (size_t)D + ((size_t)D + 1) * K) * 8 + 1024; }
 int clamp_degree(int D, int K, int M, int smem_optin) {
-    while (D > 8 && (traj_smem_bytes(K, D, M) + 1024 > (size_t)smem_optin || fit_degree_smem(K, D) > (size_t)smem_optin)) D -= 4;
+    while (D > 8 && (traj_smem_bytes(K, D, M) + 1024 > (size_t)smem_optin || fit_degree_smem(K, D) > (size_t)smem_optin)) D -= 2;
     return D;
 }
 int initial_degree(double T, double rate, int K, int M, int smem_optin) {
@@ -694,12 +697,18 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
                 if (psm + 1024 <= (size_t)ctx->smem_optin) {
                     if (psm > 48 * 1024)
                         CU_TRY(ctx, cudaFuncSetAttribute(degree_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-                    degree_probe_kernel<<<1, 512, psm, st>>>((const double*)ctx->gemm_a.as<double>(), mv, (const int*)need_sweep, P,
-                                                             cc.tol, f->h_feedback + 1);
+                    CU_TRY(ctx, ctx->probe.ensure(64));
+                    CU_TRY(ctx, cudaMemsetAsync(ctx->probe.p, 0, 8, st));
+                    degree_probe_kernel<<<P, 256, psm, st>>>((const double*)ctx->gemm_a.as<double>(), mv, (const int*)need_sweep,
+                                                             (const int*)pk.pstatus, cc.tol, ctx->probe.as<int>());
                     CU_TRY(ctx, cudaGetLastError());
+                    CU_TRY(ctx, cudaMemcpyAsync(f->h_feedback + 1, ctx->probe.p, 8, cudaMemcpyDeviceToHost, st));
                     CU_TRY(ctx, cudaStreamSynchronize(st));
+                    // +3: the last three coefficients of the adopted grid must lie in the resolved tail; a sampler (rate_typical
+                    // given) gets six more degrees of head-room, because its parameter sets will move away from this batch
+                    const int margin = 3 + (rate_typical > 0.0 ? 6 : 0);
                     if (f->h_feedback[2] == cc.D && f->h_feedback[1] > 4)
-                        adopt = std::min(cc.D, clamp_degree(degree_ladder_ceil(f->h_feedback[1] + 3), K, M, ctx->smem_optin));
+                        adopt = std::min(cc.D, clamp_degree(degree_ladder_ceil(f->h_feedback[1] + margin), K, M, ctx->smem_optin));
                 }
                 f->D_cur = adopt;
                 f->D_T = T;

@@ -53,9 +53,8 @@ if world > 1:
 
 
 def step():
-    evaluate_resident(forest, dpar, T, out.data_ptr(), out_tree.data_ptr(), 0, stream.cuda_stream)
-    if peer is not None:
-        peer.allreduce(out.data_ptr(), P, stream.cuda_stream)
+    # N > 1: the all-reduce of the [P] sums is fused into finish_kernel (gcdyn_loglik_batch_resident_sharded)
+    evaluate_resident(forest, dpar, T, out.data_ptr(), out_tree.data_ptr(), 0, stream.cuda_stream, comm=peer)
 
 
 def sync_all():
@@ -85,7 +84,7 @@ for _ in range(5):
 sync_all()
 cheb = ctx.last_cheb()
 diag = ctx.last_diag(P)
-J = 2 * K + 4 + (cheb["effective_degree"] + 1) * K
+J = 2 * K + 4 + (cheb["interp_degree"] + 1) * K
 gemm_flop = 2.0 * Tn * P * J
 peak = ctx.probe_fp64_peak()
 host = out_tree.cpu().numpy().reshape(P, Tn)
