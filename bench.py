@@ -406,7 +406,7 @@ def run_gpu(args):
                                "MEASURED_PEAKS.json has no FP64 figure",
                 "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full of this "
                 "command (profiles/r2_dram_traffic.json); L2 is flushed before every step, so the kernels' inputs come from HBM",
-                "traffic_per_kernel": {k: v.get("dram_bytes_per_launch") for k, v in tr.items()} if tr else None,
+                "traffic_per_kernel": {k: v.get("dram_bytes_per_launch") for k, v in tr.items() if isinstance(v, dict)} if tr else None,
                 "mean_cells_per_pset": S_mean, "max_cells_per_pset": S,
                 "kernel_ms": {k: acc[k] for k in ran},
                 "kernel_share": {k: acc[k] / sum(acc[r] for r in ran) for k in ran},
