@@ -284,8 +284,9 @@ __global__ void __launch_bounds__(128) gemm_kernel(const double* __restrict__ A,
     auto As = [&](int st) { return gsm + (size_t)st * 2 * GT_TILE * GT_LD; };
     auto Bs = [&](int st) { return gsm + (size_t)st * 2 * GT_TILE * GT_LD + GT_TILE * GT_LD; };
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int p0 = blockIdx.y * GT_TILE;
-    const int64_t t0 = (int64_t)blockIdx.x * GT_TILE;
+    const unsigned n_pt = (unsigned)((P + GT_TILE - 1) / GT_TILE);             // pset tiles vary fastest (see the launch site)
+    const int p0 = (int)(blockIdx.x % n_pt) * GT_TILE;
+    const int64_t t0 = (int64_t)(blockIdx.x / n_pt) * GT_TILE;
     const long long Jst = mv.Jst;
     const double* Mt = mv.Mt;
     // segment 1: count columns + nodal columns; segment 2: K² block

@@ -73,6 +73,7 @@ struct gcdyn_ctx {
     bool profile = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int last_cheb_D = 0;
+    bool last_traj_sharded = false;       // the last evaluation integrated only this rank's slice of the parameter sets
     const int* last_feedback = nullptr;   // pinned feedback words of the forest the last evaluation ran on
     bool gemm_attr_set = false;
     bool ev_valid = false;
@@ -112,6 +113,15 @@ struct gcdyn_comm {
     bool connected = false;
     unsigned long long timeout_ns = 20000000000ULL;   // bounded wait for the peers' flags ($GCDYN_PEER_TIMEOUT_MS)
     int* h_err = nullptr;                 // pinned: raised by the kernel when a peer did not arrive in time
+    // trajectory sharding: a second peer-mapped window that holds the coefficient rows of the whole batch
+    //   [half 0 | half 1 | flag words [world] | CTA counter]   (peer_allreduce.cuh, row_exchange_kernel)
+    void* rows = nullptr;
+    void* rows_peer[gcdyn::PEER_MAX_WORLD] = {};
+    size_t rows_half = 0;                 // bytes per half
+    bool rows_connected = false;
+    unsigned long long rows_seq = 0;      // exchanges enqueued so far (host-side: the exchange is never graph-captured)
+    bool push_from_traj = true;           // $GCDYN_ROW_PUSH=kernel: the rows are copied by row_exchange_kernel instead
+    int shard_min_psets = 512;            // batches smaller than this are integrated by every rank ($GCDYN_TRAJ_SHARD_MIN_PSETS)
 };
 
 struct gcdyn_sim {
@@ -315,7 +325,7 @@ int launch_traj_inst(gcdyn_ctx* ctx, const ParamsView& pv, const PsetPack& pk, c
     const size_t smem = traj_smem_bytes(pv.K, cc.D, M);
     if (smem > 48 * 1024)
         CU_TRY(ctx, cudaFuncSetAttribute(traj_kernel<M, KP, KPL, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    traj_kernel<M, KP, KPL, NPW><<<pv.P, TRAJ_THREADS, smem, st>>>(pv, pk, cfg, cc, tab);
+    traj_kernel<M, KP, KPL, NPW><<<cfg.n_ctas > 0 ? cfg.n_ctas : pv.P, TRAJ_THREADS, smem, st>>>(pv, pk, cfg, cc, tab);
     CU_TRY(ctx, cudaGetLastError());
     return GCDYN_OK;
 }
@@ -528,6 +538,8 @@ int launch_finish(gcdyn_ctx* ctx, int M, const gcdyn_forest* f, const ParamsView
 int comm_enqueue(gcdyn_comm* c, const double* d_in, double* out, int n_psets, cudaStream_t st);   // peer all-reduce (below)
 int comm_fused_view(gcdyn_comm* c, int n_psets, gcdyn::FusedAllReduce* out);                      // its form fused into finish_kernel
 void comm_poison(gcdyn_comm* c, int n_psets, cudaStream_t st);                                     // NaN contribution of a rank that failed
+int comm_row_exchange(gcdyn_comm* c, unsigned long long seq, int P, long long Jst, long long Juse, int p0, int p1, int D,
+                      const PsetPack& pk, int* need_sweep, cudaStream_t st);                                             // all-gather of the coefficient rows
 
 // Enqueue one evaluation on `st`.  All pointers are device pointers; d_out_tree/d_status may be null.
 // `comm`: the forest is this rank's shard — d_out_pset receives the sums over all ranks (fused into finish_kernel on the
@@ -589,8 +601,33 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             if (rc) return rc;
             if (!f->mom.Mt) use_gemm = false;              // refused: too large for the free memory, or the sweep is cheaper
         }
+        // trajectory sharding (trees sharded over ranks AND a batch of several waves): every rank integrates a slice of the
+        // parameter sets and the coefficient rows are all-gathered over peer memory.  Whether the exchange takes place is a
+        // function of (P, world, flags) alone — every rank decides alike and makes the same number of exchanges.
+        const bool shard_eligible = comm && comm->rows_connected && !mh && !(flags & (GCDYN_FLAG_TOTALS | GCDYN_FLAG_SWEEP_ONLY)) &&
+                                    P >= comm->shard_min_psets && P >= comm->world;
+        bool shard_traj = false;
+        unsigned long long row_seq = 0;
+        int own_lo = 0, own_hi = P;
+        if (shard_eligible) {
+            row_seq = ++comm->rows_seq;
+            const size_t need_bytes = use_gemm ? (size_t)P * (size_t)f->mom.Jst * 8 + (size_t)P * sizeof(gcdyn::RowMeta) : 0;
+            if (!use_gemm || need_bytes > comm->rows_half) {
+                // this rank cannot take part (no contraction here, or the window is too small for this degree): tell the
+                // peers (degree 0 in the flag word) so that nobody contracts rows that never arrive; every rank reports
+                rc = comm_row_exchange(comm, row_seq, 0, 0, 0, 0, 0, 0, pk, nullptr, st);
+                if (rc) return rc;
+                ++launches;
+                if (use_gemm) return fail(ctx, GCDYN_ENOMEM, "row window too small for this batch: gcdyn_comm_rows_create needs " +
+                                                             std::to_string(2 * need_bytes) + " bytes");
+            } else {
+                shard_traj = true;
+                own_lo = (int)((long long)P * comm->rank / comm->world);
+                own_hi = (int)((long long)P * (comm->rank + 1) / comm->world);
+            }
+        }
         if (use_gemm) {
-            CU_TRY(ctx, ctx->gemm_a.ensure((size_t)P * (size_t)f->mom.Jst * 8));
+            if (!shard_traj) CU_TRY(ctx, ctx->gemm_a.ensure((size_t)P * (size_t)f->mom.Jst * 8));
             CU_TRY(ctx, ctx->flags.ensure((size_t)(P + 2) * 4));
             need_sweep = ctx->flags.as<int>();
             cc.T = T;
@@ -598,7 +635,8 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
             cc.D = f->mom.D;
             cc.compact_tc = pv.gamma_stride == 0 ? 1 : 0;
             cc.mv = f->mom;
-            cc.A = ctx->gemm_a.as<double>();
+            cc.A = shard_traj ? reinterpret_cast<double*>(static_cast<char*>(comm->rows) + (size_t)(row_seq & 1ULL) * comm->rows_half)
+                              : ctx->gemm_a.as<double>();
             cc.need_sweep = need_sweep;
             cc.nflag = need_sweep + P;
         }
@@ -647,9 +685,32 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
                 cc.any_self_loop = f->any_self_loop ? 1 : 0;
             }
         }
+        if (shard_traj) {
+            cfg.p_base = own_lo; cfg.n_ctas = own_hi - own_lo; cfg.own_lo = own_lo; cfg.own_hi = own_hi;
+            // the rows travel from the CTAs that finish them (GCDYN_ROW_PUSH=kernel: from row_exchange_kernel instead)
+            if (comm->push_from_traj) {
+                cc.push.w2 = (int)((cc.compact_tc ? f->mom.J1 : f->mom.Jst) / 2);
+                for (int r = 0; r < comm->world; ++r)
+                    if (r != comm->rank)
+                        cc.push.dst[cc.push.n++] = reinterpret_cast<double*>(static_cast<char*>(comm->rows_peer[r]) + (size_t)(row_seq & 1ULL) * comm->rows_half);
+            }
+        }
         rc = launch_traj(ctx, M, pv, pk, cfg, cc, ctx->table.as<double>(), st);
         if (rc) return rc;
         ++launches;
+        if (shard_traj) {
+            const long long juse = cc.push.n > 0 ? 0 : (cc.compact_tc ? f->mom.J1 : f->mom.Jst);
+            cc.push.n = 0;
+            rc = comm_row_exchange(comm, row_seq, P, f->mom.Jst, juse, own_lo, own_hi, cc.D, pk, need_sweep, st);
+            if (rc) return rc;
+            // psets of other ranks that were flagged for the exact fallback: their Taylor tables are needed here
+            cfg.p_base = 0; cfg.n_ctas = 0; cfg.only_missing = 1;
+            rc = launch_traj(ctx, M, pv, pk, cfg, cc, ctx->table.as<double>(), st);
+            if (rc) return rc;
+            cfg.only_missing = 0;
+            launches += 2;
+        }
+        ctx->last_traj_sharded = shard_traj;
         if (prof) cudaEventRecord(ctx->ev[2], st);
         if (totals) {
             // the per-pset sums are already in d_out_pset; finish_kernel only redoes the psets the grid did not resolve
@@ -667,20 +728,26 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         if (use_gemm) {
             const MomentView& mv = f->mom;
             if (prof) cudaEventRecord(ctx->ev[3], st);
-            dim3 grid((unsigned)((Tn + GT_TILE - 1) / GT_TILE), (unsigned)((P + GT_TILE - 1) / GT_TILE));
+            // one linear tile index, pset tiles fastest: the CTAs resident together share a few tree panels of Mt and all of
+            // A (which always fits in L2), so Mt streams from HBM once per launch — with tree tiles fastest a forest whose
+            // moments exceed L2 re-read all of Mt for every row of pset tiles (config 5: 5.7 GB of DRAM reads for a 0.2 GB
+            // operand, profiles/r2_ncu_c5_traj_gemm_summary.csv)
+            const long long n_tt = (Tn + GT_TILE - 1) / GT_TILE, n_pt = (P + GT_TILE - 1) / GT_TILE;
+            if (n_tt * n_pt > 0x7fffffffLL) return fail(ctx, GCDYN_EUNSUPPORTED, "too many (tree, pset) tiles for one launch");
+            dim3 grid((unsigned)(n_tt * n_pt), 1);
             if (!ctx->gemm_attr_set) {
                 CU_TRY(ctx, cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
                 ctx->gemm_attr_set = true;
             }
             // split the column range when the tile grid alone cannot fill the machine (deterministic: fixed order in finish)
-            const long long tiles = (long long)grid.x * grid.y;
+            const long long tiles = n_tt * n_pt;
             // (measured at config-3 size, 256 tiles: 1 → 24.9 µs, 2 → 25.8, 3 → 24.7, 4 → 22.9, 6 → 22.8 with a slower finish)
             const int splits = tiles >= 4LL * ctx->sm_count ? 1 : (tiles >= 2LL * ctx->sm_count ? 2 : 4);
             grid.z = (unsigned)splits;
             CU_TRY(ctx, ctx->partial.ensure((size_t)splits * P * (size_t)Tn * 8));
             {
                 cudaLaunchConfig_t lc = pdl_config(grid, dim3(128), GT_SMEM_BYTES, st);
-                CU_TRY(ctx, cudaLaunchKernelEx(&lc, gemm_kernel, (const double*)ctx->gemm_a.as<double>(), mv, cc.compact_tc ? 0 : 1,
+                CU_TRY(ctx, cudaLaunchKernelEx(&lc, gemm_kernel, (const double*)cc.A, mv, cc.compact_tc ? 0 : 1,
                                                P, (int64_t)Tn, ctx->partial.as<double>()));
             }
             ++launches;
@@ -699,7 +766,7 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
                         CU_TRY(ctx, cudaFuncSetAttribute(degree_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
                     CU_TRY(ctx, ctx->probe.ensure(64));
                     CU_TRY(ctx, cudaMemsetAsync(ctx->probe.p, 0, 8, st));
-                    degree_probe_kernel<<<P, 256, psm, st>>>((const double*)ctx->gemm_a.as<double>(), mv, (const int*)need_sweep,
+                    degree_probe_kernel<<<P, 256, psm, st>>>((const double*)cc.A, mv, (const int*)need_sweep,
                                                              (const int*)pk.pstatus, cc.tol, ctx->probe.as<int>());
                     CU_TRY(ctx, cudaGetLastError());
                     CU_TRY(ctx, cudaMemcpyAsync(f->h_feedback + 1, ctx->probe.p, 8, cudaMemcpyDeviceToHost, st));
@@ -993,8 +1060,10 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
     CU_TRY(ctx, cudaStreamSynchronize(st));
     std::memcpy(out_pset, h_out, (size_t)P * 8);
     if (comm && comm->h_err && *comm->h_err) {
+        const int why = *comm->h_err;
         *comm->h_err = 0;
-        return fail(ctx, GCDYN_ECUDA, "peer all-reduce timed out: a rank did not arrive (its evaluation failed or it is gone)");
+        return fail(ctx, GCDYN_ECUDA, (why & 2) ? "row exchange: the ranks disagree on the grid degree, or a rank could not take the contraction path"
+                                                : "peer all-reduce timed out: a rank did not arrive (its evaluation failed or it is gone)");
     }
     return GCDYN_OK;
 }
@@ -1598,6 +1667,26 @@ int comm_fused_view(gcdyn_comm* c, int n_psets, gcdyn::FusedAllReduce* out) {
     *out = fc;
     return GCDYN_OK;
 }
+int comm_row_exchange(gcdyn_comm* c, unsigned long long seq, int P, long long Jst, long long Juse, int p0, int p1, int D,
+                      const PsetPack& pk, int* need_sweep, cudaStream_t st) {
+    gcdyn_ctx* ctx = c->ctx;
+    gcdyn::RowExchange rx{};
+    const size_t flag_off = 2 * c->rows_half;
+    for (int r = 0; r < c->world; ++r) {
+        char* w = static_cast<char*>(c->rows_peer[r]);
+        rx.rows[r] = reinterpret_cast<double*>(w + (size_t)(seq & 1ULL) * c->rows_half);
+        rx.flag[r] = reinterpret_cast<unsigned long long*>(w + flag_off);
+    }
+    rx.done = reinterpret_cast<int*>(static_cast<char*>(c->rows) + flag_off + (size_t)c->world * 8);
+    rx.rank = c->rank; rx.world = c->world; rx.seq = seq; rx.timeout_ns = c->timeout_ns; rx.err = c->h_err;
+    // enough CTAs to keep the NVLink stores of a several-MB slice in flight; one is plenty for a refusal (P == 0)
+    const long long doubles = (long long)(p1 - p0) * Juse;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(2LL * ctx->sm_count, (doubles / 2 + 255) / 256));
+    gcdyn::row_exchange_kernel<<<grid, 256, 0, st>>>(rx, P, Jst, Juse, p0, p1, D, pk.pstatus, need_sweep, pk.S, pk.perr);
+    CU_TRY(ctx, cudaGetLastError());
+    return GCDYN_OK;
+}
+
 void comm_poison(gcdyn_comm* c, int n_psets, cudaStream_t st) {
     gcdyn::FusedAllReduce fc{};
     if (c->world <= 1 || n_psets < 1 || n_psets > c->cap || comm_fused_view(c, n_psets, &fc) != GCDYN_OK) return;
@@ -1605,6 +1694,60 @@ void comm_poison(gcdyn_comm* c, int n_psets, cudaStream_t st) {
     cudaGetLastError();
 }
 }  // namespace
+
+extern "C" int gcdyn_comm_rows_create(gcdyn_comm* c, int64_t bytes, void* handle_out) {
+    gcdyn_ctx* ctx = c ? c->ctx : nullptr;
+    GUARD_BEGIN
+    if (!c || !handle_out || bytes < 2) return fail(ctx, GCDYN_EINVAL, "bad argument");
+    if (c->rows) return fail(ctx, GCDYN_EINVAL, "this communicator already has a row window");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t half = (((size_t)bytes + 1) / 2 + 255) & ~(size_t)255;
+    const size_t total = 2 * half + ((size_t)c->world + 2) * 8;
+    cudaError_t e = cudaMalloc(&c->rows, total);
+    if (e == cudaSuccess) e = cudaMemset(static_cast<char*>(c->rows) + 2 * half, 0, total - 2 * half);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h{};
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->rows);
+    if (e != cudaSuccess) {
+        if (c->rows) cudaFree(c->rows);
+        c->rows = nullptr;
+        return fail(ctx, e == cudaErrorMemoryAllocation ? GCDYN_ENOMEM : GCDYN_ECUDA, cudaGetErrorString(e));
+    }
+    std::memcpy(handle_out, &h, 64);
+    c->rows_half = half;
+    c->rows_peer[c->rank] = c->rows;
+    if (const char* ev = std::getenv("GCDYN_TRAJ_SHARD_MIN_PSETS")) c->shard_min_psets = std::max(1, std::atoi(ev));
+    if (const char* ev = std::getenv("GCDYN_ROW_PUSH")) c->push_from_traj = std::strcmp(ev, "kernel") != 0;
+    if (c->world == 1) c->rows_connected = true;
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+extern "C" int gcdyn_comm_rows_connect(gcdyn_comm* c, const void* handles) {
+    gcdyn_ctx* ctx = c ? c->ctx : nullptr;
+    GUARD_BEGIN
+    if (!c || !handles) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    if (!c->rows) return fail(ctx, GCDYN_EINVAL, "gcdyn_comm_rows_create has not been called");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    for (int r = 0; r < c->world; ++r) {
+        if (r == c->rank || c->rows_peer[r]) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char*>(handles) + (size_t)r * 64, 64);
+        CU_TRY(ctx, cudaIpcOpenMemHandle(&c->rows_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->rows_connected = true;
+    return GCDYN_OK;
+    GUARD_END(ctx)
+}
+
+extern "C" int gcdyn_comm_error(gcdyn_comm* c) {
+    if (!c || !c->h_err) return 0;
+    const int e = *c->h_err;
+    *c->h_err = 0;
+    return e;
+}
+
+extern "C" int gcdyn_last_traj_sharded(gcdyn_ctx* ctx) { return ctx && ctx->last_traj_sharded ? 1 : 0; }
 
 extern "C" int gcdyn_comm_allreduce(gcdyn_comm* c, double* d_inout, int32_t n_psets, void* stream) {
     gcdyn_ctx* ctx = c ? c->ctx : nullptr;
@@ -1634,6 +1777,9 @@ extern "C" void gcdyn_comm_destroy(gcdyn_comm* c) {
     cudaDeviceSynchronize();
     for (int r = 0; r < c->world; ++r)
         if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    for (int r = 0; r < c->world; ++r)
+        if (r != c->rank && c->rows_peer[r]) cudaIpcCloseMemHandle(c->rows_peer[r]);
+    if (c->rows) cudaFree(c->rows);
     if (c->window) cudaFree(c->window);
     if (c->h_err) cudaFreeHost(c->h_err);
     cudaSetDevice(prev);

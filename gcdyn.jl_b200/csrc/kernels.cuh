@@ -88,6 +88,11 @@ struct TrajCfg {
     int S_cap;                   // table capacity in cells (adaptive mode never exceeds it)
     int grid_doubles;            // doubles reserved per pset for [τ_s | 1/h_s] ahead of the rows (even)
     long long tab_stride;        // doubles per pset in the table (grid block + rows)
+    // trajectory sharding (trees AND parameter sets split over ranks): this launch covers psets p_base + blockIdx.x;
+    // only_missing: a second launch over all psets in which a CTA works only for a pset OUTSIDE [own_lo, own_hi) that its
+    // owner flagged for the exact fallback — the fallback sums need the Taylor table, which is not exchanged
+    int p_base, only_missing, own_lo, own_hi;
+    int n_ctas;                  // grid size of this launch (0: one CTA per pset of the batch)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -191,6 +196,16 @@ struct MomentView {
     const double* colsum;  // [Jst] forest-level column sums
 };
 
+// Trajectory sharding: the CTA that finished a parameter set's coefficient row stores it straight into the row windows of
+// the other ranks (P2P stores over NVLink, fenced at system scope before the CTA retires); row_exchange_kernel
+// (peer_allreduce.cuh) then only publishes the metadata and the flags.  n == 0: off.
+constexpr int ROW_PUSH_MAX = 15;
+struct RowPush {
+    int n;                       // peers to push to
+    int w2;                      // double2 per row that the contraction uses
+    double* dst[ROW_PUSH_MAX];   // the peers' coefficient buffers (same layout as ChebCfg::A)
+};
+
 struct ChebCfg {
     double T;
     double tol;            // accepted size of the interpolant's last three Chebyshev coefficients (absolute, on F)
@@ -208,6 +223,7 @@ struct ChebCfg {
     // when nothing is left to combine (one rank, pset resolved), decides accept/reject right after its sum
     int mh_on, mh_sharded;
     MhView mh;
+    RowPush push;          // trajectory sharding: send the finished row to the peers
 };
 
 // Cell containing τ on a pset's (non-uniform) grid: largest s < S with grid[s] ≤ τ.
@@ -626,8 +642,9 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
     extern __shared__ __align__(16) double smem[];
     constexpr int NPROD = 32 * NPW, NCONS = TRAJ_THREADS - NPROD;   // integrating / consumer threads
     static_assert(NPW == 1 || (NPW == 2 && KPL == 1), "two integrating warps own one type per lane");
-    const int p = blockIdx.x;
+    const int p = cfg.p_base + blockIdx.x;
     const int K = pv.K;
+    if (cfg.only_missing && ((p >= cfg.own_lo && p < cfg.own_hi) || !cc.need_sweep[p] || (pk.pstatus[p] & ST_SOLVER))) return;
 #ifdef GCDYN_TRAJ_TRACE
     __shared__ long long g_trace[16];
 #endif
@@ -1017,6 +1034,28 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
     __syncthreads();                                    // node values, status of this pset are complete and visible
     TRACE_STAMP(4);
     nodal_finish(cc, p, ts, &s_flag, s_pst, mh_it);
+    if (cc.push.n > 0) {                                // CTA-uniform
+        __syncthreads();                                // every column of the row has been written
+        const double2* src = reinterpret_cast<const double2*>(cc.A + (size_t)p * cc.mv.Jst);
+        const size_t at = (size_t)p * (size_t)(cc.mv.Jst / 2);
+        for (int i0 = threadIdx.x; i0 < cc.push.w2; i0 += 4 * TRAJ_THREADS) {
+            double2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * TRAJ_THREADS;
+                if (i < cc.push.w2) v[u] = __ldcg(src + i);
+            }
+            for (int r = 0; r < cc.push.n; ++r) {
+                double2* dst = reinterpret_cast<double2*>(cc.push.dst[r]) + at;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * TRAJ_THREADS;
+                    if (i < cc.push.w2) dst[i] = v[u];
+                }
+            }
+        }
+        __threadfence_system();                         // performed at the peers before this CTA counts as finished
+    }
 #ifdef GCDYN_TRAJ_TRACE
     __syncthreads();
     TRACE_STAMP(5);

@@ -134,4 +134,92 @@ __global__ void __launch_bounds__(256) peer_poison_kernel(PeerView pv, int P) {
     if (threadIdx.x == 0) *pv.seq_dev = seq;
 }
 
+// ---- trajectory sharding: all-gather of the coefficient rows -------------------------------------------------------
+// The per-pset work (trajectory integration + node values, traj_kernel) does not depend on the trees, so with the trees
+// sharded over ranks every rank would repeat it for all P parameter sets.  With a ROW WINDOW (gcdyn_comm_rows_create)
+// each rank integrates only its slice [p0, p1) of the parameter sets, writes those coefficient rows A[p][0..Jst) into its
+// own window and this kernel pushes them — plus 32 bytes of per-pset metadata (status, fallback flag, cell count, error
+// indicator) — into every peer's window with 16-byte P2P stores; the last CTA publishes {sequence, grid degree} in every
+// peer's flag word, waits (bounded) for the peers' flags and copies the peers' metadata into the local arrays.  When the
+// kernel completes, the local window holds all P rows and the contraction runs as usual.  Two halves alternate per call:
+// a rank that is one call ahead (it cannot be further: the LL all-reduce of the call in between is a barrier) writes the
+// other half.  The flag carries the grid degree: ranks that disagree (or a rank that could not take the contraction path,
+// degree 0) raise `*err = 2` instead of contracting rows of the wrong shape.
+struct RowMeta { int pstatus, need_sweep, S, D; double perr, pad; };
+static_assert(sizeof(RowMeta) == 32, "RowMeta is two 16-byte stores");
+
+struct RowExchange {
+    double* rows[PEER_MAX_WORLD];            // rank r's window, the half of this call: [P*Jst doubles | RowMeta[P]]
+    unsigned long long* flag[PEER_MAX_WORLD];// rank r's flag words [world]
+    int* done;                               // local CTA counter (reset by the last CTA)
+    int rank, world;
+    unsigned long long seq, timeout_ns;
+    int* err;
+};
+
+__global__ void __launch_bounds__(256) row_exchange_kernel(RowExchange rx, int P, long long Jst, long long Juse, int p0, int p1, int D,
+                                                           int* __restrict__ pstatus, int* __restrict__ need_sweep,
+                                                           int* __restrict__ S, double* __restrict__ perr) {
+    __shared__ int s_last, s_bad;
+    double* mine = rx.rows[rx.rank];
+    RowMeta* meta_mine = reinterpret_cast<RowMeta*>(mine + (size_t)P * Jst);
+    // this rank's metadata first (its own copy too: the import below reads every pset from the window)
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int p = p0 + tid; p < p1; p += nth) {
+        RowMeta m;
+        m.pstatus = pstatus[p]; m.need_sweep = need_sweep[p]; m.S = S[p]; m.D = D; m.perr = perr[p]; m.pad = 0.0;
+        for (int r = 0; r < rx.world; ++r) {
+            RowMeta* dst = reinterpret_cast<RowMeta*>(rx.rows[r] + (size_t)P * Jst) + p;
+            reinterpret_cast<int4*>(dst)[0] = reinterpret_cast<const int4*>(&m)[0];
+            reinterpret_cast<int4*>(dst)[1] = reinterpret_cast<const int4*>(&m)[1];
+        }
+    }
+    // the rows of the slice, the first Juse columns of each (shared Γ: the K² type-change columns are not used): one load,
+    // world − 1 peer stores (Jst and Juse are multiples of 4 doubles: 16-byte aligned)
+    const unsigned w2 = (unsigned)(Juse / 2);                                     // double2 per row
+    const long long n2 = (long long)(p1 - p0) * w2;
+    const double2* src = reinterpret_cast<const double2*>(mine);
+    for (long long i = tid; i < n2; i += nth) {
+        const long long row = i / w2;
+        const long long at = ((long long)p0 + row) * (Jst / 2) + (i - row * w2);
+        const double2 v = __ldcg(src + at);
+        for (int r = 0; r < rx.world; ++r)
+            if (r != rx.rank) reinterpret_cast<double2*>(rx.rows[r])[at] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(rx.done, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) { *rx.done = 0; s_bad = 0; }
+    __threadfence_system();
+    __syncthreads();
+    const unsigned long long word = (rx.seq << 8) | (unsigned long long)(D & 0xff);
+    if (threadIdx.x < rx.world) st_release_sys(rx.flag[threadIdx.x] + rx.rank, word);
+    if (threadIdx.x < rx.world) {
+        const unsigned long long* f = rx.flag[rx.rank] + threadIdx.x;
+        const unsigned long long t0 = global_ns();
+        unsigned long long w;
+        while (((w = ld_acquire_sys(f)) >> 8) < rx.seq) {
+            __nanosleep(100);
+            if (global_ns() - t0 > rx.timeout_ns) { atomicOr(&s_bad, 1); break; }
+        }
+        if ((w >> 8) >= rx.seq && (int)(w & 0xff) != (D & 0xff)) atomicOr(&s_bad, 2);
+    }
+    __syncthreads();
+    if (s_bad) {
+        if (threadIdx.x == 0 && rx.err) *rx.err = s_bad;
+        // nothing of the peers can be trusted: every pset they own is marked as a solver failure (−Inf/NaN downstream)
+        for (int p = threadIdx.x; p < P; p += blockDim.x)
+            if (p < p0 || p >= p1) { pstatus[p] = 2 /* ST_SOLVER */; need_sweep[p] = 0; S[p] = 0; perr[p] = __longlong_as_double(0x7ff8000000000000LL); }
+        return;
+    }
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        if (p >= p0 && p < p1) continue;
+        const int4 a = __ldcg(reinterpret_cast<const int4*>(meta_mine + p));
+        const double2 b = __ldcg(reinterpret_cast<const double2*>(meta_mine + p) + 1);
+        pstatus[p] = a.x; need_sweep[p] = a.y; S[p] = a.z; perr[p] = b.x;
+    }
+}
+
 }  // namespace gcdyn

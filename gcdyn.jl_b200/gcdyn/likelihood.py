@@ -132,6 +132,10 @@ def _lib():
         "gcdyn_last_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "gcdyn_comm_create": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, vp, C.POINTER(vp)]),
         "gcdyn_comm_connect": (C.c_int, [vp, vp]),
+        "gcdyn_comm_rows_create": (C.c_int, [vp, C.c_int64, vp]),
+        "gcdyn_comm_rows_connect": (C.c_int, [vp, vp]),
+        "gcdyn_comm_error": (C.c_int, [vp]),
+        "gcdyn_last_traj_sharded": (C.c_int, [vp]),
         "gcdyn_comm_allreduce": (C.c_int, [vp, vp, C.c_int32, vp]),
         "gcdyn_comm_destroy": (None, [vp]),
         "gcdyn_loglik_batch_sharded": (C.c_int, [vp, vp, C.POINTER(Params), C.c_double, C.c_int, C.POINTER(Opts), vp,

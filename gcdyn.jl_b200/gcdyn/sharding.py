@@ -85,7 +85,10 @@ class PeerAllReduce:
     GPU; the 64-byte CUDA IPC handles are exchanged once through `torch.distributed` (any backend).  Every
     rank ends with bit-identical sums.  Collective: every rank calls `allreduce` the same number of times."""
 
-    def __init__(self, ctx, max_psets, group=None):
+    def __init__(self, ctx, max_psets, group=None, row_bytes=0):
+        """`row_bytes` > 0 also creates the ROW WINDOW of the trajectory sharding (`gcdyn_comm_rows_create`): sharded ODE
+        evaluations of >= 512 parameter sets then integrate only this rank's slice of the sets and all-gather the
+        coefficient rows over peer memory.  `row_window_bytes(P, K, degree)` sizes it."""
         import ctypes as C
         import torch.distributed as dist
         from .likelihood import _lib, _check
@@ -102,6 +105,29 @@ class PeerAllReduce:
             blob = C.create_string_buffer(b"".join(gathered), 64 * self.world)
             _check(self._lib.gcdyn_comm_connect(self._h, blob), ctx._h)
             dist.barrier(group)        # every window is mapped everywhere before the first store
+        if row_bytes:
+            rh = C.create_string_buffer(64)
+            _check(self._lib.gcdyn_comm_rows_create(self._h, int(row_bytes), rh), ctx._h)
+            if self.world > 1:
+                gathered = [None] * self.world
+                dist.all_gather_object(gathered, rh.raw, group=group)
+                blob = C.create_string_buffer(b"".join(gathered), 64 * self.world)
+                _check(self._lib.gcdyn_comm_rows_connect(self._h, blob), ctx._h)
+                dist.barrier(group)
+
+    @staticmethod
+    def row_window_bytes(n_psets, n_types, degree=128):
+        """Bytes `row_bytes` needs for batches of `n_psets` on a nodal grid of `degree` (128 = the largest the library
+        uses): two halves of P rows of Jst = 2K+4 + (degree+1)·K + K² doubles (rounded up to 4) plus 32 bytes per set."""
+        K = int(n_types)
+        j1 = (2 * K + 4 + (int(degree) + 1) * K + 3) & ~3
+        jst = (j1 + K * K + 3) & ~3
+        return 2 * int(n_psets) * (jst * 8 + 32)
+
+    def error(self):
+        """`gcdyn_comm_error`: the communicator's error word, cleared on read (call after synchronising a resident
+        evaluation): 0 none, 1 a peer did not arrive in time, 2 the ranks disagreed on the grid degree."""
+        return int(self._lib.gcdyn_comm_error(self._h))
 
     def allreduce(self, d_inout, n_psets, stream=0):
         """Enqueue on `stream` (raw cudaStream_t, 0 = the context's stream): `d_inout` (raw device address of

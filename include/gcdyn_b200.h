@@ -28,8 +28,9 @@
 extern "C" {
 #endif
 
-#define GCDYN_B200_VERSION 120  /* major*100 + minor; 1.10 adds gcdyn_comm_*, gcdyn_loglik_batch_sharded, gcdyn_mh_*;
-                                   1.20 adds GCDYN_FLAG_TOTALS, gcdyn_last_cells, gcdyn_loglik_batch_resident_sharded */
+#define GCDYN_B200_VERSION 130  /* major*100 + minor; 1.10 adds gcdyn_comm_*, gcdyn_loglik_batch_sharded, gcdyn_mh_*;
+                                   1.20 adds GCDYN_FLAG_TOTALS, gcdyn_last_cells, gcdyn_loglik_batch_resident_sharded,
+                                   gcdyn_loglik_grad_batch; 1.30 adds gcdyn_comm_rows_*, gcdyn_comm_error, gcdyn_last_traj_sharded */
 
 /* return codes */
 #define GCDYN_OK            0
@@ -255,6 +256,24 @@ int  gcdyn_loglik_batch_sharded(gcdyn_ctx* ctx, const gcdyn_forest* forest, cons
 int  gcdyn_loglik_batch_resident_sharded(gcdyn_ctx* ctx, const gcdyn_forest* forest, const gcdyn_dparams* dparams,
                                          double present_time, int method, const gcdyn_opts* opts, gcdyn_comm* comm,
                                          double* d_out_pset, double* d_out_tree_pset, int32_t* d_status, void* stream);
+/* Trajectory sharding (strong scaling of the per-parameter-set work).  The trajectory integration and the coefficient
+ * rows it produces do not depend on the trees, so with the trees sharded every rank would repeat them for all P sets.
+ * A communicator that owns a ROW WINDOW splits them instead: on a sharded ODE evaluation of at least 512 parameter sets
+ * (GCDYN_TRAJ_SHARD_MIN_PSETS overrides) without GCDYN_FLAG_TOTALS, rank r integrates the sets [P*r/world, P*(r+1)/world),
+ * the rows are all-gathered by one kernel of P2P stores into every peer's window, and each rank contracts all P rows with
+ * its own trees.  Values are bit-identical to the unsplit evaluation.
+ *   gcdyn_comm_rows_create   allocates the window (`bytes` >= 2 * P * (Jst*8 + 32), Jst = row length at the calibrated
+ *                            degree; a call whose rows do not fit fails with GCDYN_ENOMEM and names the size) and returns
+ *                            its 64-byte CUDA IPC handle;
+ *   gcdyn_comm_rows_connect  takes the `world` handles in rank order.
+ * Every rank must hold the same parameter sets and make the same calls.  gcdyn_comm_error returns and clears the
+ * communicator's error word after the caller synchronised a resident call: 0 none, 1 a peer did not arrive in time,
+ * 2 the ranks disagreed on the grid degree (or a peer could not take the contraction path) - the sums are NaN / -Inf.
+ * gcdyn_last_traj_sharded: 1 when the last evaluation on `ctx` integrated only this rank's slice. */
+int  gcdyn_comm_rows_create(gcdyn_comm* comm, int64_t bytes, void* handle_out);
+int  gcdyn_comm_rows_connect(gcdyn_comm* comm, const void* handles);
+int  gcdyn_comm_error(gcdyn_comm* comm);
+int  gcdyn_last_traj_sharded(gcdyn_ctx* ctx);
 void gcdyn_comm_destroy(gcdyn_comm* comm);
 
 /* ---- device-resident random-walk Metropolis (BASELINE config 4) --------------------------

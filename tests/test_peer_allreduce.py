@@ -102,6 +102,58 @@ sys.stdout.write("rank%d-ok\n" % rank)
 os._exit(0)                                          # the windows are out of step now: skip the orderly teardown
 """
 
+# Trajectory sharding: with a row window every rank integrates a slice of the parameter sets and the coefficient rows are
+# all-gathered over peer memory; values must equal the unsplit evaluation, including a parameter set that the calibrated grid
+# does not resolve (its exact fallback needs the Taylor table on EVERY rank: the second, "missing" trajectory launch).
+ROWS_WORKER = r"""
+import os, sys
+os.environ["GCDYN_TRAJ_SHARD_MIN_PSETS"] = "8"
+sys.path[:0] = [os.path.join("@ROOT@", "gcdyn.jl_b200")]
+import numpy as np, torch, torch.distributed as dist
+import gcdyn
+from gcdyn.sharding import PeerAllReduce
+from gcdyn.likelihood import evaluate, pack_params, _lib
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("gloo")
+ctx = gcdyn.Context(local)
+P, K = 27, 5                                         # an odd count: uneven slices
+peer = PeerAllReduce(ctx, P, row_bytes=PeerAllReduce.row_window_bytes(P, K))
+plain = PeerAllReduce(ctx, P)                        # no row window: every rank integrates everything
+ts = np.linspace(-1.0, 1.0, K)
+mk = lambda i, ys=2.0: gcdyn.SigmoidalBranchingProcess(1.2, 0.0, ys + 0.02 * i, 0.5, 1.0, 1.0, 0.6, 0.2, ts)
+models = [mk(i) for i in range(P)]
+trees = gcdyn.rand_tree(models[0], 2.5, ts[2], 40, rng=np.random.default_rng(3))     # same forest on every rank
+whole = gcdyn.Forest(trees, ts, 2.5, ctx=ctx)
+shard = gcdyn.Forest(trees[rank::world], ts, 2.5, ctx=ctx)
+shard2 = gcdyn.Forest(trees[rank::world], ts, 2.5, ctx=ctx)
+def check(ms, expect_fallback):
+    full, _, _ = evaluate(whole, pack_params(ms), 2.5)
+    for _ in range(3):                               # both halves of the row window
+        got, tp, st = evaluate(shard, pack_params(ms), 2.5, comm=peer, per_tree=True)
+        assert _lib().gcdyn_last_traj_sharded(ctx._h) == (1 if world > 1 else 0)
+        d = ctx.last_diag(P)
+        assert (d["cells"] > 0).all(), d["cells"]    # the metadata of the other ranks' parameter sets arrived
+        assert (ctx.last_cheb()["n_fallback"] > 0) == expect_fallback, ctx.last_cheb()
+        assert not st.any() and np.max(np.abs(got - full) / np.abs(full)) <= 1e-12, (rank, got, full)
+        ref, tpr, _ = evaluate(shard2, pack_params(ms), 2.5, comm=plain, per_tree=True)
+        assert _lib().gcdyn_last_traj_sharded(ctx._h) == 0
+        assert np.array_equal(tp, tpr) and np.array_equal(got, ref)       # bit-identical to the unsplit sharded evaluation
+        gathered = [None] * world
+        dist.all_gather_object(gathered, got.tobytes())
+        assert all(g == gathered[0] for g in gathered)
+check(models, False)
+# two much faster parameter sets, one in each rank's slice: the grid calibrated above does not resolve them
+stiff = list(models)
+stiff[2] = mk(2, 12.0)
+stiff[P - 3] = mk(P - 3, 12.5)
+check(stiff, True)
+assert peer.error() == 0
+peer.close(); plain.close()
+dist.barrier()
+sys.stdout.write("rank%d-ok\n" % rank)
+"""
+
 
 def _run(world, worker=None):
     import tempfile
@@ -138,3 +190,11 @@ def test_peer_allreduce_wait_is_bounded():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     _run(2, TIMEOUT_WORKER)
+
+
+@pytest.mark.gpu
+def test_trajectory_sharding_matches_the_unsplit_evaluation():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run(2, ROWS_WORKER)

@@ -49,7 +49,9 @@ flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
 peer = None
 if world > 1:
     from gcdyn.sharding import PeerAllReduce
-    peer = PeerAllReduce(ctx, P)
+    # the row window of the trajectory sharding (C5_TRAJ_SHARD=0: every rank integrates all P parameter sets)
+    rows = PeerAllReduce.row_window_bytes(P, K) if os.environ.get("C5_TRAJ_SHARD", "1") != "0" else 0
+    peer = PeerAllReduce(ctx, P, row_bytes=rows)
 
 
 def step():
@@ -74,8 +76,21 @@ if world > 1:                                   # device time of the slowest ran
     t = torch.tensor([ms], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+from gcdyn.likelihood import _lib
+traj_sharded = bool(_lib().gcdyn_last_traj_sharded(ctx._h))
 ctx.set_profiling(True)
+acc_sh = {}
+if world > 1:                                   # the sharded step's own breakdown ("trajectory" includes the row exchange)
+    for _ in range(5):
+        flush.zero_()
+        step()
+        for k, v in ctx.last_kernel_ms().items():
+            acc_sh[k] = acc_sh.get(k, 0.0) + v / 5
+    sync_all()
+    assert peer.error() == 0
 acc = {}
+evaluate_resident(forest, dpar, T, out.data_ptr(), out_tree.data_ptr(), 0, stream.cuda_stream)   # (allocates its own row buffer)
+sync_all()
 for _ in range(5):
     flush.zero_()
     evaluate_resident(forest, dpar, T, out.data_ptr(), out_tree.data_ptr(), 0, stream.cuda_stream)
@@ -92,15 +107,24 @@ par = workloads.par_dict(models[:1])
 sub = subset_flat(flat, np.arange(min(Tn, 500)))
 want = oracle.loglik_flat_shared(sub, par, 0, T)
 rel_tree = float(np.max(np.abs(host[0, :len(want)] - want) / np.abs(want)))
+# ... and a parameter set of the LAST rank's slice, from the sharded step (its coefficient row came over NVLink)
+step(); sync_all()
+host_sh = out_tree.cpu().numpy().reshape(P, Tn)
+want_last = oracle.loglik_flat_shared(subset_flat(flat, np.arange(min(Tn, 100))), workloads.par_dict(models[P - 1:]), 0, T)
+rel_last = float(np.max(np.abs(host_sh[P - 1, :len(want_last)] - want_last) / np.abs(want_last)))
+same_as_unsharded = bool(np.array_equal(host_sh, host))
 rel_sum = float(abs(host[0, :len(want)].sum() - want.sum()) / abs(want.sum()))
 if rank == 0:
   print(json.dumps({"config": f"C5: {Tn} trees per GPU ({flat.n_nodes} nodes, {forest.info()['n_items']} items), K={K}, P={P}, T={T}, "
                             f"{world} GPU(s), {mode} scaling, {Tn * world} trees in total",
                   "sim_seconds": t_sim, "ms_per_step": ms, "tree_pset_evals_per_s": Tn * world * P / (ms * 1e-3),
+                  "trajectory_sharded": traj_sharded, "kernel_ms_sharded_step": acc_sh or None,
                   "kernel_ms": acc, "chebyshev": cheb, "taylor_cells_max": diag["steps"],
                   "gemm": {"J": J, "gflop": gemm_flop / 1e9, "tflops": gemm_flop / (acc["gemm"] * 1e-3) / 1e12,
                            "frac_of_measured_dfma_peak": gemm_flop / (acc["gemm"] * 1e-3) / 1e12 / peak, "dfma_peak_tflops": peak},
-                  "parity_first_500_trees_pset0": {"max_rel_err_tree": rel_tree, "rel_err_sum": rel_sum}}))
+                  "parity_first_500_trees_pset0": {"max_rel_err_tree": rel_tree, "rel_err_sum": rel_sum},
+                  "parity_first_100_trees_last_pset_sharded_step": rel_last,
+                  "sharded_step_per_tree_values_bit_identical_to_unsharded": same_as_unsharded}))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
