@@ -4,8 +4,12 @@
     python bench.py --gpus N --steps K --warmup W            # this build, one rank per GPU (torchrun for N>1)
     python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm: the reference algorithm on host cores
 
-Workload at every N: BASELINE.json config 3 — 1000 trees per GPU × 256 parameter sets, K = 20 types
-(weak scaling: trees are sharded, the [P] partial sums are combined by ONE all-reduce).  A step is one
+Default workload at every N: BASELINE.json config 3 — 1000 trees per GPU × 256 parameter sets, K = 20 types
+(weak scaling: trees are sharded, the [P] partial sums are combined by ONE all-reduce fused into the last kernel).
+`--workload C5` = config 5 at scale (10^4 trees of ~10^3 nodes from the native simulator × 1024 parameter sets, K = 50),
+`--workload C4` = config 4 (64 device-resident Metropolis chains on the config-3 forest; a step = 100 iterations);
+`--scaling strong` keeps the TOTAL tree count fixed and splits it over the ranks (with >= 512 parameter sets the
+trajectories are sharded too: each rank integrates P/N parameter sets and pushes the coefficient rows to its peers).  A step is one
 batched evaluation of all P parameter sets against the rank's trees, producing the per-(tree,pset)
 matrix and the [P] sums.  `value` = (tree, pset) evaluations per second over the whole job, with the
 forest and the parameters resident in HBM; `e2e` is the same through the host-buffer C-ABI call
@@ -40,7 +44,9 @@ UNIT = "(tree,pset) evals/s"
 def config_dict(name, trees_per_gpu, psets, n_gpus, extra=None):
     import workloads
     c = workloads.CONFIGS[name]
-    d = {"workload": f"BASELINE config 3: {trees_per_gpu} trees/GPU x {psets} parameter sets, K={c['K']} "
+    what = {"C3": "BASELINE config 3", "C4": "BASELINE config 4 (Metropolis chains = parameter sets, config-3 forest)",
+            "C5": "BASELINE config 5 (trees of 500..2000 nodes, native simulator)"}.get(name, name)
+    d = {"workload": f"{what}: {trees_per_gpu} trees/GPU x {psets} parameter sets, K={c['K']} "
                      f"sigmoid birth response, rho=0.5, sigma=0.1, present_time={c['T']}, simulator seed {c['seed']}",
          "trees_per_gpu": trees_per_gpu, "trees_total": trees_per_gpu * n_gpus, "psets": psets, "K": c["K"],
          "present_time": c["T"], "parallelism": f"trees sharded over {n_gpus} GPU(s), one all-reduce of [P] doubles"
@@ -165,7 +171,8 @@ def run_reference(args):
         return
     import workloads
     c = workloads.CONFIGS[WORKLOAD]
-    flat = workloads.flat_forest(WORKLOAD, 0, args.trees)
+    # (config 5: the CPU arm only ever touches a bounded sample, so it only generates one)
+    flat = workloads.flat_forest(WORKLOAD, 0, min(args.trees, 256) if c.get("native") else args.trees)
     par = workloads.par_dict(workloads.jittered_models(WORKLOAD, args.psets))
     cores = host_threads()
     # bounded sample per step: sized from a probe so that (warmup + steps) stay within a few minutes
@@ -228,6 +235,9 @@ def run_gpu(args):
             os.close(saved)
     c = workloads.CONFIGS[WORKLOAD]
     T, K, P, Tn = c["T"], c["K"], args.psets, args.trees
+    if args.scaling == "strong":
+        Tn = args.trees // world                         # --trees is the TOTAL under strong scaling
+    native = bool(c.get("native"))
 
     # ---- inputs: this rank's shard of the forest, the replicated parameter batch
     flat = workloads.flat_forest(WORKLOAD, rank * Tn, Tn)
@@ -261,7 +271,8 @@ def run_gpu(args):
         from gcdyn.sharding import PeerAllReduce
         ok = 1
         try:
-            peer = PeerAllReduce(ctx, P)
+            # >= 512 parameter sets: a row window, so that every rank integrates only its slice of them
+            peer = PeerAllReduce(ctx, P, row_bytes=PeerAllReduce.row_window_bytes(P, K) if P >= 512 else 0)
         except Exception as e:          # noqa: BLE001 - any failure on any rank -> everybody uses NCCL
             print(f"[bench] rank {rank}: peer all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
             ok = 0
@@ -346,6 +357,20 @@ def run_gpu(args):
                   " (host buffers; forest handle created once per dataset, as a sampler would)"}
     if world > 1:
         assert np.allclose(o, result, rtol=1e-12, atol=0)
+    # the fused all-reduce against a library collective over the ranks' own per-tree values
+    allreduce_check = None
+    traj_sharded = False
+    if world > 1:
+        from gcdyn.likelihood import _lib
+        step_resident()
+        torch.cuda.synchronize()
+        traj_sharded = bool(_lib().gcdyn_last_traj_sharded(ctx._h))
+        mine = out_tree.view(P, Tn).sum(dim=1)
+        dist.all_reduce(mine)
+        got = out.cpu().numpy()
+        allreduce_check = float(np.max(np.abs(got - mine.cpu().numpy()) / np.abs(got)))
+        assert allreduce_check <= 1e-11, allreduce_check
+        assert peer is None or peer.error() == 0
 
     if rank != 0:
         if world > 1:
@@ -396,7 +421,7 @@ def run_gpu(args):
     gemm_bytes = (Tn * J + P * J + Tn * P) * 8.0
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json" if WORKLOAD == "C3" else f"r2_dram_traffic_{WORKLOAD}.json")))
         traffic = tr.get(f"{dom}_kernel", {}).get("dram_bytes_per_launch")
     except Exception:
         tr = {}
@@ -423,11 +448,16 @@ def run_gpu(args):
     host_tree = out_tree.cpu().numpy().reshape(P, Tn)
     check = sorted(set(int(round(x)) for x in np.linspace(0, P - 1, min(16, P))))
     rels = []
+    n_par = min(Tn, 64) if native else Tn            # config 5: ~10^3 nodes per tree, the oracle takes ~0.1 s per (tree, pset)
+    from gcdyn.sharding import subset_flat
+    flat_par = subset_flat(flat, np.arange(n_par)) if n_par < Tn else flat
     for p in check:
-        want = oracle.loglik_flat_shared(flat, par, p, T)
-        rels.append(abs(host_tree[p].sum() - want.sum()) / abs(want.sum()))
-    parity = {"psets_checked": len(check), "psets": check, "max_rel_err_sum": float(max(rels)), "gate": 1e-8}
-    if world > 1:
+        want = oracle.loglik_flat_shared(flat_par, par, p, T)
+        rels.append(abs(host_tree[p, :n_par].sum() - want.sum()) / abs(want.sum()))
+    parity = {"psets_checked": len(check), "psets": check, "trees_checked": n_par, "max_rel_err_sum": float(max(rels)), "gate": 1e-8}
+    if allreduce_check is not None:
+        parity["fused_allreduce_vs_nccl_of_per_tree_values"] = allreduce_check
+    if world > 1 and not native:
         chk = check[:: max(1, len(check) // 4)][:4]
         tot = {p: 0.0 for p in chk}
         for r in range(world):
@@ -442,12 +472,12 @@ def run_gpu(args):
     cpu = cpu_baseline(flat, par, T) if world == 1 else None
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(WORKLOAD, Tn, P, world, {
                 "nodes_per_gpu": info["n_nodes"], "lookup_items_per_gpu": n_items, "taylor_steps": S,
                 "taylor_order": M, "max_err_indicator": float(np.max(diag["err_indicator"])),
-                "allreduce": allreduce_kind}),
+                "allreduce": allreduce_kind, "trajectories_sharded": traj_sharded}),
             "clocks": clocks, "e2e": e2e, "cold": cold,
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "parity": parity}
@@ -459,17 +489,132 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_mh(args):
+    """Config 4: C device-resident random-walk Metropolis chains (gcdyn_mh_*) on the config-3 forest.  A step is
+    MH_ITERS iterations of all chains = one gcdyn_mh_run call (it synchronises; the library owns its stream, so the step is
+    timed by the host clock around the call — >= 100 iterations per call keep the ~20 us call overhead below 1 %).
+    `value`: chains keep their history on the device (no per-iteration output); `e2e`: the call that also returns every
+    iteration's parameters and log-likelihoods to host memory."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import gcdyn
+    import workloads
+    import oracle
+    from gcdyn.likelihood import MhDesc, _lib, _check, _ptr, _p_f64, _p_i64
+    from gcdyn.mcmc import theta_of, model_of
+    MH_ITERS = 100
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("gloo")
+    c = workloads.CONFIGS["C4"]
+    T, K, n_chains = c["T"], c["K"], args.psets
+    Tn = args.trees // world if args.scaling == "strong" else args.trees
+    flat = workloads.flat_forest("C4", rank * Tn, Tn)
+    base, _ = workloads.base_model("C3")
+    ctx = gcdyn.Context(local)
+    forest = gcdyn.Forest(flat, None, T, ctx=ctx)
+    comm = None
+    if world > 1:
+        from gcdyn.sharding import PeerAllReduce
+        comm = PeerAllReduce(ctx, n_chains)
+    lib = _lib()
+    th = theta_of(base)
+    th0 = np.ascontiguousarray(th + 0.05 * np.random.default_rng(4).standard_normal((n_chains, 6)))
+    lo, up = np.ascontiguousarray(th - 1.5), np.ascontiguousarray(th + 1.5)
+    ts = np.ascontiguousarray(base.type_space, dtype=np.float64)
+    gam = np.ascontiguousarray(np.asarray(base.Γ, dtype=np.float64).ravel(order="F"))
+    desc = MhDesc(n_chains, len(ts), _ptr(ts, _p_f64), _ptr(gam, _p_f64), float(base.ρ), float(base.σ), _ptr(th0, _p_f64),
+                  _ptr(lo, _p_f64), _ptr(up, _p_f64), 0.02, 4)
+    h = C.c_void_p()
+    _check(lib.gcdyn_mh_create(ctx._h, forest._h, C.byref(desc), float(T), comm._h if comm else None, C.byref(h)), ctx._h)
+    run = lambda n, a=None, b=None: _check(lib.gcdyn_mh_run(h, int(n), a, b), ctx._h)
+    run(0)
+    for _ in range(max(args.warmup, 3)):
+        run(MH_ITERS)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(MH_ITERS)
+    dt = time.perf_counter() - t0
+    chain = np.empty((MH_ITERS, n_chains, 6)); lls = np.empty((MH_ITERS, n_chains))
+    for _ in range(3):
+        run(MH_ITERS, _ptr(chain, _p_f64), _ptr(lls, _p_f64))
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        run(MH_ITERS, _ptr(chain, _p_f64), _ptr(lls, _p_f64))
+    dte = time.perf_counter() - t1
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        tt = torch.tensor([dt, dte], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt, dte = float(tt[0]), float(tt[1])
+    state_th = np.empty((n_chains, 6)); state_ll = np.empty(n_chains); acc = np.zeros(n_chains, dtype=np.int64); it = C.c_int64()
+    _check(lib.gcdyn_mh_state(h, _ptr(state_th, _p_f64), _ptr(state_ll, _p_f64), _ptr(acc, _p_i64), C.byref(it)), ctx._h)
+    lib.gcdyn_mh_destroy(h)
+    if rank != 0:
+        dist.barrier(); dist.destroy_process_group()
+        return
+    # parity beside the number: the sampler's own log-likelihood of four chains' final states against the oracle (all shards)
+    chk = [0, n_chains // 3, 2 * n_chains // 3, n_chains - 1]
+    models = [model_of(state_th[cix], base) for cix in chk]
+    par = workloads.par_dict(models)
+    rel = 0.0
+    tot = np.zeros(len(chk))
+    for r in range(world):
+        fr = flat if r == 0 else workloads.flat_forest("C4", r * Tn, Tn)
+        for j in range(len(chk)):
+            tot[j] += float(oracle.loglik_flat_shared(fr, par, j, T).sum())
+    rel = float(np.max(np.abs(state_ll[chk] - tot) / np.abs(tot)))
+    assert rel <= 1e-8, rel
+    n_it = args.steps * MH_ITERS
+    ms_step = 1e3 * dt / args.steps
+    value = world * Tn * n_chains * n_it / dt
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": config_dict("C4", Tn, n_chains, world, {
+                "step": f"{MH_ITERS} Metropolis iterations of {n_chains} chains (one gcdyn_mh_run call, CUDA graphs of 16 fused iterations)",
+                "ms_per_iteration": ms_step / MH_ITERS, "iterations_per_s": n_it / dt,
+                "acceptance_rate_mean": float(acc.mean() / max(1, it.value)),
+                "timing": "host clock around the synchronising call (the library owns the stream); no L2 flush: a sampler's working "
+                          "set stays in L2 between iterations by design"}),
+            "clocks": clocks,
+            "e2e": {"value": world * Tn * n_chains * n_it / dte, "unit": UNIT, "ms_per_step": 1e3 * dte / args.steps,
+                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": MH_ITERS * n_chains * 7 * 8,
+                    "api": "gcdyn_mh_run with host history buffers (every iteration's parameters and log-likelihoods copied back)"},
+            "gpu_launches": args.steps * MH_ITERS * 2,
+            "roofline": None, "parity": {"chains_checked": len(chk), "max_rel_err_loglik_vs_oracle": rel, "gate": 1e-8}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="gcdyn_b200", choices=["gcdyn_b200", "reference"])
-    ap.add_argument("--trees", type=int, default=1000, help="trees per GPU")
-    ap.add_argument("--psets", type=int, default=256)
+    ap.add_argument("--workload", default="C3", choices=["C3", "C4", "C5"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--trees", type=int, default=None, help="trees per GPU (weak) / in total (strong); default: the workload's")
+    ap.add_argument("--psets", type=int, default=None)
     ap.add_argument("--order", type=int, default=0)
     ap.add_argument("--taylor-steps", type=int, default=0)
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
+    import workloads
+    args.trees = args.trees or workloads.CONFIGS[WORKLOAD]["trees"]
+    args.psets = args.psets or workloads.CONFIGS[WORKLOAD]["psets"]
+    if args.impl != "reference" and WORKLOAD == "C4":
+        return run_mh(args)
     if args.impl == "reference":
         run_reference(args)
     else:

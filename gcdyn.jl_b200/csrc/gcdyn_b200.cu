@@ -73,6 +73,7 @@ struct gcdyn_ctx {
     bool profile = false;
     cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int last_cheb_D = 0;
+    int max_cells = 0;                    // opts.max_cells of the call being enqueued (0 = the table capacity)
     bool last_traj_sharded = false;       // the last evaluation integrated only this rank's slice of the parameter sets
     const int* last_feedback = nullptr;   // pinned feedback words of the forest the last evaluation ran on
     bool gemm_attr_set = false;
@@ -574,6 +575,7 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         cfg.tol = tol;
         cfg.S_fixed = S_fixed;
         cfg.S_cap = S_fixed > 0 ? S_fixed : cap_steps(T, rate_max, M);
+        if (S_fixed <= 0 && ctx->max_cells > 0) cfg.S_cap = std::min(cfg.S_cap, ctx->max_cells);   // the caller's `maxiters`
         const long long L = M + 2;
         cfg.grid_doubles = 2 * cfg.S_cap + 2;
         cfg.tab_stride = cfg.grid_doubles + (long long)cfg.S_cap * K * L;
@@ -1038,6 +1040,7 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
 
     // one pass: every pset adapts its own step count inside traj_kernel (or uses opts->steps as given);
     // a pset that cannot be resolved within the table capacity comes back as a solver failure (-Inf)
+    ctx->max_cells = o.max_cells > 0 ? o.max_cells : 0;
     rc = enqueue_eval(ctx, f, pv, rate_max_of(pr), T, method, M, o.steps, tol, o.flags,
                       pr->gamma_pset_stride == 0 ? pr->Gamma : nullptr, h_out, nullptr,
                       status ? ctx->status.as<int32_t>() : nullptr, st, nullptr, 0.0, comm);
@@ -1260,6 +1263,7 @@ int gcdyn_loglik_batch_resident(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcd
         return fail(ctx, GCDYN_EINVAL, "GCDYN_FLAG_TOTALS produces no per-tree values: d_out_tree_pset and d_status must be NULL");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
+    ctx->max_cells = o.max_cells > 0 ? o.max_cells : 0;
     return enqueue_eval(ctx, f, dp->v, dp->rate_max, present_time, method, M, o.steps, o.tol > 0.0 ? o.tol : 1e-11,
                         o.flags, dp->host_gamma.empty() ? nullptr : dp->host_gamma.data(), d_out_pset, d_out_tree_pset,
                         d_status, st, nullptr);
@@ -1285,6 +1289,7 @@ int gcdyn_loglik_batch_resident_sharded(gcdyn_ctx* ctx, const gcdyn_forest* f, c
         return fail(ctx, GCDYN_EINVAL, "GCDYN_FLAG_TOTALS produces no per-tree values: d_out_tree_pset and d_status must be NULL");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
+    ctx->max_cells = o.max_cells > 0 ? o.max_cells : 0;
     return enqueue_eval(ctx, f, dp->v, dp->rate_max, present_time, method, M, o.steps, o.tol > 0.0 ? o.tol : 1e-11,
                         o.flags, dp->host_gamma.empty() ? nullptr : dp->host_gamma.data(), d_out_pset, d_out_tree_pset,
                         d_status, st, nullptr, 0.0, comm);
@@ -1352,6 +1357,7 @@ int gcdyn_loglik_grad_batch(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_p
     double* d_ll = d_tot + P;
     double* d_grad = d_ll + P;
     int* d_st = reinterpret_cast<int*>(d_grad + (size_t)P * NS);
+    ctx->max_cells = 0;
     rc = enqueue_eval(ctx, f, pv, rate_max_of(pr), T, GCDYN_METHOD_ODE, M, 0, tol, GCDYN_FLAG_TOTALS | FLAG_FORCE_MOMENTS,
                       pr->gamma_pset_stride == 0 ? pr->Gamma : nullptr, d_tot, nullptr, nullptr, st, nullptr);
     if (rc) return rc;
@@ -1883,6 +1889,7 @@ namespace {
 // happened (it cannot when the forest takes the item sweep)
 int mh_loglik(gcdyn_mh* m, double* dst, cudaStream_t st, bool hook = false, bool* fused = nullptr) {
     gcdyn_ctx* ctx = m->ctx;
+    ctx->max_cells = 0;
     int rc = enqueue_eval(ctx, m->forest, m->pv, m->rate_bound, m->T, GCDYN_METHOD_ODE, 16, 0, 1e-11,
                           GCDYN_FLAG_TOTALS | FLAG_FORCE_MOMENTS, m->host_gamma.data(),
                           dst, nullptr, nullptr, st, nullptr, m->rate_typical, m->comm, hook ? &m->v : nullptr, fused);

@@ -72,7 +72,7 @@ class MhDesc(C.Structure):
 
 class Opts(C.Structure):
     _fields_ = [("steps", C.c_int32), ("order", C.c_int32), ("tol", C.c_double), ("flags", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("max_cells", C.c_int32)]
 
 
 _LIB = None
@@ -384,7 +384,7 @@ def evaluate_resident(forest, dparams, present_time, d_out_pset, d_out_tree_pset
     """`gcdyn_loglik_batch_resident`: everything already in HBM; `d_*` are raw device addresses
     (e.g. `tensor.data_ptr()`), `stream` a raw cudaStream_t (e.g. `torch.cuda.current_stream().cuda_stream`).
     Enqueues and returns without synchronising."""
-    op = Opts(steps=int(steps), order=int(order), tol=0.0, flags=int(flags), reserved=0)
+    op = Opts(steps=int(steps), order=int(order), tol=0.0, flags=int(flags), max_cells=0)
     if comm is not None:            # the forest is this rank's shard: d_out_pset receives the sums over all ranks
         _check(_lib().gcdyn_loglik_batch_resident_sharded(
             forest.ctx._h, forest._h, dparams._h, float(present_time if present_time is not None else 0.0),
@@ -399,16 +399,18 @@ def evaluate_resident(forest, dparams, present_time, d_out_pset, d_out_tree_pset
 
 # ----------------------------------------------------------------------------- evaluation
 
-def _opts(reltol=None, abstol=None, steps=0, order=0, flags=0):
+def _opts(reltol=None, abstol=None, steps=0, order=0, flags=0, maxiters=None):
     tol = 0.0
     for t in (reltol, abstol):
         if t is not None and 0 < t < 1e-11:   # we are always at least as tight as requested
             tol = t if tol == 0.0 else min(tol, t)
-    return Opts(steps=int(steps), order=int(order), tol=float(tol), flags=int(flags), reserved=0)
+    # the reference's `maxiters` bounds the solver's steps per solve; here it bounds the adaptive cells per trajectory
+    cap = 0 if maxiters is None or not (maxiters < 2 ** 31 - 1) else max(1, int(maxiters))
+    return Opts(steps=int(steps), order=int(order), tol=float(tol), flags=int(flags), max_cells=cap)
 
 
 def evaluate(forest: Forest, params: PackedParams, present_time, method="ode", *, per_tree=False,
-             want_status=True, reltol=None, abstol=None, steps=0, order=0, flags=0, comm=None):
+             want_status=True, reltol=None, abstol=None, steps=0, order=0, flags=0, comm=None, maxiters=None):
     """One `gcdyn_loglik_batch` call.  Returns (out_pset[P], out_tree_pset[P,T] | None, status[P,T] | None).
     `comm` (a `gcdyn.sharding.PeerAllReduce`): the forest is this rank's shard and `out_pset` is summed over the
     ranks inside the call (`gcdyn_loglik_batch_sharded`)."""
@@ -421,7 +423,7 @@ def evaluate(forest: Forest, params: PackedParams, present_time, method="ode", *
     tp = np.empty((P, T), dtype=np.float64) if per_tree else None
     st = np.zeros((P, T), dtype=np.int32) if (want_status or per_tree) else None
     ps = params.struct()
-    op = _opts(reltol, abstol, steps, order, flags)
+    op = _opts(reltol, abstol, steps, order, flags, maxiters)
     T = float(present_time if present_time is not None else 0.0)
     if comm is not None:
         _check(lib.gcdyn_loglik_batch_sharded(forest.ctx._h, forest._h, C.byref(ps), T, METHOD_CODE[method], C.byref(op),
@@ -503,8 +505,10 @@ def loglikelihood(model, trees, present_time, *, reltol=1e-3, abstol=1e-3, maxit
     `model` may also be a list of models — the batched entry — returning one value per model.
     `trees` may be a `TreeNode`, a list of them, or a `Forest` already resident on the GPU.
     The result is the CONVERGED solution (error indicator ≤ 1e-13), which is at least as accurate
-    as any `reltol`/`abstol` the reference accepts; `maxiters` is accepted and ignored."""
-    return _run("ode", model, trees, present_time, reltol=reltol, abstol=abstol, steps=steps, order=order)
+    as any `reltol`/`abstol` the reference accepts.  `maxiters` caps the adaptive cells of a trajectory (the
+    integrator's counterpart of solver steps): a parameter set that needs more is a solver failure — a warning and
+    `-Inf`, as the reference does when `sol.retcode != :Success` (mbp.jl:154-158)."""
+    return _run("ode", model, trees, present_time, reltol=reltol, abstol=abstol, steps=steps, order=order, maxiters=maxiters)
 
 
 def _alt(method, model, tree, present_time):

@@ -59,7 +59,7 @@ struct GcdynOpts
     order::Int32
     tol::Float64
     flags::Int32
-    reserved::Int32
+    max_cells::Int32      # the reference's `maxiters`: cap on the adaptive cells of a trajectory (0 = none)
 end
 
 # ---- handles -----------------------------------------------------------------------------------------------
@@ -218,7 +218,7 @@ function pack_params(models::Vector{<:AbstractBranchingProcess})
 end
 
 function b200_evaluate(models::Vector{<:AbstractBranchingProcess}, forest::B200Forest, present_time, method::Cint;
-                       per_tree = false, tol = 0.0)
+                       per_tree = false, tol = 0.0, maxiters = 0)
     # the leaves were validated against the forest's own present time (mbp.jl:125-134): another one would extrapolate silently
     if method != GCDYN_METHOD_NAIVE && !isnan(forest.flat.present_time) && Float64(present_time) != forest.flat.present_time
         throw(ArgumentError("Sampled survival events must all be at the present time."))
@@ -231,7 +231,7 @@ function b200_evaluate(models::Vector{<:AbstractBranchingProcess}, forest::B200F
     GC.@preserve pp out rows status begin
         par = GcdynParams(pp.P, pp.K, 0, pp.stride, pointer(pp.lambda), C_NULL, C_NULL, C_NULL, C_NULL, C_NULL,
                           pointer(pp.mu), pointer(pp.delta), pointer(pp.rho), pointer(pp.sigma), pointer(pp.Gamma))
-        opts = GcdynOpts(0, 0, tol, 0, 0)
+        opts = GcdynOpts(0, 0, tol, 0, Int32(clamp(maxiters, 0, typemax(Int32))))
         b200_check(forest.ctx, ccall((:gcdyn_loglik_batch, LIBGCDYN), Cint,
             (Ptr{Cvoid}, Ptr{Cvoid}, Ref{GcdynParams}, Cdouble, Cint, Ref{GcdynOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
             forest.ctx.handle, forest.handle, par, Float64(present_time), method, opts, out,
@@ -250,7 +250,7 @@ function StatsAPI.loglikelihood(model::AbstractBranchingProcess, trees::Vector{T
                                 reltol = 1e-3, abstol = 1e-3, maxiters = 1e5) where T
     forest = B200Forest(flatten(trees, model, present_time))
     tol = min(reltol, abstol) < 1e-11 ? min(reltol, abstol) : 0.0          # the library is never looser than 1e-11
-    return b200_evaluate([model], forest, present_time, GCDYN_METHOD_ODE; tol)[1][1]
+    return b200_evaluate([model], forest, present_time, GCDYN_METHOD_ODE; tol, maxiters = floor(Int, min(maxiters, 2.0^31 - 1)))[1][1]
 end
 
 StatsAPI.loglikelihood(model::AbstractBranchingProcess, tree::TreeNode, present_time; kw...) =
@@ -315,10 +315,13 @@ stadler_appx_unconditioned_loglikelihood(model::AbstractBranchingProcess, tree::
 # ---- multi-GPU: one process per GPU, trees sharded; the [P] sums are combined by the library's peer-memory kernel ----
 
 "`gcdyn_comm_*`: `allgather_handles(handle::Vector{UInt8}) -> Vector{UInt8}` (world × 64 bytes, rank order) is supplied
-by the caller, e.g. `h -> MPI.Allgather(h, comm)`."
+by the caller, e.g. `h -> MPI.Allgather(h, comm)`.  `row_bytes > 0` adds the row window of the trajectory sharding
+(`gcdyn_comm_rows_create/_connect`): sharded evaluations of ≥ 512 parameter sets then integrate only this rank's slice of
+the sets and exchange the coefficient rows over peer memory; `2 * P * (Jst * 8 + 32)` bytes with
+`Jst = 2K + 4 + 129K + K²` covers every grid degree."
 mutable struct B200Comm
     handle::Ptr{Cvoid}
-    function B200Comm(ctx::B200Context, rank::Integer, world::Integer, max_psets::Integer, allgather_handles)
+    function B200Comm(ctx::B200Context, rank::Integer, world::Integer, max_psets::Integer, allgather_handles; row_bytes::Integer = 0)
         mine = Vector{UInt8}(undef, 64)
         out = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:gcdyn_comm_create, LIBGCDYN), Cint, (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{UInt8}, Ref{Ptr{Cvoid}}),
@@ -328,6 +331,15 @@ mutable struct B200Comm
             all = allgather_handles(mine)
             rc = ccall((:gcdyn_comm_connect, LIBGCDYN), Cint, (Ptr{Cvoid}, Ptr{UInt8}), out[], all)
             rc == 0 || error(unsafe_string(ccall((:gcdyn_last_error, LIBGCDYN), Cstring, (Ptr{Cvoid},), ctx.handle)))
+        end
+        if row_bytes > 0
+            rc = ccall((:gcdyn_comm_rows_create, LIBGCDYN), Cint, (Ptr{Cvoid}, Int64, Ptr{UInt8}), out[], row_bytes, mine)
+            rc == 0 || error(unsafe_string(ccall((:gcdyn_last_error, LIBGCDYN), Cstring, (Ptr{Cvoid},), ctx.handle)))
+            if world > 1
+                all = allgather_handles(mine)
+                rc = ccall((:gcdyn_comm_rows_connect, LIBGCDYN), Cint, (Ptr{Cvoid}, Ptr{UInt8}), out[], all)
+                rc == 0 || error(unsafe_string(ccall((:gcdyn_last_error, LIBGCDYN), Cstring, (Ptr{Cvoid},), ctx.handle)))
+            end
         end
         c = new(out[])
         finalizer(x -> ccall((:gcdyn_comm_destroy, LIBGCDYN), Cvoid, (Ptr{Cvoid},), x.handle), c)

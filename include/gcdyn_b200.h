@@ -123,7 +123,9 @@ typedef struct {
     double  tol;     /* accepted size of the last Taylor terms (error indicator); 0 = 1e-11, which
                         keeps the relative error of a log-likelihood below ~1e-12        */
     int32_t flags;   /* GCDYN_FLAG_*                                                                    */
-    int32_t reserved;
+    int32_t max_cells; /* the reference's `maxiters` (mbp.jl:116): a parameter set whose trajectory needs more
+                        adaptive cells than this is a solver failure - status bit 2 and -Inf, where the reference
+                        warns and returns -Inf (mbp.jl:154-158); 0 = bounded by the table capacity only          */
 } gcdyn_opts;
 
 #define GCDYN_FLAG_SWEEP_ONLY 4 /* per-tree sums by the item sweep only (skip the Chebyshev-moment GEMM) */
@@ -189,8 +191,8 @@ int  gcdyn_loglik_grad_batch(gcdyn_ctx* ctx, const gcdyn_forest* forest, const g
 int  gcdyn_last_diag(gcdyn_ctx* ctx, int32_t* steps, int32_t* order, int32_t* n_launches,
                      double* err_indicator, int32_t n_psets);
 /* Taylor cells each of the first n_psets parameter sets of the last ODE evaluation took (host copy; synchronises).
- * The integrator has no counterpart of the reference's `maxiters`: the number of cells is bounded by the table capacity
- * and a parameter set that would exceed it comes back as a solver failure (-Inf), as mbp.jl:154-158 does. */
+ * opts.max_cells (the reference's `maxiters`) caps them; a parameter set that would exceed the cap or the table capacity
+ * comes back as a solver failure (-Inf), as mbp.jl:154-158 does. */
 int  gcdyn_last_cells(gcdyn_ctx* ctx, int32_t* cells, int32_t n_psets);
 
 /* Native forward simulator (host code, OpenMP): draws n_trees trees from the law of the reference's

@@ -206,6 +206,13 @@ def test_public_api_matches_oracle_on_simulated_trees(ctx):
     # single tree method, and reltol/abstol/maxiters keywords are accepted
     one = gcdyn.loglikelihood(model, trees[0], 3.0, reltol=1e-6, abstol=1e-6, maxiters=1e4)
     assert abs(one - oracle.loglikelihood_shared(model, trees[0], 3.0)) <= TREE_RTOL * abs(one)
+    # maxiters caps the adaptive cells of a trajectory; exceeding it is the reference's `@warn` + -Inf (mbp.jl:154-158),
+    # on the item-sweep path (one model) and on the contraction path (a batch) alike
+    with pytest.warns(UserWarning, match="Density will evaluate to zero"):
+        assert gcdyn.loglikelihood(model, trees, 3.0, maxiters=2) == -np.inf
+    with pytest.warns(UserWarning, match="Density will evaluate to zero"):
+        assert np.all(np.isneginf(gcdyn.loglikelihood([model] * 9, trees, 3.0, maxiters=2)))
+    assert abs(gcdyn.loglikelihood(model, trees, 3.0, maxiters=10 ** 5) - want) <= SUM_RTOL * abs(want)
     # batched entry: a list of models gives one value per model
     models = [model, gcdyn.SigmoidalBranchingProcess(1.0, 0.0, 2.0, 0.5, 1.0, 1.0, 0.7, 0.25, ts)]
     got2 = gcdyn.loglikelihood(models, trees, 3.0)

@@ -21,7 +21,10 @@ CONFIGS = {
     "C2": dict(K=10, trees=100, psets=1, T=4.0, seed=2),
     "C3": dict(K=20, trees=1000, psets=256, T=4.0, seed=3),
     "C5s": dict(K=50, trees=200, psets=64, T=4.0, seed=5),   # small stand-in for config 5 (parity tests)
+    # config 5 at scale: 10^4 trees of ~10^3 nodes from the NATIVE simulator (gcdyn_sim_forest), kept when 500 <= nodes <= 2000
+    "C5": dict(K=50, trees=10000, psets=1024, T=5.0, seed=5, native=True),
 }
+CONFIGS["C4"] = dict(CONFIGS["C3"], psets=64)               # config 4: 64 Metropolis chains on the config-3 forest
 
 
 def base_model(name):
@@ -38,6 +41,7 @@ def jittered_models(name, n_psets=None):
     Normal(0, 0.2) on xshift; Γ shared, ρ and σ fixed."""
     c = CONFIGS[name]
     P = n_psets or c["psets"]
+    name = "C3" if name == "C4" else name
     base, _ = base_model(name)
     if P == 1 or name == "C1":
         return [base]
@@ -64,6 +68,20 @@ def trees(name, first=0, count=None):
 
 
 def flat_forest(name, first=0, count=None):
+    c = CONFIGS[name]
+    if c.get("native"):
+        # one simulator stream per shard: shard index = first // count (strong scaling: the shards differ with N; the
+        # workload is the distribution, not one fixed forest — a 10^7-node forest from the host simulator would take hours)
+        from gcdyn.sharding import subset_flat
+        count = c["trees"] if count is None else count
+        model, init = base_model(name)
+        pool = gcdyn.simulate_flat(model, c["T"], init, 6 * count, seed=c["seed"] + 1000 * (first // max(count, 1)))
+        sizes = np.diff(pool.tree_off)
+        ok = np.nonzero((sizes >= 500) & (sizes <= 2000))[0][:count]
+        if len(ok) < count:
+            raise RuntimeError(f"simulator produced only {len(ok)} trees of 500..2000 nodes out of {6 * count}")
+        return subset_flat(pool, ok)
+    name = "C3" if name == "C4" else name
     model, _ = base_model(name)
     return gcdyn.flatten(trees(name, first, count), model.type_space, CONFIGS[name]["T"])
 
