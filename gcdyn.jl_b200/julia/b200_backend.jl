@@ -54,12 +54,13 @@ struct GcdynParams
     Gamma::Ptr{Float64}
 end
 
+# max_cells: the reference's `maxiters` — cap on the adaptive cells of a trajectory (0 = none)
 struct GcdynOpts
     steps::Int32
     order::Int32
     tol::Float64
     flags::Int32
-    max_cells::Int32      # the reference's `maxiters`: cap on the adaptive cells of a trajectory (0 = none)
+    max_cells::Int32
 end
 
 # ---- handles -----------------------------------------------------------------------------------------------
