@@ -1290,9 +1290,16 @@ int gcdyn_loglik_batch_resident_sharded(gcdyn_ctx* ctx, const gcdyn_forest* f, c
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? reinterpret_cast<cudaStream_t>(stream) : ctx->stream;
     ctx->max_cells = o.max_cells > 0 ? o.max_cells : 0;
-    return enqueue_eval(ctx, f, dp->v, dp->rate_max, present_time, method, M, o.steps, o.tol > 0.0 ? o.tol : 1e-11,
-                        o.flags, dp->host_gamma.empty() ? nullptr : dp->host_gamma.data(), d_out_pset, d_out_tree_pset,
-                        d_status, st, nullptr, 0.0, comm);
+    const int rc = enqueue_eval(ctx, f, dp->v, dp->rate_max, present_time, method, M, o.steps, o.tol > 0.0 ? o.tol : 1e-11,
+                                o.flags, dp->host_gamma.empty() ? nullptr : dp->host_gamma.data(), d_out_pset, d_out_tree_pset,
+                                d_status, st, nullptr, 0.0, comm);
+    if (rc) {                                              // release the peers: NaN contribution instead of a missing one
+        const std::string why = ctx->err;
+        cudaGetLastError();
+        comm_poison(comm, dp->v.P, st);
+        return fail(ctx, rc, why);
+    }
+    return GCDYN_OK;
     GUARD_END(ctx)
 }
 

@@ -13,6 +13,13 @@
  *     and never retained; opaque handles own device memory;
  *   - the library calls cudaSetDevice itself, installs no signal handlers, and a
  *     gcdyn_ctx may be used from any host thread (one call at a time per ctx);
+ *   - STREAMS: a ctx, a forest handle and a communicator own scratch memory that is reused
+ *     from call to call (table, coefficient rows, partial sums, flags; the forest's moments
+ *     and calibrated grid degree).  Calls that share any of these handles must be issued on
+ *     ONE stream - the ctx's own, or the one passed to the *_resident entry points - or be
+ *     separated by a synchronisation of that stream; results of an unsynchronised resident
+ *     call are ordered on its stream like any kernel's.  A forest caches its moments for one
+ *     present_time: alternating present times on one handle is correct but rebuilds them;
  *   - there is NO CPU fallback: without a CUDA device every compute call fails with
  *     GCDYN_ENODEVICE.
  *   - "density evaluates to zero" cases of the reference (`@warn` + `return -Inf`,
