@@ -1,4 +1,5 @@
-"""Phase timing of traj_kernel (clock64 stamps per pset, dumped through gcdyn_trace_dump).  Needs the trace build:
+"""(c_wait: per cell that waits for a ring slot, i.e. cells 7.., c_wait0: loop back-edge of the first six cells.)
+Phase timing of traj_kernel (clock64 stamps per pset, dumped through gcdyn_trace_dump).  Needs the trace build:
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fopenmp -shared -lgomp \
        -DGCDYN_TRAJ_TRACE -o tools/_trace/libgcdyn_trace.so gcdyn.jl_b200/csrc/gcdyn_b200.cu
   GCDYN_B200_LIB=tools/_trace/libgcdyn_trace.so python tools/trace_probe.py
@@ -27,12 +28,12 @@ for p in range(P):
     rows.append(dict(p=p, sm=int(r[16]), S=int(r[18]), start_ns=int(r[14] - g0), end_ns=int(r[15] - g0), setup=int(r[2] - r[0]),
                      integ=int(r[3] - r[2]), per_cell=int((r[3] - r[2]) / max(1, r[18])), cons_after=int(r[6] - r[3]),
                      sync=int(r[4] - max(r[3], r[6])), finish=int(r[5] - r[4]), total=int(r[5] - r[0]),
-                     c_wait=int(r[7] / max(1, r[18])), c_stage=int(r[8] / max(1, r[18])), c_epi=int(r[9] / max(1, r[18]))))
+                     c_wait=int(r[7] / max(1, r[18] - 6)), c_wait0=int(r[10] / min(6, max(1, r[18]))), c_stage=int(r[8] / max(1, r[18])), c_epi=int(r[9] / max(1, r[18]))))
 rows.sort(key=lambda r: -r["end_ns"])
 print("kernel span ns:", rows[0]["end_ns"], " start spread ns:", max(r["start_ns"] for r in rows))
 for r in rows[:6] + rows[-3:]:
     print(r)
-for key in ("setup", "integ", "per_cell", "cons_after", "sync", "finish", "total", "S", "c_wait", "c_stage", "c_epi"):
+for key in ("setup", "integ", "per_cell", "cons_after", "sync", "finish", "total", "S", "c_wait", "c_wait0", "c_stage", "c_epi"):
     v = np.array([r[key] for r in rows]); print(f"{key:10s} mean {v.mean():9.0f} min {v.min():8d} max {v.max():8d}")
 print("cheb", ctx.last_cheb(), "diag", {k: v for k, v in ctx.last_diag(4).items() if k != "err_indicator"})
 import collections
