@@ -295,8 +295,19 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    # N > 1: the ranks' 75 us flush kernels differ by a few us, and a step that contains a rendezvous (the fused all-reduce)
+    # would charge that difference to the path.  One peer barrier (the library's one-CTA all-reduce on a dummy double) after
+    # the flush and BEFORE the start event lets every rank's timed step begin together; what remains inside the timed
+    # region is the skew of the path's own kernels.  (--no-align restores the old behaviour.)
+    align = torch.zeros(1, dtype=torch.float64, device="cuda") if (peer is not None and not args.no_align) else None
+
+    def flush_and_align():
         flush.zero_()
+        if align is not None:
+            peer.allreduce(align.data_ptr(), 1, stream.cuda_stream)
+
+    for _ in range(max(args.warmup, 3)):
+        flush_and_align()
         step_resident()
     barrier()
     diag = ctx.last_diag(P)
@@ -308,7 +319,7 @@ def run_gpu(args):
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
     for i in range(args.steps):
-        flush.zero_()
+        flush_and_align()
         starts[i].record(stream)
         step_resident()
         ends[i].record(stream)
@@ -336,7 +347,7 @@ def run_gpu(args):
     barrier()
     e2e_s = 0.0
     for i in range(args.steps):
-        flush.zero_()
+        flush_and_align()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         o, _, _ = evaluate(forest, params, T, steps=args.taylor_steps, order=args.order, want_status=False, comm=peer)
@@ -357,6 +368,22 @@ def run_gpu(args):
                   " (host buffers; forest handle created once per dataset, as a sampler would)"}
     if world > 1:
         assert np.allclose(o, result, rtol=1e-12, atol=0)
+    # every rank's own step WITHOUT the rendezvous (same kernels, no peer traffic): the sharded step cannot be faster than the
+    # slowest of these, whatever the collective costs — the GPUs of one box differ by several per cent
+    per_rank_ms = None
+    if world > 1:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for a, b in evs:
+            flush.zero_()
+            a.record(stream)
+            evaluate_resident(forest, dpar, T, out.data_ptr(), out_tree.data_ptr(), 0, stream.cuda_stream,
+                              steps=args.taylor_steps, order=args.order)
+            b.record(stream)
+        torch.cuda.synchronize()
+        mine_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / len(evs)], dtype=torch.float64, device="cuda")
+        allms = [torch.zeros_like(mine_ms) for _ in range(world)]
+        dist.all_gather(allms, mine_ms)
+        per_rank_ms = [float(x.item()) for x in allms]
     # the fused all-reduce against a library collective over the ranks' own per-tree values
     allreduce_check = None
     traj_sharded = False
@@ -477,7 +504,9 @@ def run_gpu(args):
             "config": config_dict(WORKLOAD, Tn, P, world, {
                 "nodes_per_gpu": info["n_nodes"], "lookup_items_per_gpu": n_items, "taylor_steps": S,
                 "taylor_order": M, "max_err_indicator": float(np.max(diag["err_indicator"])),
-                "allreduce": allreduce_kind, "trajectories_sharded": traj_sharded}),
+                "allreduce": allreduce_kind, "trajectories_sharded": traj_sharded,
+                "per_rank_step_ms_without_rendezvous": per_rank_ms,
+                "aligned_start": "peer barrier between the L2 flush and each timed step (outside the timed region)" if align is not None else None}),
             "clocks": clocks, "e2e": e2e, "cold": cold,
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "parity": parity}
@@ -605,6 +634,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--trees", type=int, default=None, help="trees per GPU (weak) / in total (strong); default: the workload's")
     ap.add_argument("--psets", type=int, default=None)
+    ap.add_argument("--no-align", action="store_true", help="N > 1: no peer barrier between the L2 flush and the timed step")
     ap.add_argument("--order", type=int, default=0)
     ap.add_argument("--taylor-steps", type=int, default=0)
     args = ap.parse_args()

@@ -520,13 +520,34 @@ __global__ void __launch_bounds__(256) finish_kernel(ForestView fv, ParamsView p
     const uint4* local = pr.win[pr.rank].ll + (size_t)(seq & 1ULL) * pr.world * pr.cap;
     const unsigned long long t0 = global_ns();
     for (int q = threadIdx.x; q < P; q += blockDim.x) {
+        // the entries of (up to) eight ranks are requested together (independent loads), re-polled until every one carries
+        // this call's sequence number, and added in rank order
         double s = 0.0;
-        for (int r = 0; r < pr.world; ++r) {
-            double v;
-            while (!ll_load(local + (size_t)r * pr.cap + q, (unsigned)seq, v)) {
-                if (global_ns() - t0 > fc.timeout_ns) { s_timeout = 1; v = __longlong_as_double(0x7ff8000000000000LL); break; }
+        for (int r0 = 0; r0 < pr.world; r0 += 8) {
+            double v[8];
+            const int nr = min(8, pr.world - r0);
+            const unsigned all = (1u << nr) - 1u;
+            unsigned got = 0u;
+            for (;;) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    if (r < nr && !((got >> r) & 1u)) {
+                        double t;
+                        if (ll_load(local + (size_t)(r0 + r) * pr.cap + q, (unsigned)seq, t)) { v[r] = t; got |= 1u << r; }
+                    }
+                }
+                if (got == all) break;
+                if (global_ns() - t0 > fc.timeout_ns) {
+                    s_timeout = 1;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        if (r < nr && !((got >> r) & 1u)) v[r] = __longlong_as_double(0x7ff8000000000000LL);
+                    break;
+                }
             }
-            s += v;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < nr) s += v[r];
         }
         out_pset[q] = s;
         if (mh_on && !s_timeout) mh_accept_chain(mh, mh_it, q);

@@ -68,8 +68,13 @@ for _ in range(3):
 sync_all()
 steps = 10
 ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+# (N > 1: a peer barrier between the flush and the timed step, so that the ranks' flush kernels do not skew the step; C5_NO_ALIGN=1 = off)
+align = torch.zeros(1, dtype=torch.float64, device="cuda") if (peer is not None and not os.environ.get("C5_NO_ALIGN")) else None
 for a, b in ev:
-    flush.zero_(); a.record(stream); step(); b.record(stream)
+    flush.zero_()
+    if align is not None:
+        peer.allreduce(align.data_ptr(), 1, stream.cuda_stream)
+    a.record(stream); step(); b.record(stream)
 sync_all()
 ms = sum(a.elapsed_time(b) for a, b in ev) / steps
 if world > 1:                                   # device time of the slowest rank
@@ -118,7 +123,7 @@ if rank == 0:
   print(json.dumps({"config": f"C5: {Tn} trees per GPU ({flat.n_nodes} nodes, {forest.info()['n_items']} items), K={K}, P={P}, T={T}, "
                             f"{world} GPU(s), {mode} scaling, {Tn * world} trees in total",
                   "sim_seconds": t_sim, "ms_per_step": ms, "tree_pset_evals_per_s": Tn * world * P / (ms * 1e-3),
-                  "trajectory_sharded": traj_sharded, "kernel_ms_sharded_step": acc_sh or None,
+                  "trajectory_sharded": traj_sharded, "aligned_start": align is not None, "kernel_ms_sharded_step": acc_sh or None,
                   "kernel_ms": acc, "chebyshev": cheb, "taylor_cells_max": diag["steps"],
                   "gemm": {"J": J, "gflop": gemm_flop / 1e9, "tflops": gemm_flop / (acc["gemm"] * 1e-3) / 1e12,
                            "frac_of_measured_dfma_peak": gemm_flop / (acc["gemm"] * 1e-3) / 1e12 / peak, "dfma_peak_tflops": peak},
