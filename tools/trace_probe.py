@@ -14,7 +14,7 @@ params = pack_params(models); ctx = gcdyn.Context(0); forest = gcdyn.Forest(flat
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for _ in range(5):
     if not os.environ.get("NOFLUSH"): flush.zero_()
-    evaluate(forest, params, 4.0, want_status=False)
+    evaluate(forest, params, 4.0, want_status=False, order=int(os.environ.get("ORDER", "0")))
     torch.cuda.synchronize()
 lib = _lib()
 lib.gcdyn_trace_dump.argtypes = [C.POINTER(C.c_longlong)]
