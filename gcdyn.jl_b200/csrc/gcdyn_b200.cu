@@ -315,7 +315,8 @@ size_t traj_smem_bytes(int K, int D, int M) {
     size_t n = 2 * KSB + (K <= 64 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
     const size_t KS = ((size_t)K + 1) & ~(size_t)1;
     if (D > 0) n += 2 * (size_t)D + (((size_t)D + 3) & ~(size_t)1) + ((((size_t)D + 1) * K + 1) & ~(size_t)1) + 24 * (size_t)K;
-    n += (size_t)RING_SLOTS * 4 + (size_t)RING_SLOTS * (M + 1) * KS;
+    const size_t slots = K <= 64 ? RING_SLOTS : RING_SLOTS_WIDE;      // ring_slots(KPL): the K > 64 layout keeps two cells in flight
+    n += slots * 4 + slots * (M + 1) * KS;
     if (D > 0) n += 2 * (size_t)K * (M + 2);
     return n * sizeof(double);
 }
@@ -416,6 +417,11 @@ int degree_ladder_ceil(int d) {
 // a batch is in that state — the parameters have moved to another regime — does finish_kernel report back through a
 // pinned word, and the next call takes the next rung.
 size_t fit_degree_smem(int K, int D) { return (2 * (size_t)D + ((size_t)D + 1) * K) * 8 + 1024; }
+// The nodal stage needs node values, cosine table and check scratch next to the ring: for the widest layouts it does not fit
+// at any degree, and the evaluation takes the exact item sweep (which needs none of it).
+bool nodal_stage_fits(int K, int M, int smem_optin) {
+    return traj_smem_bytes(K, 8, M) + 1024 <= (size_t)smem_optin && fit_degree_smem(K, 8) <= (size_t)smem_optin;
+}
 int clamp_degree(int D, int K, int M, int smem_optin) {
     while (D > 8 && (traj_smem_bytes(K, D, M) + 1024 > (size_t)smem_optin || fit_degree_smem(K, D) > (size_t)smem_optin)) D -= 2;
     return D;
@@ -583,7 +589,9 @@ int enqueue_eval(gcdyn_ctx* ctx, const gcdyn_forest* f, const ParamsView& pv, do
         CU_TRY(ctx, ctx->table.ensure(tab_bytes));
         // ---- per-tree sums: Chebyshev-moment GEMM (DMMA), with the item sweep as exact fallback.  The Chebyshev
         //      stage (node values = coefficient row, resolution check, fallback flag) runs inside traj_kernel.
-        bool use_gemm = !(flags & GCDYN_FLAG_SWEEP_ONLY) && Tn > 0 && !f->mom_refused &&
+        if (traj_smem_bytes(K, 0, M) + 1024 > (size_t)ctx->smem_optin)
+            return fail(ctx, GCDYN_EUNSUPPORTED, "this many types at this Taylor order do not fit the trajectory kernel's shared memory");
+        bool use_gemm = !(flags & GCDYN_FLAG_SWEEP_ONLY) && Tn > 0 && !f->mom_refused && nodal_stage_fits(K, M, ctx->smem_optin) &&
                         (P >= 8 || (f->mom.Mt && f->mom_T == T) || (flags & FLAG_FORCE_MOMENTS));
         const int* only_flagged = nullptr;
         ChebCfg cc{};

@@ -357,6 +357,9 @@ __device__ long long g_trace_out[1024 * 24];
 #ifndef GCDYN_RING_SLOTS
 #define GCDYN_RING_SLOTS 6
 #endif
+// (the K > 64 layout keeps δΓ — K² doubles — in shared memory as well: two cells in flight there, or K = 128 would not fit)
+constexpr int RING_SLOTS_WIDE = 2;
+__host__ __device__ constexpr int ring_slots(int KPL) { return KPL == 1 ? GCDYN_RING_SLOTS : RING_SLOTS_WIDE; }
 constexpr int RING_SLOTS = GCDYN_RING_SLOTS;                 // cells in flight between the integrating warp(s) and the consumer warps
 constexpr int CELL_LAST = 1, CELL_FAIL = 2;   // flags of a published cell
 
@@ -394,15 +397,15 @@ struct TrajSmem {                      // carve-up of the kernel's dynamic share
     double* ring;                      // [RING_SLOTS][(M+1)*KS]  A_n[x], n-major (conflict-free for lanes = types)
     double* rowbuf;                    // [2][K*L] table rows of the cell being evaluated at the Chebyshev nodes
     int KS;
-    __device__ TrajSmem(double* sm, int K, int D, int M) {
+    __device__ TrajSmem(double* sm, int K, int D, int M, int slots) {
         KS = (K + 1) & ~1;
         costab = sm;
         tauk = costab + 2 * D;
         V = tauk + (D > 0 ? ((D + 3) & ~1) : 0);
         chk = V + (D > 0 ? ((((size_t)(D + 1) * K) + 1) & ~(size_t)1) : 0);
         meta = chk + (D > 0 ? 24 * (size_t)K : 0);
-        ring = meta + RING_SLOTS * 4;
-        rowbuf = ring + (size_t)RING_SLOTS * (M + 1) * KS;
+        ring = meta + slots * 4;
+        rowbuf = ring + (size_t)slots * (M + 1) * KS;
     }
 };
 
@@ -451,7 +454,7 @@ __device__ __forceinline__ void early_count_columns(const ParamsView& pv, const 
 // The warps that do not integrate (ct = 0..nct-1).  Node k of the Chebyshev grid sits at τ_k = T(1 + cos(πk/D))/2, so
 // cells (increasing τ) meet the nodes in decreasing k; a node belongs to the largest cell with τ_s ≤ τ_k (find_cell's
 // rule), the last cell takes the rest.
-template <int M>
+template <int M, int SLOTS>
 __device__ __forceinline__ void cell_consume(const ParamsView& pv, const TrajCfg& tc, const ChebCfg& cfg, bool cheb, int p,
                                              double* __restrict__ tab, const TrajSmem& ts, uint64_t* full, uint64_t* empty,
                                              int ct, int nct, const PsetPack& pk, int* s_flag) {
@@ -485,8 +488,8 @@ __device__ __forceinline__ void cell_consume(const ParamsView& pv, const TrajCfg
     double* Anod = cheb ? cfg.A + (size_t)p * cfg.mv.Jst + cfg.mv.C1 : nullptr;
     int kn = D;
     for (int sc = 0;; ++sc) {
-        const int slot_i = sc % RING_SLOTS;
-        mbar_wait_warp(full + slot_i, (uint32_t)(sc / RING_SLOTS) & 1u);
+        const int slot_i = sc % SLOTS;
+        mbar_wait_warp(full + slot_i, (uint32_t)(sc / SLOTS) & 1u);
         const double* meta = ts.meta + slot_i * 4;
         const int flag = (int)meta[3];
         if (flag & CELL_FAIL) {
@@ -658,7 +661,8 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
     const bool cheb = cc.D > 0;                         // CTA-uniform
     const int KSB = KPL == 1 ? KP : ((K + 3) & ~3);     // broadcast buffer length (multiple of 4)
     const size_t traj_doubles = 2 * (size_t)KSB + (KPL == 1 ? 0 : (((size_t)K * K + 1) & ~(size_t)1));
-    const TrajSmem ts(smem + traj_doubles, K, cheb ? cc.D : 0, M);
+    constexpr int SLOTS = ring_slots(KPL);              // cells in flight between the integrating and the consumer warps
+    const TrajSmem ts(smem + traj_doubles, K, cheb ? cc.D : 0, M, SLOTS);
     // The integrating warp is chosen from the hardware warp slots so that CTAs sharing an SM integrate on different
     // sub-partitions (two integrations on one FP64 pipe: +32 % per Taylor stage, tools/traj_micro.cu).  Slot groups
     // of four are the usual allocation for a 4-warp CTA; any other allocation only loses the benefit.
@@ -673,7 +677,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
         s_flag = 0;
         if (blockIdx.x == 0 && cheb) *cc.nflag = 0;
 #pragma unroll
-        for (int i = 0; i < RING_SLOTS; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, NCONS); }
+        for (int i = 0; i < SLOTS; ++i) { mbar_init(s_full + i, 1); mbar_init(s_empty + i, NCONS); }
     }
     // fused Metropolis iteration: six threads draw the six coordinates of chain p's proposal and write its parameters,
     // which everybody reads behind the barrier
@@ -726,7 +730,7 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
     if (prod_rank < 0) {
         const int ct = cons_rank * 32 + lane;
         prep_pset(pv, pk, p, 0, ct, NCONS, false, !(cheb && cc.compact_tc));
-        cell_consume<M>(pv, cfg, cc, cheb, p, tab, ts, s_full, s_empty, ct, NCONS, pk, &s_flag);
+        cell_consume<M, SLOTS>(pv, cfg, cc, cheb, p, tab, ts, s_full, s_empty, ct, NCONS, pk, &s_flag);
 #ifdef GCDYN_TRAJ_TRACE
         if (ct == 0) g_trace[6] = clock64();
 #endif
@@ -832,9 +836,9 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
 #define TRACE_ACC(v) do { } while (0)
 #endif
     for (;;) {
-        const int slot_i = s % RING_SLOTS;
+        const int slot_i = s % SLOTS;
         if (s >= cfg.S_cap) { failed = true; break; }
-        if (s >= RING_SLOTS) mbar_wait(s_empty + slot_i, (uint32_t)(s / RING_SLOTS - 1) & 1u);   // consumers left it
+        if (s >= SLOTS) mbar_wait(s_empty + slot_i, (uint32_t)(s / SLOTS - 1) & 1u);   // consumers left it
         TRACE_ACC(tr_wait);
         double* slot = ts.ring + (size_t)slot_i * (M + 1) * ts.KS;
         double A[KPL][M + 1];
@@ -993,8 +997,8 @@ __global__ void __launch_bounds__(TRAJ_THREADS, 2) traj_kernel(ParamsView pv, Ps
     if (lane == 0) { g_trace[7] = tr_wait; g_trace[8] = tr_stage; g_trace[9] = tr_epi; }
 #endif
     if (failed) {                                       // tell the consumers to stop (the regular exit flagged its last cell)
-        const int slot_i = s % RING_SLOTS;
-        if (s >= RING_SLOTS) mbar_wait(s_empty + slot_i, (uint32_t)(s / RING_SLOTS - 1) & 1u);
+        const int slot_i = s % SLOTS;
+        if (s >= SLOTS) mbar_wait(s_empty + slot_i, (uint32_t)(s / SLOTS - 1) & 1u);
         if (pt == 0) { ts.meta[slot_i * 4 + 3] = (double)CELL_FAIL; }
         prod_sync();
         if (pt == 0) mbar_arrive(s_full + slot_i);

@@ -315,11 +315,13 @@ def test_many_types_uses_multi_type_lanes(ctx):
     assert abs(got - want) <= SUM_RTOL * abs(want)
 
 
-@pytest.mark.parametrize("K,order", [(33, 16), (48, 8), (64, 24), (65, 16), (32, 20)])
+@pytest.mark.parametrize("K,order", [(33, 16), (48, 8), (64, 24), (65, 16), (32, 20), (96, 16), (128, 16), (128, 24)])
 def test_type_count_boundaries_of_the_trajectory_kernel(ctx, K, order):
     """The kernel switches layout at K = 32 (one warp) / 33..64 (two integrating warps, register rows of width 40, 48,
     56, 64) / 65.. (types strided over lanes, δΓ in shared memory).  Each side of every boundary: batch of 9 psets
-    through the GEMM path == the item sweep, one pset == the oracle, a failed pset does not stall the others."""
+    through the GEMM path == the item sweep, one pset == the oracle, a failed pset does not stall the others.
+    K = 128 = GCDYN_MAX_TYPES: the widest layout keeps two cells in flight so that δΓ (K² doubles) still fits beside the ring;
+    the nodal stage does not fit there and the batch takes the exact sweep."""
     import oracle
     rng = np.random.default_rng(100 + K)
     ts = np.linspace(-2, 2, K)
