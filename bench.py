@@ -452,7 +452,9 @@ def run_gpu(args):
         traffic = tr.get(f"{dom}_kernel", {}).get("dram_bytes_per_launch")
     except Exception:
         tr = {}
-    roofline = {"kernel": f"{dom}_kernel", "bound": "fp64", "achieved": achieved, "peak": fp64_peak,
+    # "tensor": the contraction runs on the FP64 tensor pipe (DMMA); "fp64": the trajectory kernel's DFMA chain — both are
+    # measured against the same live FP64 FMA peak (B200's DMMA and DFMA rates are equal)
+    roofline = {"kernel": f"{dom}_kernel", "bound": "tensor" if dom == "gemm" else "fp64", "achieved": achieved, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 "peak_source": "measured live: register-resident DFMA loop on all SMs (gcdyn_probe_fp64_peak); "
                                "MEASURED_PEAKS.json has no FP64 figure",
