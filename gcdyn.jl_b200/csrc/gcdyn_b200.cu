@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -66,6 +67,11 @@ struct gcdyn_ctx {
     // workspace (grow-only)
     DevBuf params_blob, pack, table, out_tree, out_pset, status, probe, gemm_a, flags, partial, grad_out;
     PinBuf pin_in, pin_out;
+    // host-buffer calls: the shared Γ last uploaded into params_blob (and the blob's size), so that later calls with the same Γ
+    // need no host→device copy at all — the per-pset scalars are then read by the kernels straight from pinned host memory
+    std::vector<double> blob_gamma;
+    size_t blob_doubles = 0;
+    int params_mapped = 0;                // $GCDYN_PARAMS_MAPPED: 1 = read per-pset parameters from pinned host memory
     // diagnostics of the last evaluation
     int last_steps = 0, last_order = 0, last_launches = 0, last_P = 0;
     PsetPack last_pack{};
@@ -1012,6 +1018,12 @@ int forest_create_impl(gcdyn_ctx* ctx, const gcdyn_forest_desc* d, gcdyn_forest*
 int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, double T, int method,
                const gcdyn_opts* opts, double* out_pset, double* out_tree_pset, int32_t* status, gcdyn_comm* comm = nullptr) {
     if (!ctx || !f || !out_pset) return fail(ctx, GCDYN_EINVAL, "NULL argument");
+    // $GCDYN_E2E_TRACE: host-side timeline of the call (microseconds between the stamps), averaged over 10 calls, on stderr
+    static const bool e2e_trace = std::getenv("GCDYN_E2E_TRACE") != nullptr;
+    static double e2e_acc[5] = {0, 0, 0, 0, 0};
+    static int e2e_n = 0;
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double ts0 = e2e_trace ? now() : 0.0;
     int rc = check_params(ctx, pr);
     if (rc) return rc;
     if (method < 0 || method > 3) return fail(ctx, GCDYN_EINVAL, "unknown method");
@@ -1034,8 +1046,25 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
     CU_TRY(ctx, ctx->pin_in.ensure(L.n_doubles * 8));
     pack_host(pr, L, reinterpret_cast<double*>(ctx->pin_in.p));
     CU_TRY(ctx, ctx->params_blob.ensure(L.n_doubles * 8));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->params_blob.p, ctx->pin_in.p, L.n_doubles * 8, cudaMemcpyHostToDevice, st));
-    const ParamsView pv = view_of(pr, L, ctx->params_blob.as<double>());
+    const double ts1 = e2e_trace ? now() : 0.0;
+    ParamsView pv = view_of(pr, L, ctx->params_blob.as<double>());
+    {
+        const size_t kk = (size_t)pr->n_types * pr->n_types;
+        const bool same_gamma = ctx->params_mapped && pr->gamma_pset_stride == 0 && ctx->blob_doubles == L.n_doubles &&
+                                ctx->blob_gamma.size() == kk && std::memcmp(ctx->blob_gamma.data(), pr->Gamma, kk * 8) == 0;
+        if (same_gamma) {
+            // no copy node: the kernels read this call's per-pset parameters over PCIe from the pinned staging buffer
+            // (a few hundred bytes per CTA); Γ — K² doubles that EVERY CTA reads — stays in the device blob
+            const double* gamma_dev = pv.Gamma;
+            pv = view_of(pr, L, reinterpret_cast<const double*>(ctx->pin_in.p));
+            pv.Gamma = gamma_dev;
+        } else {
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->params_blob.p, ctx->pin_in.p, L.n_doubles * 8, cudaMemcpyHostToDevice, st));
+            if (pr->gamma_pset_stride == 0) { ctx->blob_gamma.assign(pr->Gamma, pr->Gamma + kk); ctx->blob_doubles = L.n_doubles; }
+            else { ctx->blob_gamma.clear(); ctx->blob_doubles = 0; }
+        }
+    }
+    const double ts2 = e2e_trace ? now() : 0.0;
 
     const bool want_rows = out_tree_pset || status;
     if ((o.flags & GCDYN_FLAG_TOTALS) && want_rows) return fail(ctx, GCDYN_EINVAL, "GCDYN_FLAG_TOTALS produces no per-tree values: out_tree_pset and status must be NULL");
@@ -1068,8 +1097,20 @@ int batch_impl(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_params* pr, do
         if (status)
             CU_TRY(ctx, cudaMemcpyAsync(status, ctx->status.p, (size_t)P * Tn * 4, cudaMemcpyDeviceToHost, st));
     }
+    const double ts3 = e2e_trace ? now() : 0.0;
     CU_TRY(ctx, cudaStreamSynchronize(st));
+    const double ts4 = e2e_trace ? now() : 0.0;
     std::memcpy(out_pset, h_out, (size_t)P * 8);
+    if (e2e_trace) {
+        const double ts5 = now();
+        e2e_acc[0] += ts1 - ts0; e2e_acc[1] += ts2 - ts1; e2e_acc[2] += ts3 - ts2; e2e_acc[3] += ts4 - ts3; e2e_acc[4] += ts5 - ts4;
+        if (++e2e_n == 10) {
+            std::fprintf(stderr, "[gcdyn e2e] validate+pack %.1f | H2D enqueue %.1f | enqueue kernels %.1f | synchronize %.1f | copy out %.1f us\n",
+                         e2e_acc[0] / 10, e2e_acc[1] / 10, e2e_acc[2] / 10, e2e_acc[3] / 10, e2e_acc[4] / 10);
+            e2e_n = 0;
+            for (double& a : e2e_acc) a = 0.0;
+        }
+    }
     if (comm && comm->h_err && *comm->h_err) {
         const int why = *comm->h_err;
         *comm->h_err = 0;
@@ -1152,6 +1193,7 @@ int gcdyn_ctx_create(int device, gcdyn_ctx** out) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (const char* ev = std::getenv("GCDYN_PARAMS_MAPPED")) ctx->params_mapped = std::atoi(ev);
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(none, GCDYN_ECUDA, cudaGetErrorString(e)); }
     *out = ctx;
@@ -1366,6 +1408,7 @@ int gcdyn_loglik_grad_batch(gcdyn_ctx* ctx, const gcdyn_forest* f, const gcdyn_p
     pack_host(pr, L, reinterpret_cast<double*>(ctx->pin_in.p));
     CU_TRY(ctx, ctx->params_blob.ensure(L.n_doubles * 8));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->params_blob.p, ctx->pin_in.p, L.n_doubles * 8, cudaMemcpyHostToDevice, st));
+    ctx->blob_doubles = 0;                                 // (the blob no longer holds what gcdyn_loglik_batch cached there)
     const ParamsView pv = view_of(pr, L, ctx->params_blob.as<double>());
     CU_TRY(ctx, ctx->grad_out.ensure(((size_t)P * (NS + 2)) * 8 + (size_t)P * 4));
     double* d_tot = ctx->grad_out.as<double>();

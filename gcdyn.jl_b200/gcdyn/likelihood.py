@@ -158,6 +158,9 @@ def _ptr(a, typ):
     return a.ctypes.data_as(typ) if a is not None else typ()
 
 
+_NULL_F64, _NULL_I32 = _p_f64(), _p_i32()
+
+
 def _check(code, ctx_handle=None):
     if code == 0:
         return
@@ -290,15 +293,20 @@ class PackedParams:
 
     _FIELDS = ("lam", "xscale", "xshift", "yscale", "yshift", "type_space", "mu", "delta", "rho", "sigma", "Gamma")
 
+    def __setattr__(self, name, value):
+        # attaching another array (or changing a size) invalidates the cached struct; contents may change freely
+        d = self.__dict__
+        d[name] = value
+        d["_struct_cache"] = None
+
     def struct(self):
         """The `gcdyn_params` view of the arrays.  Building the ctypes pointers costs more than a small evaluation
-        takes on the GPU, so the struct is cached for as long as the SAME array objects are attached (the cache
-        keeps them alive, so an identity check is enough; their contents may change freely)."""
+        takes on the GPU, so the struct is cached until an attribute is assigned (`__setattr__`); the cache keeps the
+        arrays it points at alive, and their contents may change freely."""
+        st = self.__dict__.get("_struct_cache")
+        if st is not None:
+            return st[1]
         arrays = tuple(getattr(self, f) for f in self._FIELDS)
-        scalars = (self.n_psets, self.n_types, self.response, self.gamma_pset_stride)
-        cache = self.__dict__.get("_struct_cache")
-        if cache is not None and cache[1] == scalars and all(a is b for a, b in zip(cache[0], arrays)):
-            return cache[2]
         st = Params(
             n_psets=self.n_psets, n_types=self.n_types, response=self.response,
             gamma_pset_stride=self.gamma_pset_stride,
@@ -306,7 +314,7 @@ class PackedParams:
             yscale=_ptr(self.yscale, _p_f64), yshift=_ptr(self.yshift, _p_f64),
             type_space=_ptr(self.type_space, _p_f64), mu=_ptr(self.mu, _p_f64), delta=_ptr(self.delta, _p_f64),
             rho=_ptr(self.rho, _p_f64), sigma=_ptr(self.sigma, _p_f64), Gamma=_ptr(self.Gamma, _p_f64))
-        self.__dict__["_struct_cache"] = (arrays, scalars, st)
+        self.__dict__["_struct_cache"] = (arrays, st)
         return st
 
 
@@ -429,8 +437,11 @@ def evaluate(forest: Forest, params: PackedParams, present_time, method="ode", *
         _check(lib.gcdyn_loglik_batch_sharded(forest.ctx._h, forest._h, C.byref(ps), T, METHOD_CODE[method], C.byref(op),
                                               comm._h, _ptr(out, _p_f64), _ptr(tp, _p_f64), _ptr(st, _p_i32)), forest.ctx._h)
     else:
-        _check(lib.gcdyn_loglik_batch(forest.ctx._h, forest._h, C.byref(ps), T, METHOD_CODE[method], C.byref(op),
-                                      _ptr(out, _p_f64), _ptr(tp, _p_f64), _ptr(st, _p_i32)), forest.ctx._h)
+        rc = lib.gcdyn_loglik_batch(forest.ctx._h, forest._h, C.byref(ps), T, METHOD_CODE[method], C.byref(op),
+                                    out.ctypes.data_as(_p_f64), _NULL_F64 if tp is None else tp.ctypes.data_as(_p_f64),
+                                    _NULL_I32 if st is None else st.ctypes.data_as(_p_i32))
+        if rc:
+            _check(rc, forest.ctx._h)
     return out, tp, st
 
 
