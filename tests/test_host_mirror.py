@@ -200,3 +200,35 @@ def test_sharding_partition_is_balanced_and_complete():
             for k in ("tree_off", "event", "type_idx", "btype_idx", "t_start", "t_end", "parent", "child_off",
                       "child_idx", "root_type_idx", "root_time"):
                 assert np.array_equal(getattr(s, k), getattr(ref, k)), k
+
+
+def test_maxiters_maps_onto_the_cell_cap():
+    """`maxiters` of the reference's solver call (mbp.jl:116) becomes `gcdyn_opts.max_cells`; the default 1e5 and anything
+    that does not fit an int32 mean "no cap beyond the table capacity"."""
+    from gcdyn.likelihood import _opts
+    assert _opts(maxiters=None).max_cells == 0
+    assert _opts(maxiters=7).max_cells == 7
+    assert _opts(maxiters=1e5).max_cells == 100000
+    assert _opts(maxiters=0.5).max_cells == 1
+    assert _opts(maxiters=float("inf")).max_cells == 0 and _opts(maxiters=1e12).max_cells == 0
+    # tolerances looser than the library's own are not forwarded, tighter ones are
+    assert _opts(reltol=1e-3, abstol=1e-3).tol == 0.0 and _opts(reltol=1e-12, abstol=1e-3).tol == 1e-12
+
+
+def test_packed_params_struct_is_cached_until_an_array_is_replaced():
+    import numpy as np
+    import gcdyn
+    from gcdyn.likelihood import pack_params
+    ts = np.linspace(-1.0, 1.0, 4)
+    models = [gcdyn.SigmoidalBranchingProcess(1.0, 0.0, 2.0 + 0.1 * i, 0.5, 1.0, 1.0, 0.5, 0.2, ts) for i in range(3)]
+    ps = pack_params(models)
+    a = ps.struct()
+    assert ps.struct() is a                                   # same arrays attached: same struct, no pointer rebuilding
+    ps.mu[1] = 3.0                                            # contents may change freely
+    assert ps.struct() is a and a.mu[1] == 3.0
+    old_mu = ps.mu
+    ps.mu = ps.mu.copy()                                      # another array: the struct must point at it
+    b = ps.struct()
+    assert b is not a
+    ps.mu[0] = 9.0
+    assert b.mu[0] == 9.0 and old_mu[0] != 9.0
