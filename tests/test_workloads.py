@@ -48,3 +48,19 @@ def test_bench_command_line():
     assert out.returncode == 0
     for flag in ("--gpus", "--steps", "--warmup", "--impl", "--workload", "--scaling"):
         assert flag in out.stdout
+
+
+def test_reference_arm_prints_one_line_in_the_bench_schema():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): one JSON line, same metric/unit/config keys,
+    `impl: reference`, a `cpu_baseline` that describes the run and an `e2e` that repeats the line's own value."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--trees", "64", "--psets", "4"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "tree_loglik_evals_per_sec" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["vs_baseline"] is None and d["gpu_launches"] == 0 and "workload" in d["config"]
