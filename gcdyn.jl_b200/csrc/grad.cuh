@@ -93,7 +93,6 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) traj_grad_kernel(ParamsView p
     for (int j = 0; j < KP; ++j) g[j] = (own && j < K) ? delta * g[j] : 0.0;
     const double a = lam + mu, b = mu * (1.0 - sigma);
     const double gam = own ? delta * -gdiag : 0.0;
-    const double Lam = lam + mu + gam;
     double rate = own ? fabs(lam) + fabs(mu) + 2.0 * fabs(gam) : 0.0;
     rate = warp_max_nan(rate);
     // this warp's vector
